@@ -1,0 +1,250 @@
+/* mobgs_b200 — C ABI of the B200-native MoBGS render + deblur hot path.
+ *
+ * Plain C, no torch / CUDA types in any signature: device pointers are `void*`-compatible
+ * raw pointers, the stream is an opaque `void*` (a cudaStream_t), every struct is POD.
+ *
+ * What this replaces in the reference (KAIST-VICLab/MoBGS @ 0a1e0d3).  The reference is pure
+ * Python; its only native boundary on this path is the gsplat==1.4.0 pip extension
+ * (README.md:26) reached from gaussian_renderer/__init__.py:15.  Each entry point cites the
+ * reference interface it stands in for; INTEGRATION.md shows the Python-side binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MOBGS_E* code; the message is
+ *     available (thread-local) from mobgs_last_error().  Nothing throws or exits.
+ *   - the library never allocates or frees device memory and keeps no global state; all
+ *     inputs, outputs and workspaces are caller-owned device buffers of the stated extent.
+ *   - all kernels are launched on the passed stream and never synchronise the host.
+ *   - fp32 everywhere, row-major, contiguous unless a stride is stated.
+ *   - "K" = number of cameras / latent sub-frames of one launch (gsplat's C; MoBGS num_warp).
+ *   - packed record = 16 floats per (sub-frame, Gaussian):
+ *       [0]=mean2d.x [1]=mean2d.y [2]=opacity [3..5]=conic a,b,c [6..15]=up to 10 colour channels
+ *     gradients use the same 16-float layout.
+ */
+#ifndef MOBGS_B200_H_
+#define MOBGS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOBGS_OK 0
+#define MOBGS_EINVAL (-1)   /* bad argument */
+#define MOBGS_ECUDA (-2)    /* CUDA launch / runtime error */
+#define MOBGS_ECAPACITY (-3) /* caller-provided workspace too small */
+
+#define MOBGS_REC_FLOATS 16
+#define MOBGS_MAX_COLORS 10
+#define MOBGS_TILE 16
+#define MOBGS_MAX_CTRL 12   /* GaussianModel.control_num, scene/gaussian_model.py:111 */
+
+const char* mobgs_version(void);
+const char* mobgs_last_error(void);
+
+/* Cameras of one launch.  viewmats: [K,4,4] world->camera; Ks: [K,3,3] pinhole intrinsics.
+ * Constants are gsplat.rendering.rasterization defaults (eps2d=0.3, near=0.01, far=1e10,
+ * radius_clip=0) unless the caller overrides them. */
+typedef struct {
+  int32_t K;
+  int32_t width, height;
+  const float* viewmats;
+  const float* Ks;
+  float eps2d, near_plane, far_plane, radius_clip;
+} MobgsCameras;
+
+/* ------------------------------------------------------------------------------------------
+ * gsplat.rendering.fully_fused_projection(means, covars=None, quats, scales, viewmats, Ks,
+ * width, height)  — explicit call sites gaussian_renderer/__init__.py:190,411,422,513,524 and
+ * the projection inside every rasterization() call.
+ * Outputs (any may be NULL): radii i32[K,N], means2d[K,N,2], depths[K,N], conics[K,N,3].
+ * Culled Gaussians get radii=0 and zeros. */
+typedef struct {
+  MobgsCameras cams;
+  int32_t N;
+  const float* means;   /* [N,3] */
+  const float* quats;   /* [N,4] wxyz, normalised inside */
+  const float* scales;  /* [N,3] */
+  int32_t* radii;
+  float* means2d;
+  float* depths;
+  float* conics;
+} MobgsProjectFwd;
+int mobgs_project_fwd(const MobgsProjectFwd* a, void* stream);
+
+/* VJP of the above (gsplat fully_fused_projection_bwd).  Gradient inputs are addressed with an
+ * element stride (in floats) per Gaussian so that views into a packed 16-float gradient record
+ * can be consumed without a copy; the stride between sub-frames is N * stride.  v_* inputs may be
+ * NULL (treated as zero).  Outputs v_means/v_quats/v_scales are *written* (sum over the K
+ * cameras); v_viewmats [K,4,4] is *accumulated* with atomics and must be zeroed by the caller
+ * (NULL = not needed). */
+typedef struct {
+  MobgsCameras cams;
+  int32_t N;
+  const float* means;
+  const float* quats;
+  const float* scales;
+  const int32_t* radii;        /* [K,N] from the forward */
+  const float* v_means2d; int32_t v_means2d_stride;   /* 2 floats per Gaussian */
+  const float* v_depths;  int32_t v_depths_stride;    /* 1 float  */
+  const float* v_conics;  int32_t v_conics_stride;    /* 3 floats */
+  float* v_means;   /* [N,3] */
+  float* v_quats;   /* [N,4] */
+  float* v_scales;  /* [N,3] */
+  float* v_viewmats;
+} MobgsProjectBwd;
+int mobgs_project_bwd(const MobgsProjectBwd* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused MoBGS attribute synthesis + projection for K latent sub-frames (SURVEY.md §8 a1+a2+a4):
+ *   static set  : GaussianModel getters scene/gaussian_model.py:209-257 (xyz, exp(scaling),
+ *                 normalize(rotation), sigmoid(opacity), [f_dc | 0*f_t])
+ *   dynamic set : interpolate_cubic_hermite gaussian_renderer/__init__.py:23-56 (x 1e-2),
+ *                 get_rotation_dy (rotation + dt*omega), get_features(dt) = [f_dc | dt*f_t],
+ *                 dt = t_poly[k] - trbf_center (detached)
+ * Gaussian index g: [0,Ns) static, [Ns,Ns+Nd) dynamic — the torch.cat order of render():181-185.
+ * Writes the packed record (colour channels 0..8 = features, channel 9 = camera depth: the
+ * "RGB+ED" layout), radii and depths; optionally the world-space means [K,N,3]. */
+typedef struct {
+  int32_t Ns;
+  const float* xyz;         /* [Ns,3] */
+  const float* rotation;    /* [Ns,4] */
+  const float* scaling;     /* [Ns,3] log-scale */
+  const float* opacity;     /* [Ns]   logit */
+  const float* features_dc; /* [Ns,6] */
+} MobgsStaticParams;
+
+typedef struct {
+  int32_t Nd;
+  int32_t n_ctrl_max;            /* control_xyz.shape[1] (12) */
+  const float* control_xyz;      /* [Nd,n_ctrl_max,3], units 100x world */
+  const int64_t* control_num;    /* [Nd] current_control_num (int64, as load_ply produces) */
+  const float* rotation;         /* [Nd,4] */
+  const float* omega;            /* [Nd,4] */
+  const float* scaling;          /* [Nd,3] */
+  const float* opacity;          /* [Nd] */
+  const float* features_dc;      /* [Nd,6] */
+  const float* features_t;       /* [Nd,3] */
+  const float* trbf_center;      /* [Nd] */
+  const float* offset;           /* [Nd,3] optional `coherent` offset added to the means, or NULL */
+} MobgsDynamicParams;
+
+typedef struct {
+  MobgsCameras cams;
+  MobgsStaticParams st;
+  MobgsDynamicParams dy;
+  const float* t_spline;   /* [K] device: spline time per sub-frame (already clamped where the reference clamps) */
+  const float* t_poly;     /* [K] device: time used for dt = t - trbf_center */
+  float* records;          /* [K,N,16] */
+  int32_t* radii;          /* [K,N] */
+  float* depths;           /* [K,N] */
+  float* means3d;          /* [K,N,3] or NULL */
+} MobgsSynthFwd;
+int mobgs_synth_project_fwd(const MobgsSynthFwd* a, void* stream);
+
+/* VJP: consumes the packed gradient records [K,N,16] written by mobgs_blend_bwd and writes the
+ * parameter gradients (each written exactly once, summed over K; control_xyz gradient buffer
+ * must be zeroed by the caller).  v_viewmats accumulated atomically (zeroed by caller) or NULL. */
+typedef struct {
+  MobgsCameras cams;
+  MobgsStaticParams st;
+  MobgsDynamicParams dy;
+  const float* t_spline;
+  const float* t_poly;
+  const int32_t* radii;     /* [K,N] */
+  const float* v_records;   /* [K,N,16] */
+  float* v_xyz; float* v_rotation_s; float* v_scaling_s; float* v_opacity_s; float* v_features_dc_s;
+  float* v_control_xyz; float* v_rotation_d; float* v_omega; float* v_scaling_d; float* v_opacity_d;
+  float* v_features_dc_d; float* v_features_t; float* v_offset;
+  float* v_viewmats;
+} MobgsSynthBwd;
+int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pack gsplat-style SoA tensors into records for the blend kernels (the colour concat of
+ * rasterization(render_mode="RGB+ED") is folded in: if depths != NULL it becomes channel D). */
+typedef struct {
+  int32_t K, N, D;            /* D colour channels in `colors` (<= 10, or <= 9 with depths) */
+  const float* means2d;       /* [K,N,2] */
+  const float* conics;        /* [K,N,3] */
+  const float* opacities;     /* [N] (broadcast over K, like opacities.repeat(C,1)) */
+  const float* colors;        /* [N,D] (colors_per_cam=0) or [K,N,D] (colors_per_cam=1) */
+  int32_t colors_per_cam;
+  const float* depths;        /* [K,N] or NULL */
+  float* records;             /* [K,N,16] */
+} MobgsPack;
+int mobgs_pack_records(const MobgsPack* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tile binning + per-tile depth sort (gsplat isect_tiles + radix sort + isect_offset_encode,
+ * inside every rasterization()).  Tile lists are per (sub-frame, tile), sorted by
+ * (depth, Gaussian index) ascending — the order gsplat's stable 64-bit sort produces.
+ *
+ * Step 1 counts intersections per tile and writes the exclusive prefix sum
+ * tile_offsets[K*T+1] (T = tiles_x*tiles_y); the caller reads tile_offsets[K*T] (= I) to size
+ * the lists (or provides a capacity it knows is enough).  Step 2 emits and sorts.
+ * tight != 0 additionally drops (tile, Gaussian) pairs that provably reach alpha < 1/255 on
+ * every pixel centre of the tile (results are unchanged; only the list shrinks). */
+typedef struct {
+  int32_t K, N, width, height;
+  const float* records;      /* [K,N,16] */
+  const int32_t* radii;      /* [K,N] */
+  int32_t tight;
+  int32_t* tile_counts;      /* [K*T] workspace, overwritten */
+  int32_t* tile_offsets;     /* [K*T+1] out */
+} MobgsTileCount;
+int mobgs_tile_count(const MobgsTileCount* a, void* stream);
+
+typedef struct {
+  int32_t K, N, width, height;
+  const float* records;
+  const int32_t* radii;
+  const float* depths;       /* [K,N] sort key */
+  int32_t tight;
+  const int32_t* tile_offsets; /* [K*T+1] from step 1 */
+  int32_t* tile_cursor;      /* [K*T] workspace (zeroed inside) */
+  int64_t capacity;          /* entries available in keys/keys_tmp/sorted_ids */
+  uint64_t* keys;            /* [capacity] workspace */
+  uint64_t* keys_tmp;        /* [capacity] workspace */
+  int32_t* sorted_ids;       /* [capacity] out: Gaussian index per list entry */
+} MobgsTileSort;
+int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Front-to-back alpha compositing (gsplat rasterize_to_pixels fwd), D colour channels:
+ *   alpha = min(0.999, o * exp(-sigma)); skipped if sigma < 0 or alpha < 1/255; stops *before*
+ *   blending once T(1-alpha) <= 1e-4; out = sum c alpha T + T_final * background.
+ * out_colors [K,H,W,D], out_alphas [K,H,W], last_idx [K,H,W] (list position of the last blended
+ * entry, needed by the backward). */
+typedef struct {
+  int32_t K, N, D, width, height;
+  const float* records;
+  const int32_t* tile_offsets;
+  const int32_t* sorted_ids;
+  const float* backgrounds;   /* [K,D] or NULL */
+  float* out_colors;
+  float* out_alphas;
+  int32_t* last_idx;
+} MobgsBlendFwd;
+int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
+
+/* Back-to-front VJP (gsplat rasterize_to_pixels bwd).  v_records [K,N,16] is accumulated with
+ * vector atomics and must be zeroed by the caller. */
+typedef struct {
+  int32_t K, N, D, width, height;
+  const float* records;
+  const int32_t* tile_offsets;
+  const int32_t* sorted_ids;
+  const float* backgrounds;
+  const float* out_alphas;
+  const int32_t* last_idx;
+  const float* v_out_colors;  /* [K,H,W,D] */
+  const float* v_out_alphas;  /* [K,H,W] or NULL */
+  float* v_records;
+} MobgsBlendBwd;
+int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBGS_B200_H_ */

@@ -1,0 +1,201 @@
+"""ctypes binding of libmobgs_b200.so (include/mobgs_b200.h) + the in-tree nvcc build.
+
+The library is the product: there is no Python/torch fallback.  If the shared object is missing
+or a symbol cannot be resolved, importing callers get a RuntimeError — nothing silently routes
+around the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "render_fused.cu", "hexplane_mlp.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
+]
+
+MAX_K = 32
+REC = 16
+MAX_COLORS = 10
+TILE = 16
+
+c_f32p = C.POINTER(C.c_float)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u64p = C.POINTER(C.c_uint64)
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu under mobgs_b200/csrc into libmobgs_b200.so for sm_100a (cross-compiles
+    without a GPU).  Rebuilds only when a source / header is newer than the library."""
+    srcs = _sources()
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(_ROOT, "include", "mobgs_b200.h"))
+    if not force and os.path.exists(LIB_PATH):
+        t = os.path.getmtime(LIB_PATH)
+        if all(os.path.getmtime(d) <= t for d in deps):
+            return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class Cameras(C.Structure):
+    _fields_ = [("K", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("viewmats", C.c_void_p), ("Ks", C.c_void_p),
+                ("eps2d", C.c_float), ("near_plane", C.c_float), ("far_plane", C.c_float),
+                ("radius_clip", C.c_float)]
+
+
+class ProjectFwd(C.Structure):
+    _fields_ = [("cams", Cameras), ("N", C.c_int32), ("means", C.c_void_p), ("quats", C.c_void_p),
+                ("scales", C.c_void_p), ("radii", C.c_void_p), ("means2d", C.c_void_p),
+                ("depths", C.c_void_p), ("conics", C.c_void_p)]
+
+
+class ProjectBwd(C.Structure):
+    _fields_ = [("cams", Cameras), ("N", C.c_int32), ("means", C.c_void_p), ("quats", C.c_void_p),
+                ("scales", C.c_void_p), ("radii", C.c_void_p),
+                ("v_means2d", C.c_void_p), ("v_means2d_stride", C.c_int32),
+                ("v_depths", C.c_void_p), ("v_depths_stride", C.c_int32),
+                ("v_conics", C.c_void_p), ("v_conics_stride", C.c_int32),
+                ("v_means", C.c_void_p), ("v_quats", C.c_void_p), ("v_scales", C.c_void_p),
+                ("v_viewmats", C.c_void_p)]
+
+
+class StaticParams(C.Structure):
+    _fields_ = [("Ns", C.c_int32), ("xyz", C.c_void_p), ("rotation", C.c_void_p),
+                ("scaling", C.c_void_p), ("opacity", C.c_void_p), ("features_dc", C.c_void_p)]
+
+
+class DynamicParams(C.Structure):
+    _fields_ = [("Nd", C.c_int32), ("n_ctrl_max", C.c_int32), ("control_xyz", C.c_void_p),
+                ("control_num", C.c_void_p), ("rotation", C.c_void_p), ("omega", C.c_void_p),
+                ("scaling", C.c_void_p), ("opacity", C.c_void_p), ("features_dc", C.c_void_p),
+                ("features_t", C.c_void_p), ("trbf_center", C.c_void_p), ("offset", C.c_void_p)]
+
+
+class SynthFwd(C.Structure):
+    _fields_ = [("cams", Cameras), ("st", StaticParams), ("dy", DynamicParams),
+                ("t_spline", C.c_void_p), ("t_poly", C.c_void_p), ("records", C.c_void_p),
+                ("radii", C.c_void_p), ("depths", C.c_void_p), ("means3d", C.c_void_p)]
+
+
+class SynthBwd(C.Structure):
+    _fields_ = [("cams", Cameras), ("st", StaticParams), ("dy", DynamicParams),
+                ("t_spline", C.c_void_p), ("t_poly", C.c_void_p), ("radii", C.c_void_p),
+                ("v_records", C.c_void_p),
+                ("v_xyz", C.c_void_p), ("v_rotation_s", C.c_void_p), ("v_scaling_s", C.c_void_p),
+                ("v_opacity_s", C.c_void_p), ("v_features_dc_s", C.c_void_p),
+                ("v_control_xyz", C.c_void_p), ("v_rotation_d", C.c_void_p), ("v_omega", C.c_void_p),
+                ("v_scaling_d", C.c_void_p), ("v_opacity_d", C.c_void_p),
+                ("v_features_dc_d", C.c_void_p), ("v_features_t", C.c_void_p),
+                ("v_offset", C.c_void_p), ("v_viewmats", C.c_void_p)]
+
+
+class Pack(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("means2d", C.c_void_p),
+                ("conics", C.c_void_p), ("opacities", C.c_void_p), ("colors", C.c_void_p),
+                ("colors_per_cam", C.c_int32), ("depths", C.c_void_p), ("records", C.c_void_p)]
+
+
+class TileCount(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("records", C.c_void_p), ("radii", C.c_void_p), ("tight", C.c_int32),
+                ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p)]
+
+
+class TileSort(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("records", C.c_void_p), ("radii", C.c_void_p), ("depths", C.c_void_p),
+                ("tight", C.c_int32), ("tile_offsets", C.c_void_p), ("tile_cursor", C.c_void_p),
+                ("capacity", C.c_int64), ("keys", C.c_void_p), ("keys_tmp", C.c_void_p),
+                ("sorted_ids", C.c_void_p)]
+
+
+class BlendFwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_colors", C.c_void_p),
+                ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p)]
+
+
+class BlendBwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
+                ("height", C.c_int32), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_alphas", C.c_void_p),
+                ("last_idx", C.c_void_p), ("v_out_colors", C.c_void_p), ("v_out_alphas", C.c_void_p),
+                ("v_records", C.c_void_p)]
+
+
+# name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
+# function declared in include/mobgs_b200.h appears here and resolves in the .so.
+ENTRY_POINTS = {
+    "mobgs_version": None,
+    "mobgs_last_error": None,
+    "mobgs_project_fwd": ProjectFwd,
+    "mobgs_project_bwd": ProjectBwd,
+    "mobgs_synth_project_fwd": SynthFwd,
+    "mobgs_synth_project_bwd": SynthBwd,
+    "mobgs_pack_records": Pack,
+    "mobgs_tile_count": TileCount,
+    "mobgs_tile_emit_sort": TileSort,
+    "mobgs_blend_fwd": BlendFwd,
+    "mobgs_blend_bwd": BlendBwd,
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def register_entry_point(name, struct):
+    ENTRY_POINTS[name] = struct
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library (building it first if the toolchain is here and it is stale)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                build()
+            except Exception as e:  # noqa: BLE001
+                raise RuntimeError(
+                    f"mobgs_b200: {LIB_PATH} is missing and could not be built ({e}). "
+                    "Run `python -c 'import __graft_entry__ as g; g.build()'`. There is no fallback path."
+                ) from e
+        lib = C.CDLL(LIB_PATH)
+        for name, struct in ENTRY_POINTS.items():
+            fn = getattr(lib, name)   # AttributeError => symbol missing: fail loudly
+            if struct is None:
+                fn.restype = C.c_char_p
+                fn.argtypes = []
+            else:
+                fn.restype = C.c_int
+                fn.argtypes = [C.POINTER(struct), C.c_void_p]
+        _lib = lib
+        return lib
+
+
+def call(name: str, args: C.Structure, stream: int) -> None:
+    lib = load()
+    rc = getattr(lib, name)(C.byref(args), C.c_void_p(stream))
+    if rc != 0:
+        msg = lib.mobgs_last_error().decode()
+        raise RuntimeError(f"{name} failed (code {rc}): {msg}")

@@ -1,0 +1,289 @@
+// K3': tile binning + per-tile (depth, index) radix sort.
+//
+// gsplat builds one global list of (tile | depth) 64-bit keys and runs a device-wide radix sort
+// over all intersections (4-6 passes over 12 B/entry through HBM).  Here the tile id never enters
+// the key: a counting pass + prefix sum gives every (sub-frame, tile) its own segment, entries
+// are scattered into their segment, and one CTA sorts each segment on the 64-bit key
+// (depth_bits << 32 | gaussian_index) — in shared memory when the segment fits, ping-ponging
+// through L2-resident global buffers when it does not.  Digits on which all keys of a segment
+// agree are skipped, so a typical segment takes 5-7 byte passes that never leave the SM.
+// The resulting order — ascending depth, ties by ascending Gaussian index — is exactly what
+// gsplat's stable sort of (tile, depth) keys emitted in Gaussian order produces.
+#include "common.cuh"
+
+namespace mobgs {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortSmemCap = 4096;   // keys per segment sorted entirely in shared memory
+
+struct TileRect { int x0, y0, x1, y1; };
+
+__device__ __forceinline__ TileRect tile_rect(float mx, float my, int radius, int tiles_x, int tiles_y) {
+  // gsplat isect_tiles: tile_min inclusive, tile_max exclusive, float->uint casts saturate at 0
+  const float tr = (float)radius / kTile, tx = mx / kTile, ty = my / kTile;
+  TileRect r;
+  r.x0 = min(max(0, (int)floorf(tx - tr)), tiles_x);
+  r.y0 = min(max(0, (int)floorf(ty - tr)), tiles_y);
+  r.x1 = min(max(0, (int)ceilf(tx + tr)), tiles_x);
+  r.y1 = min(max(0, (int)ceilf(ty + tr)), tiles_y);
+  return r;
+}
+
+// Smallest sigma = 0.5(a dx^2 + c dy^2) + b dx dy over the rectangle of pixel centres of a tile.
+__device__ __forceinline__ float min_sigma_rect(float mx, float my, float a, float b, float c,
+                                                float xlo, float xhi, float ylo, float yhi) {
+  const float dxl = xlo - mx, dxh = xhi - mx, dyl = ylo - my, dyh = yhi - my;
+  if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return 0.f;
+  float best = 3.4e38f;
+  // vertical edges: dx fixed, minimise over dy in [dyl, dyh]
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float dx = e ? dxh : dxl;
+    const float dy = fminf(dyh, fmaxf(dyl, -b * dx / c));
+    best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const float dy = e ? dyh : dyl;
+    const float dx = fminf(dxh, fmaxf(dxl, -b * dy / a));
+    best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
+  }
+  return best;
+}
+
+struct GaussGeom { float mx, my, opac, ca, cb, cc; };
+
+__device__ __forceinline__ GaussGeom load_geom(const float* rec) {
+  const float4 r0 = *reinterpret_cast<const float4*>(rec);
+  const float2 r1 = *reinterpret_cast<const float2*>(rec + 4);
+  return {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y};
+}
+
+// Visits every tile the reference would list for this Gaussian (optionally minus the provably
+// empty ones) and calls f(tile_index).
+template <typename F>
+__device__ __forceinline__ void for_each_tile(const GaussGeom& g, int radius, int width, int height,
+                                              int tiles_x, int tiles_y, int tight, F f) {
+  const TileRect r = tile_rect(g.mx, g.my, radius, tiles_x, tiles_y);
+  float tau = 0.f;
+  if (tight) {
+    // a pixel contributes iff opac * exp(-sigma) >= 1/255  <=>  sigma <= log(255 opac)
+    tau = __logf(255.f * g.opac) + 0.01f;   // +0.01: safety margin for fp rounding
+    if (!(tau >= 0.f)) return;
+  }
+  for (int ty = r.y0; ty < r.y1; ++ty)
+    for (int tx = r.x0; tx < r.x1; ++tx) {
+      if (tight) {
+        const float xlo = tx * kTile + 0.5f, ylo = ty * kTile + 0.5f;
+        const float xhi = fminf((float)(tx * kTile + kTile), (float)width) - 0.5f;
+        const float yhi = fminf((float)(ty * kTile + kTile), (float)height) - 0.5f;
+        if (min_sigma_rect(g.mx, g.my, g.ca, g.cb, g.cc, xlo, xhi, ylo, yhi) > tau) continue;
+      }
+      f(ty * tiles_x + tx);
+    }
+}
+
+__global__ void __launch_bounds__(256) tile_count_kernel(MobgsTileCount a, int tiles_x, int tiles_y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)a.K * a.N) return;
+  const int radius = a.radii[i];
+  if (radius <= 0) return;
+  const int k = (int)(i / a.N);
+  const GaussGeom g = load_geom(a.records + i * kRecFloats);
+  int* counts = a.tile_counts + (size_t)k * tiles_x * tiles_y;
+  for_each_tile(g, radius, a.width, a.height, tiles_x, tiles_y, a.tight,
+                [&](int tile) { atomicAdd(counts + tile, 1); });
+}
+
+// exclusive prefix sum over n ints by a single CTA; out[n] = total.
+__global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) warp_tot[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_tot[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      warp_tot[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    const int prev_warps = warp ? warp_tot[warp - 1] : 0;
+    const int c = carry;
+    if (i < n) out[i] = c + prev_warps + s - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = c + prev_warps + s;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(256) tile_emit_kernel(MobgsTileSort a, int tiles_x, int tiles_y) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)a.K * a.N) return;
+  const int radius = a.radii[i];
+  if (radius <= 0) return;
+  const int k = (int)(i / a.N);
+  const int gid = (int)(i - (size_t)k * a.N);
+  const GaussGeom g = load_geom(a.records + i * kRecFloats);
+  const size_t tbase = (size_t)k * tiles_x * tiles_y;
+  const uint64_t key = ((uint64_t)__float_as_uint(a.depths[i]) << 32) | (uint32_t)gid;
+  for_each_tile(g, radius, a.width, a.height, tiles_x, tiles_y, a.tight, [&](int tile) {
+    const int slot = a.tile_offsets[tbase + tile] + atomicAdd(a.tile_cursor + tbase + tile, 1);
+    if ((int64_t)slot < a.capacity) a.keys[slot] = key;
+  });
+}
+
+// ------------------------------------------------------------------------------------------
+// one CTA sorts one (sub-frame, tile) segment
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void radix_pass(const uint64_t* src, uint64_t* dst, int n, int shift,
+                                           int (*warp_hist)[256], int* digit_base) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int chunk = (((n + kSortWarps - 1) / kSortWarps) + 31) & ~31;
+  const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
+  int* hist = warp_hist[warp];
+  for (int d = lane; d < 256; d += 32) hist[d] = 0;
+  __syncwarp();
+  for (int i = beg; i < end; i += 32) {
+    const int idx = i + lane;
+    const bool valid = idx < end;
+    const int digit = valid ? (int)((src[idx] >> shift) & 0xff) : 256;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    if (valid && lane == (__ffs(peers) - 1)) hist[digit] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  {
+    // thread d owns digit d: exclusive scan over warps, then over digits
+    const int d = threadIdx.x;
+    int tot = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) { const int c = warp_hist[w][d]; warp_hist[w][d] = tot; tot += c; }
+    int s = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    if (lane == 31) digit_base[warp] = s;
+    __syncthreads();
+    int prev = 0;
+    for (int w = 0; w < warp; ++w) prev += digit_base[w];
+    const int base = prev + s - tot;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) warp_hist[w][d] += base;
+  }
+  __syncthreads();
+  for (int i = beg; i < end; i += 32) {
+    const int idx = i + lane;
+    const bool valid = idx < end;
+    uint64_t key = 0;
+    int digit = 256;
+    if (valid) { key = src[idx]; digit = (int)((key >> shift) & 0xff); }
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    if (valid) {
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      dst[hist[digit] + rank] = key;
+    }
+    __syncwarp();
+    if (valid && lane == (__ffs(peers) - 1)) hist[digit] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bufA = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* bufB = bufA + kSortSmemCap;
+  int (*warp_hist)[256] = reinterpret_cast<int (*)[256]>(bufB + kSortSmemCap);
+  __shared__ int digit_base[kSortWarps];
+  __shared__ unsigned long long red_or[kSortWarps], red_and[kSortWarps];
+
+  const int seg = blockIdx.x;
+  const int beg = a.tile_offsets[seg];
+  int n = a.tile_offsets[seg + 1] - beg;
+  if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
+  if (n <= 0) return;
+  uint64_t* gkeys = a.keys + beg;
+  if (n == 1) {
+    if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(gkeys[0] & 0xffffffffu);
+    return;
+  }
+  const bool in_smem = n <= kSortSmemCap;
+  uint64_t* src = in_smem ? bufA : gkeys;
+  uint64_t* dst = in_smem ? bufB : a.keys_tmp + beg;
+
+  unsigned long long vor = 0ull, vand = ~0ull;
+  for (int i = threadIdx.x; i < n; i += kSortThreads) {
+    const uint64_t key = gkeys[i];
+    if (in_smem) bufA[i] = key;
+    vor |= key; vand &= key;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red_or[threadIdx.x >> 5] = vor; red_and[threadIdx.x >> 5] = vand; }
+  __syncthreads();
+  vor = 0ull; vand = ~0ull;
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) { vor |= red_or[w]; vand &= red_and[w]; }
+  const unsigned long long diff = vor ^ vand;
+
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 8 * pass;
+    if (((diff >> shift) & 0xffull) == 0ull) continue;   // all keys share this digit
+    radix_pass(src, dst, n, shift, warp_hist, digit_base);
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  for (int i = threadIdx.x; i < n; i += kSortThreads) a.sorted_ids[beg + i] = (int)(src[i] & 0xffffffffu);
+}
+
+}  // namespace mobgs
+
+using namespace mobgs;
+
+extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->K >= 1 && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->tile_counts && a->tile_offsets, "NULL workspace");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  const int nt = a->K * tiles_x * tiles_y;
+  cudaMemsetAsync(a->tile_counts, 0, sizeof(int) * (size_t)nt, s);
+  if (a->N > 0) {
+    MOBGS_REQUIRE(a->records && a->radii, "NULL records / radii");
+    const size_t total = (size_t)a->K * a->N;
+    tile_count_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+  }
+  scan_kernel<<<1, 1024, 0, s>>>(a->tile_counts, a->tile_offsets, nt);
+  return check_launch("tile_count");
+}
+
+extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->K >= 1 && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->tile_offsets && a->tile_cursor, "NULL workspace");
+  if (a->N == 0 || a->capacity == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->records && a->radii && a->depths && a->keys && a->keys_tmp && a->sorted_ids, "NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  const int nt = a->K * tiles_x * tiles_y;
+  cudaMemsetAsync(a->tile_cursor, 0, sizeof(int) * (size_t)nt, s);
+  const size_t total = (size_t)a->K * a->N;
+  tile_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+  const size_t smem = 2 * sizeof(uint64_t) * kSortSmemCap + sizeof(int) * kSortWarps * 256;
+  cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tile_sort_kernel<<<nt, kSortThreads, smem, s>>>(*a);
+  return check_launch("tile_emit_sort");
+}

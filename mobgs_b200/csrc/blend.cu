@@ -1,0 +1,277 @@
+// K6'/K7': front-to-back alpha compositing, forward and VJP.
+//
+// One CTA = one 16x16 tile of one sub-frame, one thread = one pixel.  The tile's depth-sorted
+// list is consumed in batches of 256 entries: every thread fetches one packed 64-byte record
+// (4 x LDG.128, L2-resident: the record array is 64 B x N) into shared memory, then all
+// 256 pixels walk the batch with broadcast LDS.128 reads — geometry *and* colours come from
+// shared memory (gsplat re-reads colours from global memory per (pixel, Gaussian) pair and
+// pads D=10 to 16 channels; here the channel count is a template parameter).
+//
+// Backward: per (pixel, Gaussian) gradients are warp-reduced with shuffles, combined across the
+// 8 warps of the CTA in a shared-memory accumulator, and leave the SM as four 16-byte vector
+// reductions (REDG.128) per (tile, Gaussian) — gsplat issues 16 scalar atomics per (warp,
+// Gaussian).
+#include "common.cuh"
+
+namespace mobgs {
+
+constexpr int kBlendThreads = kTilePix;   // 256
+
+struct TileCoord { int k, tile, tx, ty; };
+
+__device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, const float4& r3, int c) {
+  switch (c) {
+    case 0: return r1.z; case 1: return r1.w;
+    case 2: return r2.x; case 3: return r2.y; case 4: return r2.z; case 5: return r2.w;
+    case 6: return r3.x; case 7: return r3.y; case 8: return r3.z; default: return r3.w;
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd a, int tiles_x, int tiles_y) {
+  __shared__ float4 srec[kBlendThreads][4];
+  const int tiles = tiles_x * tiles_y;
+  const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int tid = threadIdx.x;
+  const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
+  const bool inside = ix < a.width && iy < a.height;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const int beg = a.tile_offsets[blockIdx.x], end = a.tile_offsets[blockIdx.x + 1];
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)k * a.N * 4;
+
+  float T = 1.f;
+  float pix[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) pix[c] = 0.f;
+  int last = -1;
+  bool done = !inside;
+
+  for (int b0 = beg; b0 < end; b0 += kBlendThreads) {
+    if (__syncthreads_count(done) == kBlendThreads) break;
+    const int idx = b0 + tid;
+    if (idx < end) {
+      const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
+      srec[tid][0] = __ldg(r); srec[tid][1] = __ldg(r + 1);
+      if (D > 2) srec[tid][2] = __ldg(r + 2);
+      if (D > 6) srec[tid][3] = __ldg(r + 3);
+    }
+    __syncthreads();
+    const int bn = min(kBlendThreads, end - b0);
+    for (int t = 0; t < bn && !done; ++t) {
+      const float4 r0 = srec[t][0], r1 = srec[t][1];
+      const float dx = r0.x - px, dy = r0.y - py;
+      const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+      const float alpha = fminf(kAlphaMax, r0.z * __expf(-sigma));
+      if (sigma < 0.f || alpha < kAlphaMin) continue;
+      const float next_T = T * (1.f - alpha);
+      if (next_T <= kTStop) { done = true; break; }
+      const float w = alpha * T;
+      pix[0] += r1.z * w;
+      if (D > 1) pix[1 % D] += r1.w * w;
+      if (D > 2) {
+        const float4 r2 = srec[t][2];
+        pix[2 % D] += r2.x * w;
+        if (D > 3) pix[3 % D] += r2.y * w;
+        if (D > 4) pix[4 % D] += r2.z * w;
+        if (D > 5) pix[5 % D] += r2.w * w;
+      }
+      if (D > 6) {
+        const float4 r3 = srec[t][3];
+        pix[6 % D] += r3.x * w;
+        if (D > 7) pix[7 % D] += r3.y * w;
+        if (D > 8) pix[8 % D] += r3.z * w;
+        if (D > 9) pix[9 % D] += r3.w * w;
+      }
+      last = b0 + t;
+      T = next_T;
+    }
+  }
+  if (inside) {
+    const size_t p = ((size_t)k * a.height + iy) * a.width + ix;
+    a.out_alphas[p] = 1.f - T;
+    a.last_idx[p] = last;
+    float* oc = a.out_colors + p * D;
+    const float* bg = a.backgrounds ? a.backgrounds + (size_t)k * D : nullptr;
+#pragma unroll
+    for (int c = 0; c < D; ++c) oc[c] = bg ? pix[c] + T * bg[c] : pix[c];
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd a, int tiles_x, int tiles_y) {
+  __shared__ float4 srec[kBlendThreads][4];
+  __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
+  __shared__ int sid[kBlendThreads];
+  __shared__ int warp_max[kBlendThreads / 32];
+  const int tiles = tiles_x * tiles_y;
+  const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
+  const bool inside = ix < a.width && iy < a.height;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const int beg = a.tile_offsets[blockIdx.x];
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)k * a.N * 4;
+  float* v_recs = a.v_records + (size_t)k * a.N * kRecFloats;
+
+  float T_final = 1.f, v_a = 0.f, bg_dot = 0.f;
+  float v_c[D], buf[D];
+  int last = -1;
+#pragma unroll
+  for (int c = 0; c < D; ++c) { v_c[c] = 0.f; buf[c] = 0.f; }
+  if (inside) {
+    const size_t p = ((size_t)k * a.height + iy) * a.width + ix;
+    T_final = 1.f - a.out_alphas[p];
+    last = a.last_idx[p];
+    const float* vc = a.v_out_colors + p * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) v_c[c] = vc[c];
+    if (a.v_out_alphas) v_a = a.v_out_alphas[p];
+    if (a.backgrounds) {
+      const float* bg = a.backgrounds + (size_t)k * D;
+#pragma unroll
+      for (int c = 0; c < D; ++c) bg_dot += bg[c] * v_c[c];
+    }
+  }
+  float T = T_final;
+  // last list entry any pixel of this tile blended
+  int wmax = last;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  if (lane == 0) warp_max[tid >> 5] = wmax;
+  __syncthreads();
+  int tile_last = -1;
+#pragma unroll
+  for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
+  if (tile_last < beg) return;
+
+  // walk the list back to front in batches: batch b covers [hi - 255, hi]
+  for (int hi = tile_last; hi >= beg; hi -= kBlendThreads) {
+    const int lo = max(beg, hi - kBlendThreads + 1);
+    const int bn = hi - lo + 1;
+    __syncthreads();   // previous batch fully flushed
+    if (tid < bn) {
+      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      sid[tid] = g;
+      const float4* r = recs + (size_t)g * 4;
+      srec[tid][0] = __ldg(r); srec[tid][1] = __ldg(r + 1);
+      if (D > 2) srec[tid][2] = __ldg(r + 2);
+      if (D > 6) srec[tid][3] = __ldg(r + 3);
+    }
+#pragma unroll
+    for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
+    __syncthreads();
+    // entries above this warp's furthest pixel contribute nothing: skip them warp-uniformly
+    for (int t = max(0, hi - wmax); t < bn; ++t) {
+      const int idx = hi - t;
+      bool valid = inside && idx <= last;
+      const float4 r0 = srec[t][0], r1 = srec[t][1];
+      const float dx = r0.x - px, dy = r0.y - py;
+      float vis = 0.f, alpha = 0.f;
+      if (valid) {
+        const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+        vis = __expf(-sigma);
+        alpha = fminf(kAlphaMax, r0.z * vis);
+        if (sigma < 0.f || alpha < kAlphaMin) valid = false;
+      }
+      if (!__any_sync(0xffffffffu, valid)) continue;
+      float g[6 + D];   // v_x v_y v_opac v_ca v_cb v_cc v_col[D]
+#pragma unroll
+      for (int c = 0; c < 6 + D; ++c) g[c] = 0.f;
+      if (valid) {
+        float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
+        if (D > 2) r2 = srec[t][2];
+        if (D > 6) r3 = srec[t][3];
+        const float ra = 1.f / (1.f - alpha);
+        T *= ra;
+        const float fac = alpha * T;
+        float v_alpha = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const float col = rec_color(r1, r2, r3, c);
+          g[6 + c] = fac * v_c[c];
+          v_alpha += (col * T - buf[c] * ra) * v_c[c];
+          buf[c] += col * fac;
+        }
+        v_alpha += T_final * ra * (v_a - bg_dot);
+        if (r0.z * vis <= kAlphaMax) {
+          const float v_sigma = -r0.z * vis * v_alpha;
+          g[0] = v_sigma * (r0.w * dx + r1.x * dy);
+          g[1] = v_sigma * (r1.x * dx + r1.y * dy);
+          g[2] = vis * v_alpha;
+          g[3] = 0.5f * v_sigma * dx * dx;
+          g[4] = v_sigma * dx * dy;
+          g[5] = 0.5f * v_sigma * dy * dy;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 6 + D; ++c) g[c] = warp_sum(g[c]);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 6 + D; ++c) atomicAdd(&sacc[t][c], g[c]);
+      }
+    }
+    __syncthreads();
+    if (tid < bn) {
+      const float4* s4 = reinterpret_cast<const float4*>(sacc[tid]);
+      float* dst = v_recs + (size_t)sid[tid] * kRecFloats;
+      constexpr int kVec = (6 + D + 3) / 4;
+#pragma unroll
+      for (int v = 0; v < kVec; ++v) {
+        const float4 s = s4[v];
+        if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) red_add_v4(dst + 4 * v, s.x, s.y, s.z, s.w);
+      }
+    }
+  }
+}
+
+}  // namespace mobgs
+
+using namespace mobgs;
+
+template <int D>
+static void launch_fwd(const MobgsBlendFwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
+  blend_fwd_kernel<D><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+}
+template <int D>
+static void launch_bwd(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
+  blend_bwd_kernel<D><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+}
+
+#define MOBGS_DISPATCH_D(D, FN, ...)                                   \
+  switch (D) {                                                         \
+    case 1: FN<1>(__VA_ARGS__); break;                                 \
+    case 2: FN<2>(__VA_ARGS__); break;                                 \
+    case 3: FN<3>(__VA_ARGS__); break;                                 \
+    case 4: FN<4>(__VA_ARGS__); break;                                 \
+    case 5: FN<5>(__VA_ARGS__); break;                                 \
+    case 6: FN<6>(__VA_ARGS__); break;                                 \
+    case 7: FN<7>(__VA_ARGS__); break;                                 \
+    case 8: FN<8>(__VA_ARGS__); break;                                 \
+    case 9: FN<9>(__VA_ARGS__); break;                                 \
+    default: FN<10>(__VA_ARGS__); break;                               \
+  }
+
+extern "C" int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->K >= 1 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->D >= 1 && a->D <= MOBGS_MAX_COLORS, "D=%d out of range", a->D);
+  MOBGS_REQUIRE(a->tile_offsets && a->out_colors && a->out_alphas && a->last_idx, "NULL pointer");
+  MOBGS_REQUIRE(a->N == 0 || (a->records && a->sorted_ids), "NULL records / sorted_ids");
+  const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  MOBGS_DISPATCH_D(a->D, launch_fwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
+  return check_launch("blend_fwd");
+}
+
+extern "C" int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->K >= 1 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->D >= 1 && a->D <= MOBGS_MAX_COLORS, "D=%d out of range", a->D);
+  if (a->N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->records && a->tile_offsets && a->sorted_ids && a->out_alphas && a->last_idx &&
+                    a->v_out_colors && a->v_records, "NULL pointer");
+  const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  MOBGS_DISPATCH_D(a->D, launch_bwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
+  return check_launch("blend_bwd");
+}

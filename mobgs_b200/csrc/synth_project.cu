@@ -1,0 +1,451 @@
+// K1'/K2': attribute synthesis + EWA projection, forward and VJP.
+//
+// One thread owns one Gaussian for *all* K sub-frames of the launch: the parameters (68 B static,
+// 240 B dynamic) are read once, the K camera matrices sit in shared memory, and in the backward
+// the per-parameter gradient is summed over K in registers and written exactly once — no atomics
+// except the 12-float view-matrix gradient (one warp-reduced atomicAdd per warp and sub-frame).
+// HBM-bound; see DESIGN.md for the byte model.
+#include "common.cuh"
+
+namespace mobgs {
+
+constexpr int kProjThreads = 128;
+
+struct CamSmem {
+  Cam cam[kMaxK];
+  float t_spline[kMaxK];
+  float t_poly[kMaxK];
+};
+
+__device__ __forceinline__ void load_cams(CamSmem& sm, const MobgsCameras& c, const float* t_spline,
+                                          const float* t_poly) {
+  for (int k = threadIdx.x; k < c.K; k += blockDim.x) {
+    sm.cam[k] = load_cam(c.viewmats, c.Ks, k);
+    sm.t_spline[k] = t_spline ? t_spline[k] : 0.f;
+    sm.t_poly[k] = t_poly ? t_poly[k] : 0.f;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void store_record(float* rec, const ProjOut& o, float opac, const float col[10]) {
+  float4* r4 = reinterpret_cast<float4*>(rec);
+  if (o.radius > 0) {
+    r4[0] = make_float4(o.mx, o.my, opac, o.ca);
+    r4[1] = make_float4(o.cb, o.cc, col[0], col[1]);
+    r4[2] = make_float4(col[2], col[3], col[4], col[5]);
+    r4[3] = make_float4(col[6], col[7], col[8], col[9]);
+  } else {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    r4[0] = z; r4[1] = z; r4[2] = z; r4[3] = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// plain gsplat-style projection
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(MobgsProjectFwd a) {
+  __shared__ CamSmem sm;
+  load_cams(sm, a.cams, nullptr, nullptr);
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.N) return;
+  const ProjCfg cfg = make_cfg(a.cams);
+  float p[3], q[4], s[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { p[i] = a.means[3 * g + i]; s[i] = a.scales[3 * g + i]; }
+  const float4 q4 = *reinterpret_cast<const float4*>(a.quats + 4 * g);
+  q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+  for (int k = 0; k < a.cams.K; ++k) {
+    ProjState st;
+    const ProjOut o = project_fwd(p, q, s, sm.cam[k], cfg, st);
+    const size_t i = (size_t)k * a.N + g;
+    if (a.radii) a.radii[i] = o.radius;
+    if (a.means2d) *reinterpret_cast<float2*>(a.means2d + 2 * i) = make_float2(o.mx, o.my);
+    if (a.depths) a.depths[i] = o.depth;
+    if (a.conics) { a.conics[3 * i] = o.ca; a.conics[3 * i + 1] = o.cb; a.conics[3 * i + 2] = o.cc; }
+  }
+}
+
+__device__ __forceinline__ void reduce_viewmat_grad(float* v_viewmats, int k, const ProjGrad& g, bool active) {
+  // 12 warp reductions; lanes that did not contribute pass zeros. One atomicAdd per warp.
+  float vals[12];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) vals[i] = active ? g.r[i] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) vals[9 + i] = active ? g.t[i] : 0.f;
+  if (!__any_sync(0xffffffffu, active)) return;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) vals[i] = warp_sum(vals[i]);
+  if ((threadIdx.x & 31) == 0) {
+    float* v = v_viewmats + 16 * k;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      atomicAdd(v + 4 * i + 0, vals[3 * i + 0]);
+      atomicAdd(v + 4 * i + 1, vals[3 * i + 1]);
+      atomicAdd(v + 4 * i + 2, vals[3 * i + 2]);
+      atomicAdd(v + 4 * i + 3, vals[9 + i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kProjThreads) project_bwd_kernel(MobgsProjectBwd a) {
+  __shared__ CamSmem sm;
+  load_cams(sm, a.cams, nullptr, nullptr);
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = g < a.N;
+  const ProjCfg cfg = make_cfg(a.cams);
+  float p[3] = {0, 0, 0}, q[4] = {1, 0, 0, 0}, s[3] = {1, 1, 1};
+  if (in_range) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p[i] = a.means[3 * g + i]; s[i] = a.scales[3 * g + i]; }
+    const float4 q4 = *reinterpret_cast<const float4*>(a.quats + 4 * g);
+    q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+  }
+  float vp[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0};
+  for (int k = 0; k < a.cams.K; ++k) {
+    const size_t i = (size_t)k * a.N + g;
+    const bool active = in_range && a.radii[i] > 0;
+    ProjGrad gr;
+    if (active) {
+      ProjState st;
+      proj_state(p, q, s, sm.cam[k], cfg, st);
+      float vmx = 0, vmy = 0, vd = 0, vca = 0, vcb = 0, vcc = 0;
+      if (a.v_means2d) { const float* v = a.v_means2d + i * a.v_means2d_stride; vmx = v[0]; vmy = v[1]; }
+      if (a.v_depths) vd = a.v_depths[i * a.v_depths_stride];
+      if (a.v_conics) { const float* v = a.v_conics + i * a.v_conics_stride; vca = v[0]; vcb = v[1]; vcc = v[2]; }
+      project_bwd(p, s, sm.cam[k], st, vmx, vmy, vd, vca, vcb, vcc, gr);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) { vp[j] += gr.p[j]; vs[j] += gr.s[j]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vq[j] += gr.q[j];
+    }
+    if (a.v_viewmats) reduce_viewmat_grad(a.v_viewmats, k, gr, active);
+  }
+  if (in_range) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { a.v_means[3 * g + j] = vp[j]; a.v_scales[3 * g + j] = vs[j]; }
+    *reinterpret_cast<float4*>(a.v_quats + 4 * g) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused MoBGS synthesis + projection
+// ------------------------------------------------------------------------------------------
+struct DynRow {
+  float rot[4], omega[4], scale[3], opac, fdc[6], ft[3], trbf, off[3];
+  int n_ctrl;
+};
+
+__device__ __forceinline__ void load_dyn(const MobgsDynamicParams& d, int j, DynRow& r) {
+  const float4 r4 = *reinterpret_cast<const float4*>(d.rotation + 4 * j);
+  const float4 o4 = *reinterpret_cast<const float4*>(d.omega + 4 * j);
+  r.rot[0] = r4.x; r.rot[1] = r4.y; r.rot[2] = r4.z; r.rot[3] = r4.w;
+  r.omega[0] = o4.x; r.omega[1] = o4.y; r.omega[2] = o4.z; r.omega[3] = o4.w;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r.scale[i] = expf(d.scaling[3 * j + i]);
+    r.ft[i] = d.features_t[3 * j + i];
+    r.off[i] = d.offset ? d.offset[3 * j + i] : 0.f;
+  }
+  const float2* f2 = reinterpret_cast<const float2*>(d.features_dc + 6 * j);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const float2 f = f2[i]; r.fdc[2 * i] = f.x; r.fdc[2 * i + 1] = f.y; }
+  r.opac = sigmoidf(d.opacity[j]);
+  r.trbf = d.trbf_center[j];
+  int n = (int)d.control_num[j];
+  n = n < 2 ? 2 : (n > d.n_ctrl_max ? d.n_ctrl_max : n);
+  r.n_ctrl = n;
+}
+
+__global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSynthFwd a) {
+  __shared__ CamSmem sm;
+  load_cams(sm, a.cams, a.t_spline, a.t_poly);
+  const int N = a.st.Ns + a.dy.Nd;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  const ProjCfg cfg = make_cfg(a.cams);
+  const int K = a.cams.K;
+  if (g < a.st.Ns) {
+    float p[3], q[4], s[3], col[10];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { p[i] = a.st.xyz[3 * g + i]; s[i] = expf(a.st.scaling[3 * g + i]); }
+    const float4 q4 = *reinterpret_cast<const float4*>(a.st.rotation + 4 * g);
+    q[0] = q4.x; q[1] = q4.y; q[2] = q4.z; q[3] = q4.w;
+    const float opac = sigmoidf(a.st.opacity[g]);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) col[i] = a.st.features_dc[6 * g + i];
+    col[6] = col[7] = col[8] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      ProjState st;
+      const ProjOut o = project_fwd(p, q, s, sm.cam[k], cfg, st);
+      const size_t i = (size_t)k * N + g;
+      col[9] = o.depth;
+      store_record(a.records + i * kRecFloats, o, opac, col);
+      a.radii[i] = o.radius;
+      a.depths[i] = o.depth;
+      if (a.means3d) { a.means3d[3 * i] = p[0]; a.means3d[3 * i + 1] = p[1]; a.means3d[3 * i + 2] = p[2]; }
+    }
+  } else {
+    const int j = g - a.st.Ns;
+    DynRow r;
+    load_dyn(a.dy, j, r);
+    const float* ctrl = a.dy.control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
+    float col[10];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) col[i] = r.fdc[i];
+    for (int k = 0; k < K; ++k) {
+      const SplineTaps tp = hermite_taps(sm.t_spline[k], r.n_ctrl);
+      float p[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const float* c = ctrl + 3 * tp.idx[t];
+        p[0] += tp.w[t] * c[0]; p[1] += tp.w[t] * c[1]; p[2] += tp.w[t] * c[2];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) p[i] = p[i] * 1e-2f + r.off[i];
+      const float dt = sm.t_poly[k] - r.trbf;
+      float q[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q[i] = r.rot[i] + dt * r.omega[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) col[6 + i] = dt * r.ft[i];
+      ProjState st;
+      const ProjOut o = project_fwd(p, q, r.scale, sm.cam[k], cfg, st);
+      const size_t i = (size_t)k * N + g;
+      col[9] = o.depth;
+      store_record(a.records + i * kRecFloats, o, r.opac, col);
+      a.radii[i] = o.radius;
+      a.depths[i] = o.depth;
+      if (a.means3d) { a.means3d[3 * i] = p[0]; a.means3d[3 * i + 1] = p[1]; a.means3d[3 * i + 2] = p[2]; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSynthBwd a) {
+  __shared__ CamSmem sm;
+  load_cams(sm, a.cams, a.t_spline, a.t_poly);
+  const int N = a.st.Ns + a.dy.Nd;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = g < N;
+  const bool is_static = g < a.st.Ns;
+  const ProjCfg cfg = make_cfg(a.cams);
+  const int K = a.cams.K;
+  const int j = g - a.st.Ns;
+
+  float p[3] = {0, 0, 0}, s[3] = {1, 1, 1}, q0[4] = {1, 0, 0, 0};
+  float opac = 0.f;
+  DynRow r;
+  r.n_ctrl = 2; r.trbf = 0.f;
+  const float* ctrl = nullptr;
+  float* v_ctrl = nullptr;
+  if (in_range) {
+    if (is_static) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { p[i] = a.st.xyz[3 * g + i]; s[i] = expf(a.st.scaling[3 * g + i]); }
+      const float4 q4 = *reinterpret_cast<const float4*>(a.st.rotation + 4 * g);
+      q0[0] = q4.x; q0[1] = q4.y; q0[2] = q4.z; q0[3] = q4.w;
+      opac = sigmoidf(a.st.opacity[g]);
+    } else {
+      load_dyn(a.dy, j, r);
+      ctrl = a.dy.control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
+      v_ctrl = a.v_control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s[i] = r.scale[i];
+      opac = r.opac;
+    }
+  }
+  float vp[3] = {0, 0, 0}, vq[4] = {0, 0, 0, 0}, vs[3] = {0, 0, 0}, vom[4] = {0, 0, 0, 0};
+  float vop = 0.f, vfdc[6] = {0, 0, 0, 0, 0, 0}, vft[3] = {0, 0, 0};
+
+  for (int k = 0; k < K; ++k) {
+    const size_t i = (size_t)k * N + g;
+    const bool active = in_range && a.radii[i] > 0;
+    ProjGrad gr;
+    if (active) {
+      float q[4];
+      float dt = 0.f;
+      SplineTaps tp;
+      if (is_static) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = q0[c];
+      } else {
+        tp = hermite_taps(sm.t_spline[k], r.n_ctrl);
+        p[0] = p[1] = p[2] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float* c = ctrl + 3 * tp.idx[t];
+          p[0] += tp.w[t] * c[0]; p[1] += tp.w[t] * c[1]; p[2] += tp.w[t] * c[2];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) p[c] = p[c] * 1e-2f + r.off[c];
+        dt = sm.t_poly[k] - r.trbf;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) q[c] = r.rot[c] + dt * r.omega[c];
+      }
+      ProjState st;
+      proj_state(p, q, s, sm.cam[k], cfg, st);
+      const float4* v4 = reinterpret_cast<const float4*>(a.v_records + i * kRecFloats);
+      const float4 v0 = v4[0], v1 = v4[1], v2 = v4[2], v3 = v4[3];
+      // layout: x y opac ca | cb cc c0 c1 | c2 c3 c4 c5 | c6 c7 c8 c9(depth)
+      project_bwd(p, s, sm.cam[k], st, v0.x, v0.y, v3.w, v0.w, v1.x, v1.y, gr);
+      vop += v0.z;
+      vfdc[0] += v1.z; vfdc[1] += v1.w; vfdc[2] += v2.x; vfdc[3] += v2.y; vfdc[4] += v2.z; vfdc[5] += v2.w;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) vs[c] += gr.s[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vq[c] += gr.q[c];
+      if (is_static) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vp[c] += gr.p[c];
+      } else {
+        vft[0] += dt * v3.x; vft[1] += dt * v3.y; vft[2] += dt * v3.z;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vom[c] += dt * gr.q[c];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) vp[c] += gr.p[c];   // gradient of the `coherent` offset
+        // this thread is the only writer of its control-point row: plain read-modify-write
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float w = tp.w[t] * 1e-2f;
+          if (w != 0.f) {
+            float* c = v_ctrl + 3 * tp.idx[t];
+            c[0] += w * gr.p[0]; c[1] += w * gr.p[1]; c[2] += w * gr.p[2];
+          }
+        }
+      }
+    }
+    if (a.v_viewmats) reduce_viewmat_grad(a.v_viewmats, k, gr, active);
+  }
+  if (!in_range) return;
+  const float vo_logit = vop * opac * (1.f - opac);
+  if (is_static) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a.v_xyz[3 * g + c] = vp[c]; a.v_scaling_s[3 * g + c] = vs[c] * s[c]; }
+    *reinterpret_cast<float4*>(a.v_rotation_s + 4 * g) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    a.v_opacity_s[g] = vo_logit;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.v_features_dc_s[6 * g + c] = vfdc[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a.v_scaling_d[3 * j + c] = vs[c] * s[c];
+      a.v_features_t[3 * j + c] = vft[c];
+      if (a.v_offset) a.v_offset[3 * j + c] = vp[c];
+    }
+    *reinterpret_cast<float4*>(a.v_rotation_d + 4 * j) = make_float4(vq[0], vq[1], vq[2], vq[3]);
+    *reinterpret_cast<float4*>(a.v_omega + 4 * j) = make_float4(vom[0], vom[1], vom[2], vom[3]);
+    a.v_opacity_d[j] = vo_logit;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) a.v_features_dc_d[6 * j + c] = vfdc[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// SoA -> packed records (gsplat-compatible operator path)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_records_kernel(MobgsPack a) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t total = (size_t)a.K * a.N;
+  if (i >= total) return;
+  const int g = (int)(i % a.N);
+  float col[10];
+#pragma unroll
+  for (int c = 0; c < 10; ++c) col[c] = 0.f;
+  const float* cp = a.colors_per_cam ? a.colors + i * a.D : a.colors + (size_t)g * a.D;
+  for (int c = 0; c < a.D; ++c) col[c] = cp[c];
+  if (a.depths) col[a.D] = a.depths[i];
+  float4* r4 = reinterpret_cast<float4*>(a.records + i * kRecFloats);
+  const float2 m = *reinterpret_cast<const float2*>(a.means2d + 2 * i);
+  const float* cn = a.conics + 3 * i;
+  r4[0] = make_float4(m.x, m.y, a.opacities[g], cn[0]);
+  r4[1] = make_float4(cn[1], cn[2], col[0], col[1]);
+  r4[2] = make_float4(col[2], col[3], col[4], col[5]);
+  r4[3] = make_float4(col[6], col[7], col[8], col[9]);
+}
+
+}  // namespace mobgs
+
+using namespace mobgs;
+
+static int check_cams(const MobgsCameras& c) {
+  MOBGS_REQUIRE(c.K >= 1 && c.K <= kMaxK, "K=%d out of range [1,%d]", c.K, kMaxK);
+  MOBGS_REQUIRE(c.width > 0 && c.height > 0, "bad image size %dx%d", c.width, c.height);
+  MOBGS_REQUIRE(c.viewmats && c.Ks, "viewmats / Ks must not be NULL");
+  return MOBGS_OK;
+}
+
+extern "C" int mobgs_project_fwd(const MobgsProjectFwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  if (int e = check_cams(a->cams)) return e;
+  MOBGS_REQUIRE(a->N >= 0, "N < 0");
+  if (a->N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->means && a->quats && a->scales, "means/quats/scales must not be NULL");
+  const int grid = (a->N + kProjThreads - 1) / kProjThreads;
+  project_fwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("project_fwd");
+}
+
+extern "C" int mobgs_project_bwd(const MobgsProjectBwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  if (int e = check_cams(a->cams)) return e;
+  if (a->N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->means && a->quats && a->scales && a->radii, "inputs must not be NULL");
+  MOBGS_REQUIRE(a->v_means && a->v_quats && a->v_scales, "gradient outputs must not be NULL");
+  const int grid = (a->N + kProjThreads - 1) / kProjThreads;
+  project_bwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("project_bwd");
+}
+
+static int check_params(const MobgsStaticParams& s, const MobgsDynamicParams& d) {
+  MOBGS_REQUIRE(s.Ns >= 0 && d.Nd >= 0, "negative Gaussian count");
+  if (s.Ns > 0) MOBGS_REQUIRE(s.xyz && s.rotation && s.scaling && s.opacity && s.features_dc, "static params NULL");
+  if (d.Nd > 0) {
+    MOBGS_REQUIRE(d.control_xyz && d.control_num && d.rotation && d.omega && d.scaling && d.opacity &&
+                      d.features_dc && d.features_t && d.trbf_center, "dynamic params NULL");
+    MOBGS_REQUIRE(d.n_ctrl_max >= 2 && d.n_ctrl_max <= 64, "n_ctrl_max=%d out of range", d.n_ctrl_max);
+  }
+  return MOBGS_OK;
+}
+
+extern "C" int mobgs_synth_project_fwd(const MobgsSynthFwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  if (int e = check_cams(a->cams)) return e;
+  if (int e = check_params(a->st, a->dy)) return e;
+  const int N = a->st.Ns + a->dy.Nd;
+  if (N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->records && a->radii && a->depths, "outputs must not be NULL");
+  MOBGS_REQUIRE(a->dy.Nd == 0 || (a->t_spline && a->t_poly), "t_spline / t_poly must not be NULL");
+  const int grid = (N + kProjThreads - 1) / kProjThreads;
+  synth_project_fwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("synth_project_fwd");
+}
+
+extern "C" int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  if (int e = check_cams(a->cams)) return e;
+  if (int e = check_params(a->st, a->dy)) return e;
+  const int N = a->st.Ns + a->dy.Nd;
+  if (N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->radii && a->v_records, "radii / v_records must not be NULL");
+  if (a->st.Ns > 0)
+    MOBGS_REQUIRE(a->v_xyz && a->v_rotation_s && a->v_scaling_s && a->v_opacity_s && a->v_features_dc_s,
+                  "static gradient outputs NULL");
+  if (a->dy.Nd > 0)
+    MOBGS_REQUIRE(a->v_control_xyz && a->v_rotation_d && a->v_omega && a->v_scaling_d && a->v_opacity_d &&
+                      a->v_features_dc_d && a->v_features_t, "dynamic gradient outputs NULL");
+  const int grid = (N + kProjThreads - 1) / kProjThreads;
+  synth_project_bwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("synth_project_bwd");
+}
+
+extern "C" int mobgs_pack_records(const MobgsPack* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->K >= 1 && a->N >= 0, "bad K/N");
+  const int dtot = a->D + (a->depths ? 1 : 0);
+  MOBGS_REQUIRE(a->D >= 1 && dtot <= MOBGS_MAX_COLORS, "D=%d (+depth) exceeds %d channels", a->D, MOBGS_MAX_COLORS);
+  if (a->N == 0) return MOBGS_OK;
+  MOBGS_REQUIRE(a->means2d && a->conics && a->opacities && a->colors && a->records, "NULL pointer");
+  const size_t total = (size_t)a->K * a->N;
+  const int grid = (int)((total + 255) / 256);
+  pack_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("pack_records");
+}

@@ -1,0 +1,202 @@
+"""torch.autograd.Function wrappers over the C ABI (include/mobgs_b200.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the autograd graph; every
+arithmetic step of the path runs in libmobgs_b200.so.  All inputs must be CUDA fp32 tensors —
+there is no CPU path and none is attempted.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0   # gsplat.rendering.rasterization defaults
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError("mobgs_b200 ops need CUDA tensors (no CPU fallback exists)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _cams(viewmats, Ks, width, height, eps2d=EPS2D, near=NEAR, far=FAR, radius_clip=RADIUS_CLIP):
+    return L.Cameras(viewmats.shape[0], int(width), int(height), _p(viewmats), _p(Ks),
+                     float(eps2d), float(near), float(far), float(radius_clip))
+
+
+def _strided(g: Optional[torch.Tensor], N: int, inner: int):
+    """Returns (tensor kept alive, pointer, per-Gaussian stride in floats) for a gradient of shape
+    [K,N,inner] / [K,N] whose layout is (k*N+g)*stride + j — e.g. a view into packed records."""
+    if g is None:
+        return None, None, 0
+    st = g.stride()
+    if inner > 1:
+        ok = g.dim() == 3 and st[2] == 1 and st[0] == N * st[1] and st[1] >= inner
+    else:
+        ok = g.dim() == 2 and st[0] == N * st[1] and st[1] >= 1
+    if g.dtype != torch.float32 or not ok:
+        g = g.float().contiguous()
+        return g, g.data_ptr(), inner
+    return g, g.data_ptr(), st[1]
+
+
+class _Project(torch.autograd.Function):
+    """gsplat.rendering.fully_fused_projection (pinhole, packed=False, covars=None)."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, viewmats, Ks, width, height, eps2d, near, far, radius_clip):
+        means, quats, scales = _f32c(means), _f32c(quats), _f32c(scales)
+        viewmats, Ks = _f32c(viewmats), _f32c(Ks)
+        K, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        radii = torch.empty(K, N, dtype=torch.int32, device=dev)
+        means2d = torch.empty(K, N, 2, device=dev)
+        depths = torch.empty(K, N, device=dev)
+        conics = torch.empty(K, N, 3, device=dev)
+        cams = _cams(viewmats, Ks, width, height, eps2d, near, far, radius_clip)
+        a = L.ProjectFwd(cams, N, _p(means), _p(quats), _p(scales), _p(radii), _p(means2d), _p(depths), _p(conics))
+        L.call("mobgs_project_fwd", a, _stream())
+        ctx.save_for_backward(means, quats, scales, viewmats, Ks, radii)
+        ctx.cfg = (width, height, eps2d, near, far, radius_clip)
+        ctx.mark_non_differentiable(radii)
+        return radii, means2d, depths, conics
+
+    @staticmethod
+    def backward(ctx, _g_radii, g_means2d, g_depths, g_conics):
+        means, quats, scales, viewmats, Ks, radii = ctx.saved_tensors
+        width, height, eps2d, near, far, radius_clip = ctx.cfg
+        K, N = viewmats.shape[0], means.shape[0]
+        dev = means.device
+        v_means = torch.empty(N, 3, device=dev)
+        v_quats = torch.empty(N, 4, device=dev)
+        v_scales = torch.empty(N, 3, device=dev)
+        v_viewmats = torch.zeros(K, 4, 4, device=dev) if ctx.needs_input_grad[3] else None
+        k1, p1, s1 = _strided(g_means2d, N, 2)
+        k2, p2, s2 = _strided(g_depths, N, 1)
+        k3, p3, s3 = _strided(g_conics, N, 3)
+        cams = _cams(viewmats, Ks, width, height, eps2d, near, far, radius_clip)
+        a = L.ProjectBwd(cams, N, _p(means), _p(quats), _p(scales), _p(radii), p1, s1, p2, s2, p3, s3,
+                         _p(v_means), _p(v_quats), _p(v_scales), _p(v_viewmats))
+        L.call("mobgs_project_bwd", a, _stream())
+        del k1, k2, k3
+        return v_means, v_quats, v_scales, v_viewmats, None, None, None, None, None, None, None
+
+
+def project(means, quats, scales, viewmats, Ks, width, height, eps2d=EPS2D, near_plane=NEAR,
+            far_plane=FAR, radius_clip=RADIUS_CLIP):
+    return _Project.apply(means, quats, scales, viewmats, Ks, int(width), int(height),
+                          float(eps2d), float(near_plane), float(far_plane), float(radius_clip))
+
+
+class TileLists:
+    """Per-(sub-frame, tile) depth-sorted Gaussian lists."""
+
+    def __init__(self, tile_offsets, sorted_ids, n_isect, K, width, height):
+        self.tile_offsets = tile_offsets
+        self.sorted_ids = sorted_ids
+        self.n_isect = n_isect
+        self.K, self.width, self.height = K, width, height
+
+
+def build_tile_lists(records, radii, depths, width, height, tight=True) -> TileLists:
+    """mobgs_tile_count -> (one 4-byte read-back of I) -> mobgs_tile_emit_sort."""
+    K, N = radii.shape
+    dev = records.device
+    tiles = math.ceil(width / L.TILE) * math.ceil(height / L.TILE)
+    nt = K * tiles
+    counts = torch.empty(nt, dtype=torch.int32, device=dev)
+    offsets = torch.empty(nt + 1, dtype=torch.int32, device=dev)
+    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), _p(counts), _p(offsets))
+    L.call("mobgs_tile_count", a, _stream())
+    n_isect = int(offsets[-1].item())
+    cap = max(n_isect, 1)
+    keys = torch.empty(cap, dtype=torch.int64, device=dev)
+    keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
+    sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), _p(offsets),
+                   _p(counts), n_isect, _p(keys), _p(keys_tmp), _p(sorted_ids))
+    L.call("mobgs_tile_emit_sort", b, _stream())
+    return TileLists(offsets, sorted_ids, n_isect, K, width, height)
+
+
+class _Rasterize(torch.autograd.Function):
+    """isect_tiles + sort + rasterize_to_pixels of gsplat.rendering.rasterization, operating on
+    gsplat's SoA tensors.  `depths` (if given and append_depth) becomes colour channel D — the
+    torch.cat of render_mode='RGB+ED'."""
+
+    @staticmethod
+    def forward(ctx, means2d, conics, colors, opacities, backgrounds, depths, radii, width, height,
+                append_depth, tight):
+        means2d, conics, colors, opacities = _f32c(means2d), _f32c(conics), _f32c(colors), _f32c(opacities)
+        depths = _f32c(depths)
+        K, N = radii.shape
+        dev = means2d.device
+        per_cam = colors.dim() == 3
+        D0 = colors.shape[-1]
+        D = D0 + (1 if append_depth else 0)
+        if D > L.MAX_COLORS:
+            raise RuntimeError(f"mobgs_b200 blend kernels carry at most {L.MAX_COLORS} channels, got {D}")
+        records = torch.empty(K, N, L.REC, device=dev)
+        pk = L.Pack(K, N, D0, _p(means2d), _p(conics), _p(opacities), _p(colors), int(per_cam),
+                    _p(depths) if append_depth else None, _p(records))
+        L.call("mobgs_pack_records", pk, _stream())
+        lists = build_tile_lists(records, radii, depths, width, height, tight)
+        bg = None
+        if backgrounds is not None:
+            bg = _f32c(backgrounds)
+            if append_depth:
+                bg = torch.cat([bg, torch.zeros_like(bg[:, :1])], dim=-1).contiguous()
+        out_c = torch.empty(K, height, width, D, device=dev)
+        out_a = torch.empty(K, height, width, device=dev)
+        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+        a = L.BlendFwd(K, N, D, width, height, _p(records), _p(lists.tile_offsets), _p(lists.sorted_ids),
+                       _p(bg), _p(out_c), _p(out_a), _p(last))
+        L.call("mobgs_blend_fwd", a, _stream())
+        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
+        ctx.meta = (K, N, D0, D, width, height, per_cam, append_depth)
+        ctx.n_isect = lists.n_isect
+        return out_c, out_a.unsqueeze(-1)
+
+    @staticmethod
+    def backward(ctx, g_c, g_a):
+        records, offsets, sorted_ids, bg, out_a, last = ctx.saved_tensors
+        K, N, D0, D, width, height, per_cam, append_depth = ctx.meta
+        dev = records.device
+        v_rec = torch.zeros(K, N, L.REC, device=dev)
+        g_c = _f32c(g_c)
+        g_a = _f32c(g_a) if g_a is not None else None
+        a = L.BlendBwd(K, N, D, width, height, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
+                       _p(last), _p(g_c), _p(g_a), _p(v_rec))
+        L.call("mobgs_blend_bwd", a, _stream())
+        v_means2d = v_rec[..., 0:2]
+        v_conics = v_rec[..., 3:6]
+        v_op = v_rec[..., 2]
+        v_op = v_op[0] if K == 1 else v_op.sum(0)
+        v_col = v_rec[..., 6:6 + D0]
+        if not per_cam:
+            v_col = v_col[0] if K == 1 else v_col.sum(0)
+        v_depths = v_rec[..., 6 + D0] if append_depth else None
+        v_bg = None
+        if ctx.needs_input_grad[4] and bg is not None:
+            T_fin = (1.0 - out_a).unsqueeze(-1)
+            v_bg = (g_c * T_fin).sum(dim=(1, 2))[:, :D0]
+        return v_means2d, v_conics, v_col, v_op, v_bg, v_depths, None, None, None, None, None
+
+
+def rasterize(means2d, conics, colors, opacities, backgrounds, depths, radii, width, height,
+              append_depth=False, tight=True):
+    return _Rasterize.apply(means2d, conics, colors, opacities, backgrounds, depths, radii,
+                            int(width), int(height), bool(append_depth), bool(tight))
