@@ -190,6 +190,8 @@ typedef struct {
   const float* records;      /* [K,N,16] */
   const int32_t* radii;      /* [K,N] */
   int32_t tight;
+  int32_t g_begin, g_end;    /* only Gaussians g_begin <= g < g_end are listed (static-only /
+                                dynamic-only renders of render():143,236 share one projection) */
   int32_t* tile_counts;      /* [K*T] workspace, overwritten */
   int32_t* tile_offsets;     /* [K*T+1] out */
 } MobgsTileCount;
@@ -201,6 +203,7 @@ typedef struct {
   const int32_t* radii;
   const float* depths;       /* [K,N] sort key */
   int32_t tight;
+  int32_t g_begin, g_end;
   const int32_t* tile_offsets; /* [K*T+1] from step 1 */
   int32_t* tile_cursor;      /* [K*T] workspace (zeroed inside) */
   int64_t capacity;          /* entries available in keys/keys_tmp/sorted_ids */
@@ -243,6 +246,49 @@ typedef struct {
   float* v_records;
 } MobgsBlendBwd;
 int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-pixel epilogue of one blurry view (SURVEY.md §8 a8 + a9 + the "ED" division of a6):
+ *   depth  = img[9] / max(alpha, 1e-10)                 gsplat render_mode="RGB+ED"
+ *   rgb    = sigmoid(albedo + W2 relu(W1 [spec, timefeat, rays]))   helper_model.py:19-28 (Sandwich,
+ *            bias-free 1x1 convs: W1 [6,12] = mlp1.weight, W2 [3,6] = mlp2.weight)
+ *   mean   = (1/K) sum_k rgb_k + 1e-10                  train.py:540-541 (blur model)
+ * img [K,H,W,10] and alpha [K,H,W] are the blend outputs; rays [K,6,H,W] (rays_per_k=1) or
+ * [1,6,H,W] shared.  Outputs (each may be NULL): rgb [K,3,H,W], depth [K,H,W], mean [3,H,W]. */
+typedef struct {
+  int32_t K, width, height;
+  const float* img;
+  const float* alpha;
+  const float* rays; int32_t rays_per_k;
+  const float* w1;   /* [6,12] */
+  const float* w2;   /* [3,6]  */
+  float* rgb;
+  float* depth;
+  float* mean;
+} MobgsDecodeFwd;
+int mobgs_decode_fwd(const MobgsDecodeFwd* a, void* stream);
+
+/* VJP.  g_rgb / g_depth / g_mean may be NULL.  v_img [K,H,W,10] and v_alpha [K,H,W] are written;
+ * v_rays (same shape as rays; NULL = not needed) is written when rays_per_k=1 and accumulated
+ * atomically (zeroed by the caller) when shared; v_w1 / v_w2 are accumulated atomically and
+ * must be zeroed by the caller. */
+typedef struct {
+  int32_t K, width, height;
+  const float* img;
+  const float* alpha;
+  const float* rays; int32_t rays_per_k;
+  const float* w1;
+  const float* w2;
+  const float* g_rgb;
+  const float* g_depth;
+  const float* g_mean;
+  float* v_img;
+  float* v_alpha;
+  float* v_rays;
+  float* v_w1;
+  float* v_w2;
+} MobgsDecodeBwd;
+int mobgs_decode_bwd(const MobgsDecodeBwd* a, void* stream);
 
 #ifdef __cplusplus
 }

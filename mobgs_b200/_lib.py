@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "render_fused.cu", "hexplane_mlp.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -116,13 +116,15 @@ class Pack(C.Structure):
 class TileCount(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("tight", C.c_int32),
+                ("g_begin", C.c_int32), ("g_end", C.c_int32),
                 ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p)]
 
 
 class TileSort(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("depths", C.c_void_p),
-                ("tight", C.c_int32), ("tile_offsets", C.c_void_p), ("tile_cursor", C.c_void_p),
+                ("tight", C.c_int32), ("g_begin", C.c_int32), ("g_end", C.c_int32),
+                ("tile_offsets", C.c_void_p), ("tile_cursor", C.c_void_p),
                 ("capacity", C.c_int64), ("keys", C.c_void_p), ("keys_tmp", C.c_void_p),
                 ("sorted_ids", C.c_void_p)]
 
@@ -142,6 +144,21 @@ class BlendBwd(C.Structure):
                 ("v_records", C.c_void_p)]
 
 
+class DecodeFwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("img", C.c_void_p),
+                ("alpha", C.c_void_p), ("rays", C.c_void_p), ("rays_per_k", C.c_int32),
+                ("w1", C.c_void_p), ("w2", C.c_void_p), ("rgb", C.c_void_p), ("depth", C.c_void_p),
+                ("mean", C.c_void_p)]
+
+
+class DecodeBwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("img", C.c_void_p),
+                ("alpha", C.c_void_p), ("rays", C.c_void_p), ("rays_per_k", C.c_int32),
+                ("w1", C.c_void_p), ("w2", C.c_void_p), ("g_rgb", C.c_void_p), ("g_depth", C.c_void_p),
+                ("g_mean", C.c_void_p), ("v_img", C.c_void_p), ("v_alpha", C.c_void_p),
+                ("v_rays", C.c_void_p), ("v_w1", C.c_void_p), ("v_w2", C.c_void_p)]
+
+
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
 ENTRY_POINTS = {
@@ -156,6 +173,8 @@ ENTRY_POINTS = {
     "mobgs_tile_emit_sort": TileSort,
     "mobgs_blend_fwd": BlendFwd,
     "mobgs_blend_bwd": BlendBwd,
+    "mobgs_decode_fwd": DecodeFwd,
+    "mobgs_decode_bwd": DecodeBwd,
 }
 
 _lib = None

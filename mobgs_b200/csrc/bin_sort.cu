@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(256) tile_count_kernel(MobgsTileCount a, int t
   const int radius = a.radii[i];
   if (radius <= 0) return;
   const int k = (int)(i / a.N);
+  const int gid = (int)(i - (size_t)k * a.N);
+  if (gid < a.g_begin || gid >= a.g_end) return;
   const GaussGeom g = load_geom(a.records + i * kRecFloats);
   int* counts = a.tile_counts + (size_t)k * tiles_x * tiles_y;
   for_each_tile(g, radius, a.width, a.height, tiles_x, tiles_y, a.tight,
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) tile_emit_kernel(MobgsTileSort a, int til
   if (radius <= 0) return;
   const int k = (int)(i / a.N);
   const int gid = (int)(i - (size_t)k * a.N);
+  if (gid < a.g_begin || gid >= a.g_end) return;
   const GaussGeom g = load_geom(a.records + i * kRecFloats);
   const size_t tbase = (size_t)k * tiles_x * tiles_y;
   const uint64_t key = ((uint64_t)__float_as_uint(a.depths[i]) << 32) | (uint32_t)gid;

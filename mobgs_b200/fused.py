@@ -1,0 +1,188 @@
+"""The fused MoBGS path: K latent sub-frames per launch.
+
+Stage A  `synth_project`  — attribute synthesis (spline / activations / time-linear terms) +
+         projection for all K sub-frames in one launch -> packed 64-byte records.
+Stage B  `blend_records`  — tile binning + per-tile sort + alpha compositing of the records
+         (optionally restricted to the static or the dynamic index range, which is how the
+         s_render / d_render / s_alpha / d_alpha renders of render() share one projection).
+
+The gradient between the two stages travels as one packed [K,N,16] tensor (the layout the
+backward blend kernel scatters into), never as gsplat's five SoA tensors.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from .ops import _cams, _f32c, _p, _stream, build_tile_lists, EPS2D, NEAR, FAR, RADIUS_CLIP
+
+STATIC_KEYS = ("xyz", "rotation", "scaling", "opacity", "features_dc")
+DYNAMIC_KEYS = ("control_xyz", "rotation", "omega", "scaling", "opacity", "features_dc", "features_t",
+                "trbf_center")
+
+
+def _static_struct(ts):
+    xyz, rot, sc, op, fdc = ts
+    return L.StaticParams(xyz.shape[0], _p(xyz), _p(rot), _p(sc), _p(op), _p(fdc))
+
+
+def _dynamic_struct(ts, control_num, offset):
+    ctrl, rot, om, sc, op, fdc, ft, trbf = ts
+    return L.DynamicParams(ctrl.shape[0], ctrl.shape[1] if ctrl.dim() == 3 else 12, _p(ctrl), _p(control_num),
+                           _p(rot), _p(om), _p(sc), _p(op), _p(fdc), _p(ft), _p(trbf), _p(offset))
+
+
+class _SynthProject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, viewmats, Ks, t_spline, t_poly, control_num, width, height, want_means3d,
+                s_xyz, s_rot, s_sc, s_op, s_fdc,
+                d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf, d_off):
+        st = [_f32c(t) for t in (s_xyz, s_rot, s_sc, s_op, s_fdc)]
+        dy = [_f32c(t) for t in (d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf)]
+        viewmats, Ks = _f32c(viewmats), _f32c(Ks)
+        t_spline, t_poly = _f32c(t_spline), _f32c(t_poly)
+        control_num = control_num.to(torch.int64).contiguous()
+        off = _f32c(d_off) if d_off is not None else None
+        K = viewmats.shape[0]
+        Ns, Nd = st[0].shape[0], dy[0].shape[0]
+        N = Ns + Nd
+        dev = viewmats.device
+        records = torch.empty(K, N, L.REC, device=dev)
+        radii = torch.empty(K, N, dtype=torch.int32, device=dev)
+        depths = torch.empty(K, N, device=dev)
+        means3d = torch.empty(K, N, 3, device=dev) if want_means3d else None
+        cams = _cams(viewmats, Ks, width, height)
+        a = L.SynthFwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
+                       _p(t_poly), _p(records), _p(radii), _p(depths), _p(means3d))
+        L.call("mobgs_synth_project_fwd", a, _stream())
+        ctx.save_for_backward(viewmats, Ks, t_spline, t_poly, control_num, radii, off, *st, *dy)
+        ctx.size = (width, height)
+        ctx.mark_non_differentiable(radii, depths)
+        if means3d is None:
+            means3d = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(means3d)
+        return records, radii, depths, means3d
+
+    @staticmethod
+    def backward(ctx, g_rec, _g_radii, _g_depths, _g_m3d):
+        viewmats, Ks, t_spline, t_poly, control_num, radii, off, *rest = ctx.saved_tensors
+        st, dy = rest[:5], rest[5:]
+        width, height = ctx.size
+        K = viewmats.shape[0]
+        dev = viewmats.device
+        g_rec = _f32c(g_rec)
+        v_st = [torch.empty_like(t) for t in st]
+        v_dy = [torch.zeros_like(dy[0])] + [torch.empty_like(t) for t in dy[1:]]
+        v_dy[7].zero_()     # trbf_center: dt is detached in the reference (render():102) -> no gradient
+        v_off = torch.empty_like(off) if off is not None else None
+        v_view = torch.zeros(K, 4, 4, device=dev) if ctx.needs_input_grad[0] else None
+        cams = _cams(viewmats, Ks, width, height)
+        a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
+                       _p(t_poly), _p(radii), _p(g_rec),
+                       _p(v_st[0]), _p(v_st[1]), _p(v_st[2]), _p(v_st[3]), _p(v_st[4]),
+                       _p(v_dy[0]), _p(v_dy[1]), _p(v_dy[2]), _p(v_dy[3]), _p(v_dy[4]), _p(v_dy[5]),
+                       _p(v_dy[6]), _p(v_off), _p(v_view))
+        L.call("mobgs_synth_project_bwd", a, _stream())
+        return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, v_off)
+
+
+def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_spline, t_poly,
+                  width, height, offset=None, want_means3d=False):
+    """static_params: (xyz[Ns,3], rotation[Ns,4], scaling[Ns,3], opacity[Ns(,1)], features_dc[Ns,6]);
+    dynamic_params: (control_xyz[Nd,P,3], rotation, omega, scaling, opacity, features_dc,
+    features_t[Nd,3], trbf_center[Nd(,1)]); control_num int64 [Nd(,1)].
+    -> records [K,N,16], radii i32 [K,N], depths [K,N], means3d [K,N,3] or empty."""
+    return _SynthProject.apply(viewmats, Ks, t_spline, t_poly, control_num, int(width), int(height),
+                               bool(want_means3d), *static_params, *dynamic_params, offset)
+
+
+class _BlendRecords(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, g_range, tight, vsp_k):
+        records = _f32c(records)
+        K, N = radii.shape
+        dev = records.device
+        lists = build_tile_lists(records, radii, depths, width, height, tight, g_range)
+        bg = _f32c(backgrounds) if backgrounds is not None else None
+        out_c = torch.empty(K, height, width, D, device=dev)
+        out_a = torch.empty(K, height, width, device=dev)
+        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+        a = L.BlendFwd(K, N, D, width, height, _p(records), _p(lists.tile_offsets), _p(lists.sorted_ids),
+                       _p(bg), _p(out_c), _p(out_a), _p(last))
+        L.call("mobgs_blend_fwd", a, _stream())
+        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
+        ctx.meta = (K, N, D, width, height, vsp_k, vsp is not None)
+        ctx.n_isect = lists.n_isect
+        ctx.mark_non_differentiable(last)
+        return out_c, out_a, last
+
+    @staticmethod
+    def backward(ctx, g_c, g_a, _g_last):
+        records, offsets, sorted_ids, bg, out_a, last = ctx.saved_tensors
+        K, N, D, width, height, vsp_k, has_vsp = ctx.meta
+        v_rec = torch.zeros(K, N, L.REC, device=records.device)
+        g_c = _f32c(g_c) if g_c is not None else torch.zeros(K, height, width, D, device=records.device)
+        g_a = _f32c(g_a) if g_a is not None else None
+        a = L.BlendBwd(K, N, D, width, height, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
+                       _p(last), _p(g_c), _p(g_a), _p(v_rec))
+        L.call("mobgs_blend_bwd", a, _stream())
+        v_vsp = v_rec[vsp_k, :, 0:2].unsqueeze(0).clone() if has_vsp else None
+        return v_rec, None, None, None, v_vsp, None, None, None, None, None, None
+
+
+def blend_records(records, radii, depths, backgrounds, D, width, height, g_range=None, tight=True,
+                  vsp: Optional[torch.Tensor] = None, vsp_k: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """-> (colors [K,H,W,D] incl. background, alphas [K,H,W]).  `vsp` is an optional leaf [1,N,2]
+    that receives d loss / d means2d of sub-frame vsp_k as its .grad (densification statistics,
+    reference train.py:634-648)."""
+    out_c, out_a, _ = _BlendRecords.apply(records, radii, depths, backgrounds, vsp, int(D), int(width),
+                                          int(height), g_range, bool(tight), int(vsp_k))
+    return out_c, out_a
+
+
+class _Decode(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img10, alpha, rays, w1, w2, want_mean):
+        img10, alpha, rays, w1, w2 = (_f32c(t) for t in (img10, alpha, rays, w1, w2))
+        K, H, W, D = img10.shape
+        assert D == 10 and rays.shape[1] == 6 and rays.shape[0] in (1, K)
+        per_k = int(rays.shape[0] == K and K > 1)
+        dev = img10.device
+        rgb = torch.empty(K, 3, H, W, device=dev)
+        depth = torch.empty(K, H, W, device=dev)
+        mean = torch.empty(3, H, W, device=dev) if want_mean else None
+        a = L.DecodeFwd(K, W, H, _p(img10), _p(alpha), _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth), _p(mean))
+        L.call("mobgs_decode_fwd", a, _stream())
+        ctx.save_for_backward(img10, alpha, rays, w1, w2)
+        ctx.per_k = per_k
+        if mean is None:
+            mean = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(mean)
+        return rgb, depth, mean
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_mean):
+        img10, alpha, rays, w1, w2 = ctx.saved_tensors
+        K, H, W, _ = img10.shape
+        dev = img10.device
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else None
+        g_depth = _f32c(g_depth) if g_depth is not None else None
+        g_mean = _f32c(g_mean) if (g_mean is not None and g_mean.numel() > 0) else None
+        v_img = torch.empty_like(img10)
+        v_alpha = torch.empty_like(alpha)
+        v_rays = None
+        if ctx.needs_input_grad[2]:
+            v_rays = torch.empty_like(rays) if ctx.per_k else torch.zeros_like(rays)
+        v_w1, v_w2 = torch.zeros_like(w1), torch.zeros_like(w2)
+        a = L.DecodeBwd(K, W, H, _p(img10), _p(alpha), _p(rays), ctx.per_k, _p(w1), _p(w2), _p(g_rgb),
+                        _p(g_depth), _p(g_mean), _p(v_img), _p(v_alpha), _p(v_rays), _p(v_w1), _p(v_w2))
+        L.call("mobgs_decode_bwd", a, _stream())
+        return v_img, v_alpha, v_rays, v_w1, v_w2, None
+
+
+def decode(img10, alpha, rays, w1, w2, want_mean=False):
+    """img10 [K,H,W,10], alpha [K,H,W], rays [K|1,6,H,W], w1 [6,12], w2 [3,6]
+    -> rgb [K,3,H,W], expected depth [K,H,W], blur-model mean [3,H,W] (or empty)."""
+    return _Decode.apply(img10, alpha, rays, w1, w2, bool(want_mean))

@@ -1,0 +1,182 @@
+"""Drop-in for the reference's `gaussian_renderer` package (gaussian_renderer/__init__.py):
+same `render` / `get_flow` / `get_flow_static` signatures and return structure, so the
+reference's train.py / eval.py / utils/scene_utils.py import it unchanged (put the directory
+that contains this package's parent `mobgs_b200/` first on sys.path as `gaussian_renderer`, see
+INTEGRATION.md), but one fused projection launch + at most three blend launches per call instead
+of five independent gsplat pipelines.
+
+Works with the reference's GaussianModel / Camera objects or the stand-ins of mobgs_b200.scene.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import fused, ops
+from . import network_gui  # noqa: F401  (train.py does `from gaussian_renderer import render, network_gui`)
+
+ED_ALPHA_FLOOR = 1e-10
+TIGHT_TILES = True
+
+
+def _static_params(pc):
+    return (pc._xyz, pc._rotation, pc._scaling, pc._opacity, pc._features_dc)
+
+
+def _dynamic_params(pc):
+    return (pc.control_xyz, pc._rotation, pc._omega, pc._scaling, pc._opacity, pc._features_dc,
+            pc._features_t, pc._trbf_center)
+
+
+def _bg10(bg_color, dev):
+    b3 = bg_color[:3].to(device=dev, dtype=torch.float32)
+    return torch.cat([b3, b3, b3, b3.new_zeros(1)])[None]
+
+
+def _times(cam, delta_exposure, dev, clamp):
+    """(t_spline, t_poly) as 0-d device tensors, built without a host sync."""
+    t0 = torch.as_tensor(float(cam.time), dtype=torch.float32, device=dev)
+    if delta_exposure is None:
+        return t0, t0
+    t = t0 + torch.as_tensor(delta_exposure, dtype=torch.float32, device=dev) / cam.max_time
+    return (torch.clamp(t, 0, 1) if clamp else t), t
+
+
+def _decode(dyn_pc, img10, alpha, cam):
+    """Sandwich decoder (dyn_pc.rgbdecoder's weights) + expected-depth division, one fp32 kernel.
+    -> rgb [3,H,W], depth [1,H,W]"""
+    dec = dyn_pc.rgbdecoder
+    rgb, depth, _ = fused.decode(img10, alpha, cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
+                                 dec.mlp2.weight.reshape(3, 6))
+    return rgb.squeeze(0), depth
+
+
+def _alpha_render(alpha, bg_color):
+    """rasterization(colors=1, backgrounds=bg[0:1]) channel 0 = (1 - T) + T * bg0."""
+    return alpha + (1.0 - alpha) * bg_color[0].to(alpha)
+
+
+def render(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0,
+           override_color=None, stage="fine", cam_type=None, is_static=False, over_t=None, over_vde=None,
+           get_static=False, get_dynamic=False, stat_stat=True, ref_wc=None, iter_fact=1, flow=None,
+           coherent=None, target_ts=None, target_w2cs=None, get_heatmap=False, w2c=None,
+           delta_exposure=None, get_flow=False, cluster=None):
+    """Reference: gaussian_renderer/__init__.py:59-316 (same dict keys, :294-316)."""
+    cam = viewpoint_camera
+    dev = dyn_pc._scaling.device
+    W, H = int(cam.image_width), int(cam.image_height)
+    viewmat = cam.world_view_transform.transpose(0, 1) if w2c is None else w2c
+    Kmat = cam.K
+    Ns, Nd = stat_pc.get_xyz.shape[0], dyn_pc.get_xyz.shape[0]
+    N = Ns + Nd
+    warped = delta_exposure is not None
+    t_spline, t_poly = _times(cam, delta_exposure, dev, clamp=True)
+    bg10 = _bg10(bg_color, dev)
+
+    records, radii, depths, means3d = fused.synth_project(
+        _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
+        viewmat[None], Kmat[None], t_spline[None], t_poly[None], W, H, offset=coherent, want_means3d=True)
+    # leaf carrying the projected means whose .grad receives d loss / d means2d of *this* render
+    vsp = records[:, :, 0:2].detach().clone().requires_grad_(True)
+
+    img10, alpha = fused.blend_records(records, radii, depths, bg10, 10, W, H, tight=TIGHT_TILES, vsp=vsp)
+    rendered_image, depth = _decode(dyn_pc, img10, alpha, cam)
+    radii0 = radii[0]
+
+    d_image = d_depth = d_alpha = s_image = s_depth = s_alpha = None
+    if get_dynamic:
+        d10, da = fused.blend_records(records, radii, depths, bg10, 10, W, H, g_range=(Ns, N), tight=TIGHT_TILES)
+        d_image, d_depth = _decode(dyn_pc, d10, da, cam)
+        d_alpha = _alpha_render(da, bg_color)
+    if get_static:
+        s10, sa = fused.blend_records(records, radii, depths, bg10, 10, W, H, g_range=(0, Ns), tight=TIGHT_TILES)
+        s_depth = rendered_image[..., -1]   # reference quirk kept (:250)
+        s_image, _ = _decode(dyn_pc, s10, sa, cam)
+        s_alpha = _alpha_render(sa, bg_color)
+
+    rendered_flow = ori_coord_map = None
+    if warped and get_flow:
+        t0, _ = _times(cam, None, dev, clamp=False)
+        ori_rec, _, _, _ = fused.synth_project(
+            _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
+            viewmat[None], Kmat[None], t0[None], t0[None], W, H, offset=coherent)
+        flow_2d = (ori_rec[..., 0:2] - records[..., 0:2].detach()).squeeze(0)
+        rendered_flow, _ = ops.rasterize(records[..., 0:2], records[..., 3:6], flow_2d, records[0, :, 2],
+                                         None, depths, radii, W, H, tight=TIGHT_TILES)
+        ori_coord_map = torch.tensor(cam.get_pixels(W, H, use_center=False)).type_as(rendered_flow) + rendered_flow
+
+    means3d0 = means3d[0]
+    return {"render": rendered_image,
+            "s_render": s_image,
+            "s_depth": s_depth,
+            "d_render": d_image,
+            "d_depth": d_depth,
+            "d_alpha": d_alpha,
+            "d_means3d": means3d0[Ns:] if get_dynamic else None,
+            "s_alpha": s_alpha,
+            "viewspace_points": vsp,
+            "visibility_filter": radii0 > 0,
+            "radii": radii0,
+            "depth": depth,
+            "blending_factor": None,
+            "world_coordinates": None,
+            "splat_center": None,
+            "means_3d_final": means3d0 * 1e2,
+            "colors_precomp_final": records[0, :, 6:15],
+            "ori_flow": rendered_flow,
+            "ori_coord_map": ori_coord_map,
+            "means_3d": means3d0[Ns:],
+            "labels": None,
+            "centroids": None}
+
+
+def get_flow(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposure=None):
+    """Reference: gaussian_renderer/__init__.py:318-492.  One K=2 projection launch (mid / exposure
+    time) feeds all four rasterisations."""
+    cam = viewpoint_camera
+    dev = dyn_pc._scaling.device
+    W, H = int(cam.image_width), int(cam.image_height)
+    viewmat = cam.world_view_transform.transpose(0, 1)
+    Kmat = cam.K
+    Ns, Nd = stat_pc.get_xyz.shape[0], dyn_pc.get_xyz.shape[0]
+    N = Ns + Nd
+    bg10 = _bg10(bg_color, dev)
+    ts_mid, tp_mid = _times(cam, 0.0, dev, clamp=True)
+    ts_exp, tp_exp = _times(cam, delta_exposure, dev, clamp=True)
+    rec, radii, depths, _ = fused.synth_project(
+        _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
+        torch.stack([viewmat, viewmat]), torch.stack([Kmat, Kmat]),
+        torch.stack([ts_mid, ts_exp]), torch.stack([tp_mid, tp_exp]), W, H)
+    mid, exp = slice(0, 1), slice(1, 2)
+
+    _, la = fused.blend_records(rec[exp], radii[exp], depths[exp], None, 1, W, H, g_range=(Ns, N), tight=TIGHT_TILES)
+    latent_alpha = _alpha_render(la, bg_color)
+
+    e2m = rec[0, :, 0:2] - rec[1, :, 0:2]
+    grid = torch.tensor(cam.get_pixels(W, H, use_center=False), device=dev, dtype=torch.float32)
+    e2m_flow, _ = ops.rasterize(rec[exp, :, 0:2], rec[exp, :, 3:6], e2m, rec[1, :, 2], None, depths[exp],
+                                radii[exp], W, H, tight=TIGHT_TILES)
+    exp2mid_coord_map = grid + e2m_flow
+    m2e_flow, _ = ops.rasterize(rec[mid, :, 0:2], rec[mid, :, 3:6], -e2m, rec[0, :, 2], None, depths[mid],
+                                radii[mid], W, H, tight=TIGHT_TILES)
+    mid2exp_coord_map = grid + m2e_flow
+
+    img10, a10 = fused.blend_records(rec[exp], radii[exp], depths[exp], bg10, 10, W, H, tight=TIGHT_TILES)
+    latent_img, _ = _decode(dyn_pc, img10, a10, cam)
+    return exp2mid_coord_map, mid2exp_coord_map, latent_img, latent_alpha
+
+
+def get_flow_static(source_camera, target_camera, splat_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor):
+    """Reference: gaussian_renderer/__init__.py:494-552."""
+    means, quats = stat_pc.get_xyz, stat_pc._rotation
+    scales, opac = stat_pc.get_scaling, stat_pc.get_opacity.squeeze(-1)
+    W, H = int(source_camera.image_width), int(source_camera.image_height)
+    Kmat = source_camera.K
+    views = torch.stack([source_camera.world_view_transform.transpose(0, 1),
+                         target_camera.world_view_transform.transpose(0, 1)])
+    _, m2d, _, _ = ops.project(means, quats, scales, views, torch.stack([Kmat, Kmat]), W, H)
+    flow_2d = m2d[0] - m2d[1]
+    Ws, Hs = int(splat_camera.image_width), int(splat_camera.image_height)
+    radii, sm2d, sdep, scon = ops.project(means, quats, scales,
+                                          splat_camera.world_view_transform.transpose(0, 1)[None], Kmat[None], Ws, Hs)
+    rendered_flow, _ = ops.rasterize(sm2d, scon, flow_2d, opac, None, sdep, radii, Ws, Hs, tight=TIGHT_TILES)
+    return flow_2d, rendered_flow

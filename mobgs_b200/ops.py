@@ -111,7 +111,7 @@ class TileLists:
         self.K, self.width, self.height = K, width, height
 
 
-def build_tile_lists(records, radii, depths, width, height, tight=True) -> TileLists:
+def build_tile_lists(records, radii, depths, width, height, tight=True, g_range=None) -> TileLists:
     """mobgs_tile_count -> (one 4-byte read-back of I) -> mobgs_tile_emit_sort."""
     K, N = radii.shape
     dev = records.device
@@ -119,14 +119,15 @@ def build_tile_lists(records, radii, depths, width, height, tight=True) -> TileL
     nt = K * tiles
     counts = torch.empty(nt, dtype=torch.int32, device=dev)
     offsets = torch.empty(nt + 1, dtype=torch.int32, device=dev)
-    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), _p(counts), _p(offsets))
+    g0, g1 = (0, N) if g_range is None else (int(g_range[0]), int(g_range[1]))
+    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), g0, g1, _p(counts), _p(offsets))
     L.call("mobgs_tile_count", a, _stream())
     n_isect = int(offsets[-1].item())
     cap = max(n_isect, 1)
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
     keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
     sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
-    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), _p(offsets),
+    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), g0, g1, _p(offsets),
                    _p(counts), n_isect, _p(keys), _p(keys_tmp), _p(sorted_ids))
     L.call("mobgs_tile_emit_sort", b, _stream())
     return TileLists(offsets, sorted_ids, n_isect, K, width, height)
