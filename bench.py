@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py — the MoBGS render + deblur hot path on B200.
+
+One "step" = one blurry training view: K latent sub-frames rendered in one launch chain
+(synth+project -> tile bin/sort -> blend -> decode+mean), L1 loss against a target image, full
+backward to every Gaussian / decoder / pose gradient.  At N>1 every rank renders its own view
+(data parallel over views; parameters replicated) and the flat Gaussian-gradient buffer is
+all-reduced over NCCL — weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every key.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_static, n_dynamic, width, height, K)
+    "c1_1k_128_K1": (700, 300, 128, 128, 1),                 # BASELINE configs[0] (CPU-runnable)
+    "c2_200k_960x540_K7": (140_000, 60_000, 960, 540, 7),     # configs[1]
+    "c3_500k_960x540_K7": (350_000, 150_000, 960, 540, 7),    # configs[2]
+    "c4_1M_1080p_K7": (700_000, 300_000, 1920, 1080, 7),      # the metric's "1M Gaussians K=7"
+    "c4_1M_1080p_K9": (700_000, 300_000, 1920, 1080, 9),      # configs[3]
+}
+DEFAULT_WORKLOAD = "c4_1M_1080p_K7"
+METRIC = "rendered_Mpix_per_s_train_step"   # K*H*W / (fwd+loss+bwd time); ms_per_step = train-step ms
+HBM_PEAK_FALLBACK = 6650.0                  # GB/s, B200_PROFILING.md fallback
+
+
+def _peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return HBM_PEAK_FALLBACK, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (oracle/), bounded sample
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step_factory(sample):
+    """Returns (step_fn, pixels_per_step, description).  One step = K sub-frame oracle renders of
+    the sample scene + blur mean + L1 + backward, on all host cores."""
+    import torch
+    from oracle import mobgs_ref as M
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    ns, nd, W, H, K = sample
+    torch.set_num_threads(os.cpu_count() or 1)
+    stat, dyn, intr = synthetic_scene(ns, nd, W, H, seed=1234)
+    cams = [make_camera(intr, subframe_w2c(k, K)) for k in range(K)]
+    deltas = (torch.linspace(-1, 1, K) * 0.4).tolist() if K > 1 else [0.0]
+    bg = torch.zeros(3)
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(7))
+
+    def step():
+        for pc in (stat, dyn):
+            for p in pc.parameters():
+                p.grad = None
+        imgs = [M.render_ref(cams[k], stat, dyn, None, bg, delta_exposure=deltas[k])["render"] for k in range(K)]
+        loss = (M.blur_mean(imgs) - tgt).abs().mean()
+        loss.backward()
+        return float(loss.detach())
+
+    desc = f"oracle port (pure PyTorch fp32), {ns + nd} Gaussians, {W}x{H}, K={K}, fwd+L1+bwd"
+    return step, K * W * H, desc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = WORKLOADS["c1_1k_128_K1"]
+    step, pix, desc = cpu_reference_step_factory(sample)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = pix / dt / 1e6
+    cores = os.cpu_count() or 1
+    ns, nd, W, H, K = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "gaussians": ns + nd, "width": W, "height": H, "subframes": K,
+                   "note": "reference arm = CPU oracle port of the gsplat-1.4.0 + MoBGS renderer path on a "
+                           "bounded sample (gsplat itself is not installable here); throughput in Mpix/s "
+                           "is size-normalised"},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def build_rays(viewmats, intr, W, H):
+    """Camera.cam_ray for K cameras on the device (scene/cameras.py:132-146): [K,6,H,W]."""
+    import torch
+    dev = viewmats.device
+    c2w = torch.inverse(viewmats)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev) + 0.5,
+                            torch.arange(W, dtype=torch.float32, device=dev) + 0.5, indexing="ij")
+    d = torch.stack([(xs - intr.cx) / intr.fx, (ys - intr.cy) / intr.fy, torch.ones_like(xs)], dim=-1)
+    d = d / d.norm(dim=-1, keepdim=True)
+    d = torch.einsum("hwj,kij->khwi", d, c2w[:, :3, :3])
+    o = c2w[:, None, None, :3, 3].expand_as(d)
+    return torch.cat([o, d], dim=-1).permute(0, 3, 1, 2).contiguous()
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mobgs_b200 import _lib
+    from mobgs_b200.scene import subframe_w2c, synthetic_scene
+    from mobgs_b200.subframes import render_subframes
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    ns, nd, W, H, K = WORKLOADS[args.workload]
+    N = ns + nd
+    stat, dyn, intr = synthetic_scene(ns, nd, W, H, seed=1234, device=dev)   # same replica on every rank
+    all_params = [p for pc in (stat, dyn) for p in pc.parameters() if p.requires_grad]
+    gen = torch.Generator().manual_seed(100 + rank)          # each rank: its own view
+    tgt_host = torch.rand(3, H, W, generator=gen).pin_memory()
+    base_time = 0.3 + 0.4 * float(torch.rand(1, generator=gen))
+    yaw = 0.5 * (rank - (world - 1) / 2)                       # degrees
+    view_host = torch.stack([subframe_w2c(k, K) for k in range(K)])
+    a = math.radians(yaw)
+    R = torch.eye(4); R[0, 0], R[0, 2], R[2, 0], R[2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+    view_host = (view_host @ R).contiguous().pin_memory()
+    deltas = torch.linspace(-1, 1, K) * 0.4 if K > 1 else torch.zeros(1)
+    tpoly_host = (base_time + deltas / 23).pin_memory()
+    Kmat = torch.tensor([[intr.fx, 0, intr.cx], [0, intr.fy, intr.cy], [0, 0, 1.0]], device=dev)
+    bg = torch.zeros(3, device=dev)
+
+    # device-resident copies for the kernel-side ("value") measurement
+    tgt_d, view_d, tpoly_d = tgt_host.to(dev), view_host.to(dev), tpoly_host.to(dev)
+    rays_d = build_rays(view_d, intr, W, H)
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
+
+    stats = {}
+
+    def step(resident: bool):
+        for p in all_params:
+            p.grad = None
+        if resident:
+            view, tpoly, tgt, rays = view_d, tpoly_d, tgt_d, rays_d
+        else:   # e2e: host buffers in, loss out
+            view = view_host.to(dev, non_blocking=True)
+            tpoly = tpoly_host.to(dev, non_blocking=True)
+            tgt = tgt_host.to(dev, non_blocking=True)
+            rays = build_rays(view, intr, W, H)
+        view = view.requires_grad_(True) if resident else view.clone().requires_grad_(True)
+        out = render_subframes(stat, dyn, view, Kmat, tpoly.clamp(0, 1), tpoly, rays, bg, W, H)
+        loss = (out["render"] - tgt).abs().mean()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in all_params if p.grad is not None])
+            dist.all_reduce(flat)
+            stats["allreduce_bytes"] = flat.numel() * 4
+        view.grad = None
+        stats["out"] = out
+        if not resident:
+            return float(loss.detach())          # D2H read of the step's result
+        return loss
+
+    def timed(resident, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            step(resident)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for _ in range(steps):
+            flush.zero_()                      # evict L2 between timed iterations (untimed)
+            e0.record()
+            step(resident)
+            e1.record()
+            e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([tot], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot = float(t)
+        return tot / steps, clocks
+
+    # ---- kernel-side throughput: inputs resident in HBM ----
+    _lib.TIMING = {}
+    _lib.LAUNCH_COUNT = 0
+    for _ in range(args.warmup):
+        step(True)
+    torch.cuda.synchronize()
+    _lib.TIMING = {}
+    _lib.LAUNCH_COUNT = 0
+    ms, clocks = timed(True, args.steps, 0, sample_clocks=True)
+    launches = _lib.LAUNCH_COUNT
+    kernel_ms = {n: sum(a.elapsed_time(b) for a, b in ev) / args.steps for n, ev in _lib.TIMING.items()}
+    _lib.TIMING = None
+
+    # ---- algorithmic bytes of the dominant kernels (I_eff measured from the forward outputs) ----
+    ieff, itot = measure_intersections(stat, dyn, view_d, Kmat, tpoly_d, W, H)
+    P = K * W * H
+    bytes_fwd = 68.0 * ieff + 48.0 * P
+    bytes_bwd = 132.0 * ieff + 52.0 * P
+    peak, peak_kind = _peak()
+    dom = max(("mobgs_blend_fwd", "mobgs_blend_bwd"), key=lambda n: kernel_ms.get(n, 0.0))
+    dom_bytes = bytes_bwd if dom == "mobgs_blend_bwd" else bytes_fwd
+    ach = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "ms_per_launch": kernel_ms[dom], "algorithmic_bytes": dom_bytes,
+                "intersections_consumed": ieff, "intersections_listed": itot, "pixels": P,
+                "note": "blend kernels are FP32-issue/MUFU bound, not HBM bound (DESIGN.md); HBM fraction "
+                        "reported as BASELINE.json's north_star asks"}
+
+    # ---- end to end through the public API with host buffers ----
+    e2e_ms, _ = timed(False, args.steps, max(1, args.warmup // 2))
+    h2d = tgt_host.numel() * 4 + view_host.numel() * 4 + tpoly_host.numel() * 4
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cstep, cpix, cdesc = cpu_reference_step_factory(WORKLOADS["c1_1k_128_K1"])
+            cstep()
+            t0 = time.perf_counter()
+            n = 0
+            while n < 2 or time.perf_counter() - t0 < 12.0:
+                cstep(); n += 1
+            cdt = (time.perf_counter() - t0) / n
+            cpu = {"value": cpix / cdt / 1e6, "unit": "Mpix/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": cdesc + f" ({n} steps, {cdt * 1e3:.0f} ms each)"}
+        line = {
+            "metric": METRIC, "value": world * P / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "gaussians": N, "static": ns, "dynamic": nd, "width": W,
+                       "height": H, "subframes": K, "views_per_step": world, "parallelism": f"dp{world}_views",
+                       "l2": "flushed between timed iterations (192 MB memset, untimed)",
+                       "step": "K-sub-frame render + decode + blur mean + L1 + full backward"
+                               + (" + NCCL all-reduce of Gaussian gradients" if world > 1 else "")},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": world * P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "clocks": clocks,
+        }
+        if world > 1:
+            line["allreduce_bytes_per_step"] = stats.get("allreduce_bytes")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_intersections(stat, dyn, view, Kmat, tpoly, W, H):
+    """I (listed) and I_eff (list entries up to the last one any pixel of the tile blended)."""
+    import torch
+    from mobgs_b200 import fused
+    from mobgs_b200.gaussian_renderer import _dynamic_params, _static_params
+    from mobgs_b200.ops import build_tile_lists
+    from mobgs_b200 import _lib as L
+    with torch.no_grad():
+        K = view.shape[0]
+        rec, radii, depths, _ = fused.synth_project(_static_params(stat), _dynamic_params(dyn),
+                                                    dyn.current_control_num, view, Kmat[None].expand(K, -1, -1),
+                                                    tpoly.clamp(0, 1), tpoly, W, H)
+        lists = build_tile_lists(rec, radii, depths, W, H, True)
+        _, _, last = fused._BlendRecords.apply(rec, radii, depths, None, None, 10, W, H, None, True, 0)
+        tx, ty = math.ceil(W / 16), math.ceil(H / 16)
+        pad = torch.full((K, ty * 16, tx * 16), -1, dtype=torch.int32, device=rec.device)
+        pad[:, :H, :W] = last
+        tile_last = pad.reshape(K, ty, 16, tx, 16).permute(0, 1, 3, 2, 4).reshape(K * ty * tx, 256).max(dim=1).values
+        beg = lists.tile_offsets[:-1]
+        ieff = torch.clamp(tile_last - beg + 1, min=0).sum().item()
+    return float(ieff), float(lists.n_isect)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

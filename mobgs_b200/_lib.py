@@ -212,9 +212,32 @@ def load() -> C.CDLL:
         return lib
 
 
+# kernels launched per entry point (memsets excluded) — bench.py's `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "mobgs_project_fwd": 1, "mobgs_project_bwd": 1, "mobgs_synth_project_fwd": 1,
+    "mobgs_synth_project_bwd": 1, "mobgs_pack_records": 1, "mobgs_tile_count": 2,
+    "mobgs_tile_emit_sort": 2, "mobgs_blend_fwd": 1, "mobgs_blend_bwd": 1,
+    "mobgs_decode_fwd": 1, "mobgs_decode_bwd": 1,
+}
+LAUNCH_COUNT = 0
+# optional per-entry-point device timing: TIMING = {} enables it; values are lists of
+# (start_event, end_event) recorded on the launching stream (bench.py reads them after a sync)
+TIMING = None
+
+
 def call(name: str, args: C.Structure, stream: int) -> None:
+    global LAUNCH_COUNT
     lib = load()
-    rc = getattr(lib, name)(C.byref(args), C.c_void_p(stream))
+    LAUNCH_COUNT += KERNELS_PER_CALL.get(name, 1)
+    if TIMING is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream())
+        rc = getattr(lib, name)(C.byref(args), C.c_void_p(stream))
+        e1.record(torch.cuda.current_stream())
+        TIMING.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, name)(C.byref(args), C.c_void_p(stream))
     if rc != 0:
         msg = lib.mobgs_last_error().decode()
         raise RuntimeError(f"{name} failed (code {rc}): {msg}")

@@ -176,9 +176,11 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
         if (sigma < 0.f || alpha < kAlphaMin) valid = false;
       }
       if (!__any_sync(0xffffffffu, valid)) continue;
-      float g[6 + D];   // v_x v_y v_opac v_ca v_cb v_cc v_col[D]
+      // v_x v_y v_opac v_ca v_cb v_cc v_col[D], zero-padded to a power of two
+      constexpr int NV = (6 + D) <= 8 ? 8 : 16;
+      float g[NV];
 #pragma unroll
-      for (int c = 0; c < 6 + D; ++c) g[c] = 0.f;
+      for (int c = 0; c < NV; ++c) g[c] = 0.f;
       if (valid) {
         float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
         if (D > 2) r2 = srec[t][2];
@@ -205,12 +207,33 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
           g[5] = 0.5f * v_sigma * dy * dy;
         }
       }
+      // Transposing butterfly: each stage halves the number of live values per lane while doubling
+      // the lanes summed, so NV values cost NV shuffles in total (not 5 * NV); afterwards lane l
+      // holds the complete sum of value index bits(l) and the lanes add to shared memory in parallel.
+      int vidx = 0;
+      {
+        int n = NV / 2;
 #pragma unroll
-      for (int c = 0; c < 6 + D; ++c) g[c] = warp_sum(g[c]);
-      if (lane == 0) {
+        for (int o = 16; o >= 1; o >>= 1) {
+          if (n >= 1) {
+            const bool up = (lane & o) != 0;
 #pragma unroll
-        for (int c = 0; c < 6 + D; ++c) atomicAdd(&sacc[t][c], g[c]);
+            for (int i = 0; i < NV / 2; ++i) {
+              if (i < n) {
+                const float send = up ? g[i] : g[i + n];
+                const float keep = up ? g[i + n] : g[i];
+                g[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              }
+            }
+            vidx += up ? n : 0;
+            n >>= 1;
+          } else {
+            g[0] += __shfl_xor_sync(0xffffffffu, g[0], o);
+          }
+        }
       }
+      constexpr int kOwnerMask = NV == 16 ? 1 : 3;   // lanes whose low bits are 0 own a value
+      if ((lane & kOwnerMask) == 0 && g[0] != 0.f) atomicAdd(&sacc[t][vidx], g[0]);
     }
     __syncthreads();
     if (tid < bn) {

@@ -117,8 +117,11 @@ class PinholeCamera:
 
 
 def synthetic_scene(n_static: int, n_dynamic: int, width: int, height: int, seed: int = 1234,
-                    device="cpu", requires_grad: bool = True):
-    """Seeded synthetic Gaussians of SURVEY.md §8d: depths U(2,10), ~2-10 px footprints."""
+                    device="cpu", requires_grad: bool = True, footprint_px=(0.4608, 2.304)):
+    """Seeded synthetic Gaussians of SURVEY.md §8d: depths U(2,10), ~2-10 px radius footprints.
+    `footprint_px` = range of the projected 1-sigma size in pixels; the default equals the spec's
+    log-scale ~ U(ln 0.004 z, ln 0.02 z) at 128 px width (fx = 115.2) and keeps the same pixel
+    footprint at every resolution."""
     g = torch.Generator().manual_seed(seed)
     fx = fy = 0.9 * width
     cx, cy = width / 2, height / 2
@@ -131,7 +134,7 @@ def synthetic_scene(n_static: int, n_dynamic: int, width: int, height: int, seed
         x = (rand(n) * 2 - 1) * 1.2 * (width / 2 / fx) * z
         y = (rand(n) * 2 - 1) * 1.2 * (height / 2 / fy) * z
         xyz = torch.stack([x, y, z], -1)
-        lo, hi = torch.log(0.004 * z)[:, None], torch.log(0.02 * z)[:, None]
+        lo, hi = torch.log(footprint_px[0] / fx * z)[:, None], torch.log(footprint_px[1] / fx * z)[:, None]
         scaling = lo + (hi - lo) * rand(n, 3)
         return xyz, scaling, randn(n, 4), 2 * randn(n, 1), rand(n, 6)
 

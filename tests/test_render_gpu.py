@@ -152,3 +152,41 @@ def test_blur_model_subframe_mean():
     (pc - tgt.cuda()).abs().mean().backward()
     (po - tgt).abs().mean().backward()
     _check_param_grads(sc, dc, so, do)
+
+
+def test_render_subframes_batched_equals_looped_oracle():
+    """One K-batched launch chain == K oracle render() calls + the blur mean, gradients included
+    (parameters, decoder, per-sub-frame view matrices, densification gradient of the centre)."""
+    from mobgs_b200.subframes import render_subframes
+    K, W, H = 5, 112, 80
+    so, do, intr = synthetic_scene(500, 300, W, H, seed=8)
+    sc, dc, _ = synthetic_scene(500, 300, W, H, seed=8, device="cuda")
+    bg = torch.tensor([0.1, 0.2, 0.3])
+    deltas = torch.linspace(-1, 1, K) * 0.4
+    w2c_o = [subframe_w2c(k, K).clone().requires_grad_(True) for k in range(K)]
+    cams_o = [make_camera(intr, w.detach()) for w in w2c_o]
+    imgs, depths = [], []
+    vsp_o = None
+    for k in range(K):
+        out = M.render_ref(cams_o[k], so, do, None, bg, w2c=w2c_o[k], delta_exposure=deltas[k].item())
+        imgs.append(out["render"]); depths.append(out["depth"])
+        if k == K // 2:
+            vsp_o = out["viewspace_points"]
+    pred_o = M.blur_mean(imgs)
+
+    view_c = torch.stack([w.detach() for w in w2c_o]).cuda().requires_grad_(True)
+    t0 = torch.full((K,), 0.5)
+    t_poly = (t0 + deltas / 23).cuda()
+    t_spline = t_poly.clamp(0, 1)
+    rays = torch.cat([c.cam_ray for c in cams_o]).cuda()
+    out_c = render_subframes(sc, dc, view_c, cams_o[0].K.cuda(), t_spline, t_poly, rays, bg.cuda(), W, H)
+    _close(out_c["render"], pred_o, "blurred render", scale_atol=False)
+    _close(out_c["depth"], torch.cat(depths), "depth", atol=2e-4, scale_atol=False, max_outlier_frac=1e-3)
+    g = torch.Generator().manual_seed(3)
+    tgt = torch.rand(pred_o.shape, generator=g)
+    wd = torch.rand(K, H, W, generator=g) * 0.1
+    ((out_c["render"] - tgt.cuda()).abs().mean() + (out_c["depth"] * wd.cuda()).mean()).backward()
+    ((pred_o - tgt).abs().mean() + (torch.cat(depths) * wd).mean()).backward()
+    _check_param_grads(sc, dc, so, do)
+    _close(view_c.grad[:, :3], torch.stack([w.grad for w in w2c_o])[:, :3], "v_viewmats", rtol=5e-3)
+    _close(out_c["viewspace_points"].grad, vsp_o.grad, "viewspace grad", max_outlier_frac=1e-3)
