@@ -53,7 +53,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.mark = [], None, index, 0
+
+    def mark_start(self):
+        """rows sampled from here on belong to the timed region"""
+        self.mark = len(self.rows)
 
     def start(self):
         try:
@@ -78,7 +82,8 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for r in self.rows:
+        rows = self.rows[self.mark:] or self.rows[-1:]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
@@ -235,15 +240,20 @@ def run_ours(args):
         return loss
 
     def timed(resident, steps, warmup, sample_clocks=False):
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()            # nvidia-smi needs a few 100 ms to deliver its first row
         for _ in range(warmup):
             step(resident)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if sample_clocks else None
         if sampler:
-            sampler.start()
+            sampler.mark_start()
+        if resident:
+            _lib.TIMING = {}
+            _lib.LAUNCH_COUNT = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tot = 0.0
         for _ in range(steps):
@@ -268,9 +278,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(True)
     torch.cuda.synchronize()
-    _lib.TIMING = {}
-    _lib.LAUNCH_COUNT = 0
-    ms, clocks = timed(True, args.steps, 0, sample_clocks=True)
+    ms, clocks = timed(True, args.steps, 3, sample_clocks=True)
     launches = _lib.LAUNCH_COUNT
     kernel_ms = {n: sum(a.elapsed_time(b) for a, b in ev) / args.steps for n, ev in _lib.TIMING.items()}
     _lib.TIMING = None
@@ -354,7 +362,7 @@ def measure_intersections(stat, dyn, view, Kmat, tpoly, W, H):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))

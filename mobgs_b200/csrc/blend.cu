@@ -17,7 +17,29 @@ namespace mobgs {
 
 constexpr int kBlendThreads = kTilePix;   // 256
 
-struct TileCoord { int k, tile, tx, ty; };
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kNegLog2e = -1.4426950408889634f;
+
+// Which of the tile's eight 16x2-pixel strips (= warps) can a Gaussian reach with alpha >= 1/255?
+// The ellipse sigma <= tau = log(255 opac) has vertical half-extent sqrt(2 tau * ca / det(conic)).
+// A strip outside it contributes nothing, so its warp skips the Gaussian without evaluating it.
+__device__ __forceinline__ unsigned strip_mask(const float4& r0, const float4& r1, float tile_y0) {
+  const float tau = __logf(255.f * r0.z) + 0.01f;
+  if (!(tau >= 0.f)) return 0u;
+  const float det = r0.w * r1.y - r1.x * r1.x;
+  if (!(det > 0.f)) return 0xffu;
+  const float ey = sqrtf(2.f * tau * r0.w / det) + 1e-3f;
+  const float lo = r0.y - ey - tile_y0, hi = r0.y + ey - tile_y0;   // tile-local pixel-centre range
+  unsigned m = 0u;
+#pragma unroll
+  for (int w = 0; w < 8; ++w)
+    if (hi >= 2.f * w + 0.5f && lo <= 2.f * w + 1.5f) m |= 1u << w;
+  return m;
+}
 
 __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, const float4& r3, int c) {
   switch (c) {
@@ -30,10 +52,12 @@ __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, c
 template <int D>
 __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
+  __shared__ unsigned smask[kBlendThreads];
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x;
+  const unsigned wbit = 1u << (tid >> 5);
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -52,17 +76,20 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd 
     const int idx = b0 + tid;
     if (idx < end) {
       const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
-      srec[tid][0] = __ldg(r); srec[tid][1] = __ldg(r + 1);
+      const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
+      srec[tid][0] = q0; srec[tid][1] = q1;
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
+      smask[tid] = strip_mask(q0, q1, (float)(ty * kTile));
     }
     __syncthreads();
     const int bn = min(kBlendThreads, end - b0);
     for (int t = 0; t < bn && !done; ++t) {
+      if (!(smask[t] & wbit)) continue;     // warp-uniform: this strip cannot reach alpha >= 1/255
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
       const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-      const float alpha = fminf(kAlphaMax, r0.z * __expf(-sigma));
+      const float alpha = fminf(kAlphaMax, r0.z * ex2_approx(sigma * kNegLog2e));
       if (sigma < 0.f || alpha < kAlphaMin) continue;
       const float next_T = T * (1.f - alpha);
       if (next_T <= kTStop) { done = true; break; }
@@ -103,11 +130,13 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
+  __shared__ unsigned smask[kBlendThreads];
   __shared__ int warp_max[kBlendThreads / 32];
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned wbit = 1u << (tid >> 5);
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -116,10 +145,10 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
   float* v_recs = a.v_records + (size_t)k * a.N * kRecFloats;
 
   float T_final = 1.f, v_a = 0.f, bg_dot = 0.f;
-  float v_c[D], buf[D];
+  float v_c[D];
   int last = -1;
 #pragma unroll
-  for (int c = 0; c < D; ++c) { v_c[c] = 0.f; buf[c] = 0.f; }
+  for (int c = 0; c < D; ++c) v_c[c] = 0.f;
   if (inside) {
     const size_t p = ((size_t)k * a.height + iy) * a.width + ix;
     T_final = 1.f - a.out_alphas[p];
@@ -135,6 +164,10 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
     }
   }
   float T = T_final;
+  // S = sum_c v_c[c] * (colour accumulated behind the current Gaussian): the only thing the VJP needs
+  // from gsplat's per-channel `buffer`, kept as one scalar.
+  float S = 0.f;
+  const float tf_term = T_final * (v_a - bg_dot);
   // last list entry any pixel of this tile blended
   int wmax = last;
 #pragma unroll
@@ -155,26 +188,25 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
       const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
       sid[tid] = g;
       const float4* r = recs + (size_t)g * 4;
-      srec[tid][0] = __ldg(r); srec[tid][1] = __ldg(r + 1);
+      const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
+      srec[tid][0] = q0; srec[tid][1] = q1;
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
+      smask[tid] = strip_mask(q0, q1, (float)(ty * kTile));
     }
 #pragma unroll
     for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
     __syncthreads();
     // entries above this warp's furthest pixel contribute nothing: skip them warp-uniformly
     for (int t = max(0, hi - wmax); t < bn; ++t) {
+      if (!(smask[t] & wbit)) continue;     // warp-uniform strip cull
       const int idx = hi - t;
-      bool valid = inside && idx <= last;
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
-      float vis = 0.f, alpha = 0.f;
-      if (valid) {
-        const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-        vis = __expf(-sigma);
-        alpha = fminf(kAlphaMax, r0.z * vis);
-        if (sigma < 0.f || alpha < kAlphaMin) valid = false;
-      }
+      const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+      const float vis = ex2_approx(sigma * kNegLog2e);
+      const float alpha = fminf(kAlphaMax, r0.z * vis);
+      const bool valid = inside && idx <= last && sigma >= 0.f && alpha >= kAlphaMin;
       if (!__any_sync(0xffffffffu, valid)) continue;
       // v_x v_y v_opac v_ca v_cb v_cc v_col[D], zero-padded to a power of two
       constexpr int NV = (6 + D) <= 8 ? 8 : 16;
@@ -185,18 +217,17 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
         float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
         if (D > 2) r2 = srec[t][2];
         if (D > 6) r3 = srec[t][3];
-        const float ra = 1.f / (1.f - alpha);
+        const float ra = __fdividef(1.f, 1.f - alpha);
         T *= ra;
         const float fac = alpha * T;
-        float v_alpha = 0.f;
+        float d = 0.f;
 #pragma unroll
         for (int c = 0; c < D; ++c) {
-          const float col = rec_color(r1, r2, r3, c);
+          d += rec_color(r1, r2, r3, c) * v_c[c];
           g[6 + c] = fac * v_c[c];
-          v_alpha += (col * T - buf[c] * ra) * v_c[c];
-          buf[c] += col * fac;
         }
-        v_alpha += T_final * ra * (v_a - bg_dot);
+        const float v_alpha = d * T + (tf_term - S) * ra;
+        S += d * fac;
         if (r0.z * vis <= kAlphaMax) {
           const float v_sigma = -r0.z * vis * v_alpha;
           g[0] = v_sigma * (r0.w * dx + r1.x * dy);
