@@ -1,0 +1,9 @@
+"""Import-only placeholder for `flow_vis` (not on the hot path)."""
+
+
+class EasyDict(dict):
+    __getattr__ = dict.get
+
+
+def __getattr__(name):
+    raise AttributeError(name)

@@ -1,0 +1,172 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference Python from /root/reference.
+
+Runs only in the build container (it needs /root/reference); the fixtures it writes are what
+travels to the GPU box.  Two families:
+
+  render_*.npz   reference gaussian_renderer.render / get_flow / get_flow_static (source file
+                 executed as-is) on the seeded stand-in scene of mobgs_b200.scene, with
+                 `gsplat.rendering` routed to the CPU oracle (compat/gsplat, backend "oracle") and
+                 the reference's own helper_model.Sandwich as the decoder.  This pins everything
+                 *around* the two gsplat operators (spline, activations, concat order, decoder,
+                 flow wiring, dict keys) to the reference's own code.
+  hexplane_*.npz reference scene.deformation.deform_network (HexPlaneField + MLP heads, net_width 128,
+                 3 levels x 6 planes x 32 features as in arguments/stereo/*.py but base resolution
+                 16 instead of 64 to keep the fixture small), imported and run on CPU: inputs,
+                 state_dict, outputs and gradients.
+
+The reference hard-codes `.cuda()` / device="cuda" in the renderer; on this
+GPU-less container those calls are redirected to the CPU through a proxy of the `torch` module
+object *inside the imported reference module only* — the reference source is not edited.
+
+    MOBGS_GSPLAT_BACKEND=oracle python tools/make_golden.py
+"""
+import os
+import sys
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+os.environ["MOBGS_GSPLAT_BACKEND"] = "oracle"
+sys.path[:0] = [os.path.join(ROOT, "compat"), ROOT, REF]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+class _TorchCPU(types.ModuleType):
+    """`torch` as seen by the reference renderer module: device='cuda' -> CPU, nothing else."""
+
+    def __init__(self):
+        super().__init__("torch")
+
+    def __getattr__(self, name):
+        attr = getattr(torch, name)
+        if name in ("ones", "zeros", "tensor", "empty"):
+            def wrapped(*a, **k):
+                if k.get("device") == "cuda":
+                    k.pop("device")
+                return attr(*a, **k)
+            return wrapped
+        return attr
+
+
+def load_reference_renderer():
+    torch.Tensor.cuda = lambda self, *a, **k: self          # .cuda() is a no-op on this box
+    import gaussian_renderer as ref
+    assert ref.__file__.startswith(REF), ref.__file__
+    ref.torch = _TorchCPU()
+    return ref
+
+
+def reference_decoder(weights_from):
+    from helper_model import Sandwich
+    dec = Sandwich(9, 3)
+    dec.load_state_dict(weights_from.state_dict())
+    return dec
+
+
+def _np(v):
+    return None if v is None else v.detach().cpu().numpy()
+
+
+RENDER_CASES = {
+    # name: (ns, nd, W, H, seed, time, kwargs)
+    "render_plain": (220, 120, 64, 48, 11, 0.5, dict(get_static=True, get_dynamic=True)),
+    "render_warped_flow": (220, 120, 64, 48, 12, 0.35, dict(get_static=True, get_dynamic=True,
+                                                            delta_exposure=0.4, get_flow=True)),
+    "render_time_clamped": (150, 100, 48, 48, 13, 0.97, dict(delta_exposure=1.0)),
+}
+
+
+def make_render_goldens(out_dir):
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    ref = load_reference_renderer()
+    bg = torch.tensor([0.1, 0.4, 0.8, 1.0])
+    for name, (ns, nd, W, H, seed, t, kw) in RENDER_CASES.items():
+        stat, dyn, intr = synthetic_scene(ns, nd, W, H, seed=seed)
+        dyn.rgbdecoder = reference_decoder(dyn.rgbdecoder)
+        cam = make_camera(intr, subframe_w2c(1, 4), time=t)
+        out = ref.render(cam, stat, dyn, None, bg, **kw)
+        keys = ["render", "s_render", "s_depth", "d_render", "d_depth", "d_alpha", "s_alpha", "depth",
+                "viewspace_points", "radii", "means_3d_final", "colors_precomp_final", "ori_flow",
+                "ori_coord_map", "means_3d"]
+        loss = out["render"].sum() + 0.1 * out["depth"].sum()
+        if out["d_alpha"] is not None:
+            loss = loss + out["d_alpha"].sum() + out["s_render"].mean()
+        if out["ori_flow"] is not None:
+            loss = loss + 0.01 * out["ori_flow"].sum()
+        loss.backward()
+        blob = {"out_" + k: _np(out[k]) for k in keys if out[k] is not None}
+        blob.update({"grad_stat" + n: _np(getattr(stat, n).grad) for n in
+                     ("_xyz", "_rotation", "_scaling", "_opacity", "_features_dc")})
+        blob.update({"grad_dyn" + n: _np(getattr(dyn, n).grad) for n in
+                     ("control_xyz", "_rotation", "_omega", "_scaling", "_opacity", "_features_dc", "_features_t")})
+        blob["grad_viewspace"] = _np(out["viewspace_points"].grad)
+        blob["grad_dec1"] = _np(dyn.rgbdecoder.mlp1.weight.grad)
+        blob["grad_dec2"] = _np(dyn.rgbdecoder.mlp2.weight.grad)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), **blob)
+        print("wrote", name, {k: v.shape for k, v in blob.items() if k.startswith("out_")})
+
+    # get_flow / get_flow_static
+    stat, dyn, intr = synthetic_scene(200, 150, 64, 48, seed=21)
+    dyn.rgbdecoder = reference_decoder(dyn.rgbdecoder)
+    cam = make_camera(intr, subframe_w2c(2, 4), time=0.45)
+    e2m, m2e, limg, lalpha = ref.get_flow(cam, stat, dyn, None, bg, delta_exposure=-0.7)
+    cams = [make_camera(intr, subframe_w2c(k, 5)) for k in (0, 4, 2)]
+    with torch.no_grad():
+        f2d, rflow = ref.get_flow_static(*cams, stat, dyn, None, bg)
+    np.savez_compressed(os.path.join(out_dir, "get_flow.npz"), exp2mid=_np(e2m), mid2exp=_np(m2e),
+                        latent_img=_np(limg), latent_alpha=_np(lalpha), static_flow_2d=_np(f2d),
+                        static_rendered_flow=_np(rflow))
+    print("wrote get_flow")
+
+
+def make_hexplane_golden(out_dir):
+    from argparse import Namespace
+    from scene.deformation import deform_network
+    torch.manual_seed(5)
+    args = Namespace(net_width=128, timebase_pe=4, defor_depth=1, posebase_pe=10, scale_rotation_pe=2,
+                     opacity_pe=2, timenet_width=64, timenet_output=32, bounds=1.6, grid_pe=0,
+                     kplanes_config={"grid_dimensions": 2, "input_coordinate_dim": 4,
+                                     "output_coordinate_dim": 32, "resolution": [16, 16, 16, 6]},
+                     multires=[1, 2, 4], no_dx=False, no_grid=False, no_ds=False, no_dr=False, no_do=True,
+                     no_dshs=True, empty_voxel=False, static_mlp=False, apply_rotation=False)
+    net = deform_network(args)
+    # non-trivial planes / biases (time planes initialise to 1, biases to 0)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+        for g in net.deformation_net.grid.grids:
+            for plane in g:
+                plane.add_(0.05 * torch.randn_like(plane))
+    net.deformation_net.set_aabb([1.2, 1.0, 1.4], [-1.3, -0.9, -1.1])
+    n = 257
+    pts = torch.rand(n, 3) * 3.0 - 1.5          # some outside the AABB -> clamped
+    scales = torch.randn(n, 3) * 0.3 - 3.0
+    rots = torch.randn(n, 4)
+    t = torch.rand(n, 1)
+    t[:8, 0] = torch.tensor([0.0, 1.0, 0.5, 0.25, 0.999, 1e-4, 0.75, 0.1])
+    pts.requires_grad_(True)
+    p2, s2, r2 = net(pts, scales, rots, t)
+    w = torch.randn(n, 10, generator=torch.Generator().manual_seed(1))
+    loss = (p2 * w[:, :3]).sum() + (s2 * w[:, 3:6]).sum() + (r2 * w[:, 6:]).sum()
+    loss.backward()
+    blob = {"in_pts": _np(pts), "in_scales": _np(scales), "in_rots": _np(rots), "in_t": _np(t),
+            "out_pts": _np(p2), "out_scales": _np(s2), "out_rots": _np(r2), "loss_w": _np(w),
+            "grad_pts": _np(pts.grad)}
+    sd = net.state_dict()
+    for k, v in sd.items():
+        blob["sd::" + k] = _np(v)
+    for k, p in net.named_parameters():
+        if p.grad is not None:
+            blob["pgrad::" + k] = _np(p.grad)
+    np.savez_compressed(os.path.join(out_dir, "hexplane_w128.npz"), **blob)
+    print("wrote hexplane", {k: v.shape for k, v in blob.items() if not k.startswith(("sd::", "pgrad::"))})
+
+
+if __name__ == "__main__":
+    out = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out, exist_ok=True)
+    make_render_goldens(out)
+    make_hexplane_golden(out)
