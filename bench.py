@@ -179,6 +179,7 @@ def run_ours(args):
     from mobgs_b200 import _lib
     from mobgs_b200.scene import subframe_w2c, synthetic_scene
     from mobgs_b200.subframes import render_subframes
+    from mobgs_b200.dist import FlatGradients
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,9 +231,10 @@ def run_ours(args):
         loss = (out["render"] - tgt).abs().mean()
         loss.backward()
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in all_params if p.grad is not None])
-            dist.all_reduce(flat)
-            stats["allreduce_bytes"] = flat.numel() * 4
+            if "fg" not in stats:      # parameter set that actually receives gradients is fixed
+                stats["fg"] = FlatGradients([p for p in all_params if p.grad is not None])
+            stats["fg"].reduce()
+            stats["allreduce_bytes"] = stats["fg"].flat.numel() * 4
         view.grad = None
         stats["out"] = out
         if not resident:

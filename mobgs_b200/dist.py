@@ -1,0 +1,79 @@
+"""Multi-GPU plumbing: one process per GPU, parameters replicated, (view, sub-frame) work items
+sharded across ranks, one all-reduce of the flat gradient buffer per step.
+
+The reference is single-process / single-GPU (no torch.distributed anywhere); the loss of one
+optimiser step is a mean over the batch's views (train.py:621-629), i.e. linear across views, so
+rendering different views on different ranks and summing gradients reproduces the single-process
+gradient exactly.  Gaussians themselves are never partitioned (per-tile sorting needs all
+Gaussians of a tile): "replicas only" along N.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_items(n_items: int, rank: int, world: int) -> range:
+    """Contiguous block partition of work items (views, or (view, sub-frame) pairs flattened as
+    v*K+k so that the sub-frames of one view stay on neighbouring ranks)."""
+    base, rem = divmod(n_items, world)
+    start = rank * base + min(rank, rem)
+    return range(start, start + base + (1 if rank < rem else 0))
+
+
+def shard_subframes(n_views: int, K: int, rank: int, world: int) -> List[Tuple[int, range]]:
+    """[(view, sub-frame range)] owned by `rank` when V*K work items are split across ranks."""
+    out = []
+    items = shard_items(n_views * K, rank, world)
+    if len(items) == 0:
+        return out
+    v0, v1 = items.start // K, (items.stop - 1) // K
+    for v in range(v0, v1 + 1):
+        lo = max(items.start, v * K) - v * K
+        hi = min(items.stop, (v + 1) * K) - v * K
+        out.append((v, range(lo, hi)))
+    return out
+
+
+class FlatGradients:
+    """Flat fp32 buffer over the gradients of a fixed parameter list; `.reduce()` = one collective."""
+
+    def __init__(self, params: Sequence[torch.Tensor]):
+        self.params = list(params)
+        self.sizes = [p.numel() for p in self.params]
+        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
+
+    def pack(self) -> torch.Tensor:
+        off = 0
+        for p, n in zip(self.params, self.sizes):
+            if p.grad is not None:
+                self.flat[off:off + n].copy_(p.grad.reshape(-1))
+            else:
+                self.flat[off:off + n].zero_()
+            off += n
+        return self.flat
+
+    def unpack(self) -> None:
+        off = 0
+        for p, n in zip(self.params, self.sizes):
+            g = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                p.grad = g.clone()
+            else:
+                p.grad.copy_(g)
+            off += n
+
+    def reduce(self, group=None, average: bool = False) -> torch.Tensor:
+        self.pack()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, group=group)
+            if average:
+                self.flat.div_(dist.get_world_size(group))
+        self.unpack()
+        return self.flat
+
+
+def trainable(params: Iterable[torch.Tensor]) -> List[torch.Tensor]:
+    return [p for p in params if p.is_floating_point() and p.requires_grad]
