@@ -290,6 +290,44 @@ typedef struct {
 } MobgsDecodeBwd;
 int mobgs_decode_bwd(const MobgsDecodeBwd* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * deform_network.forward(point, scales, rotations, times_sel) — scene/deformation.py:252-253 ->
+ * forward_dynamic2 :158-199 over HexPlaneField scene/hexplane.py:19-108 (not called by render(),
+ * but part of the model API).  One fused launch: 6*levels bilinear plane
+ * samples (align_corners=True, border), product over planes, Linear(32*levels -> 128), three
+ * heads ReLU-Linear(128,128)-ReLU-Linear(128,{7,3,4}) on tcgen05 tensor cores (3xTF32), and the
+ * dx / quat2mat / ds-clamp / quaternion-product epilogue.
+ *   planes[l*6+p]: channels-LAST copy [H][W][32] of grids[l][p] ([1,32,H,W] in the reference);
+ *                  plane order = itertools.combinations(range(4), 2); plane_w/h = W/H of each.
+ *   aabb[0..2] = HexPlaneField.aabb[0], aabb[3..5] = aabb[1] (normalize_aabb, hexplane.py:19-21).
+ *   Weights are pre-tiled by the host into the kernel's shared-memory operand layout, each block
+ *   stored twice (tf32 "hi" part, then fp32 remainder "lo"): a [rows x K] row-major matrix becomes
+ *   [K/4][rows][4] floats.
+ *     w0: feature_out[0].weight [128, 32*levels] as 2 row-halves x {hi,lo} x [K/4][64][4]
+ *     wa: the three heads' first Linear [128,128]: [3] x 2 row-halves x {hi,lo} x [32][64][4]
+ *     wb: the three heads' last Linear, rows zero-padded to 16: [3] x {hi,lo} x [32][16][4]
+ *     b0 [128], ba [3,128], bb [3,16] (zero padded) plain fp32.
+ *   head order: pos_deform (7 outputs), scales_deform (3), rotations_deform (4). */
+typedef struct {
+  int32_t N;
+  const float* pts;      /* [N,3] */
+  const float* scales;   /* [N,3] */
+  const float* rots;     /* [N,4] */
+  const float* times;    /* [N]   */
+  float aabb[6];
+  int32_t levels, net_width, plane_features;
+  const float* planes[24];
+  int32_t plane_w[24];
+  int32_t plane_h[24];
+  const float* w0; const float* b0;
+  const float* wa; const float* ba;
+  const float* wb; const float* bb;
+  float* out_pts;     /* [N,3] */
+  float* out_scales;  /* [N,3] */
+  float* out_rots;    /* [N,4] */
+} MobgsHexMlpFwd;
+int mobgs_hexplane_mlp_fwd(const MobgsHexMlpFwd* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

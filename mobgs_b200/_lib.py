@@ -159,6 +159,16 @@ class DecodeBwd(C.Structure):
                 ("v_rays", C.c_void_p), ("v_w1", C.c_void_p), ("v_w2", C.c_void_p)]
 
 
+class HexMlpFwd(C.Structure):
+    _fields_ = [("N", C.c_int32), ("pts", C.c_void_p), ("scales", C.c_void_p), ("rots", C.c_void_p),
+                ("times", C.c_void_p), ("aabb", C.c_float * 6), ("levels", C.c_int32),
+                ("net_width", C.c_int32), ("plane_features", C.c_int32), ("planes", C.c_void_p * 24),
+                ("plane_w", C.c_int32 * 24), ("plane_h", C.c_int32 * 24),
+                ("w0", C.c_void_p), ("b0", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p),
+                ("wb", C.c_void_p), ("bb", C.c_void_p), ("out_pts", C.c_void_p),
+                ("out_scales", C.c_void_p), ("out_rots", C.c_void_p)]
+
+
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
 ENTRY_POINTS = {
@@ -175,6 +185,7 @@ ENTRY_POINTS = {
     "mobgs_blend_bwd": BlendBwd,
     "mobgs_decode_fwd": DecodeFwd,
     "mobgs_decode_bwd": DecodeBwd,
+    "mobgs_hexplane_mlp_fwd": HexMlpFwd,
 }
 
 _lib = None
@@ -217,7 +228,7 @@ KERNELS_PER_CALL = {
     "mobgs_project_fwd": 1, "mobgs_project_bwd": 1, "mobgs_synth_project_fwd": 1,
     "mobgs_synth_project_bwd": 1, "mobgs_pack_records": 1, "mobgs_tile_count": 2,
     "mobgs_tile_emit_sort": 2, "mobgs_blend_fwd": 1, "mobgs_blend_bwd": 1,
-    "mobgs_decode_fwd": 1, "mobgs_decode_bwd": 1,
+    "mobgs_decode_fwd": 1, "mobgs_decode_bwd": 1, "mobgs_hexplane_mlp_fwd": 1,
 }
 LAUNCH_COUNT = 0
 # optional per-entry-point device timing: TIMING = {} enables it; values are lists of

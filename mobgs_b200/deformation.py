@@ -1,0 +1,170 @@
+"""`deform_network`-compatible HexPlane + MLP deformation (reference scene/deformation.py:228-303,
+scene/hexplane.py:111-187) whose forward is ONE fused sm_100a kernel (csrc/hexplane_mlp.cu).
+
+Parameter names / shapes mirror the reference module so that its checkpoints
+(`deformation.pth`, GaussianModel.save_deformation, scene/gaussian_model.py:755-758) load with
+`load_state_dict`, and `fused_forward(ref_net, ...)` accepts the reference's own instance.
+
+Covered configuration = the Stereo-Blur configs (arguments/stereo/*.py): net_width 128,
+defor_depth 1, 32 features per plane, no_grid/static_mlp/empty_voxel/apply_rotation False,
+grid_pe 0.  Anything else raises NotImplementedError (no fallback).
+
+Status: forward (inference) only — the module is not on the reference's live training path
+(SURVEY.md §0.3); gradients through it are not provided yet and requesting them raises.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .ops import _f32c, _p, _stream
+
+NET_WIDTH = 128
+PLANE_FEATURES = 32
+HEAD_OUT = (7, 3, 4)
+
+
+def _tile(w: torch.Tensor) -> torch.Tensor:
+    """[rows, K] row-major -> {hi, lo} x [K/4][rows][4] (the kernel's shared-memory operand layout)."""
+    rows, K = w.shape
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)     # keep 10 mantissa bits (TF32)
+    lo = w - hi
+    t = lambda m: m.reshape(rows, K // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)  # noqa: E731
+    return torch.cat([t(hi), t(lo)])
+
+
+def pack_weights(w0, b0, heads):
+    """heads: [(Wa[128,128], ba[128], Wb[n,128], bb[n])] * 3 in pos/scales/rotations order."""
+    dev = w0.device
+    w0_t = torch.cat([_tile(w0[h * 64:(h + 1) * 64].float()) for h in range(2)])
+    wa_t = torch.cat([_tile(Wa[h * 64:(h + 1) * 64].float()) for Wa, _, _, _ in heads for h in range(2)])
+    wb_list, bb_list = [], []
+    for _, _, Wb, bb in heads:
+        pad = torch.zeros(16, NET_WIDTH, device=dev)
+        pad[:Wb.shape[0]] = Wb.float()
+        wb_list.append(_tile(pad))
+        pb = torch.zeros(16, device=dev)
+        pb[:bb.shape[0]] = bb.float()
+        bb_list.append(pb)
+    ba = torch.stack([ba.float() for _, ba, _, _ in heads]).contiguous()
+    return (w0_t.contiguous(), b0.float().contiguous(), wa_t.contiguous(), ba,
+            torch.cat(wb_list).contiguous(), torch.cat(bb_list).contiguous())
+
+
+def fused_forward_raw(pts, scales, rots, times, aabb, planes: Sequence[Sequence[torch.Tensor]], w0, b0, heads):
+    """planes[l][p]: [1,32,H,W] parameters (reference layout); aabb: [2,3] tensor."""
+    if any(t.requires_grad for t in (pts, scales, rots, times)) and torch.is_grad_enabled():
+        raise NotImplementedError("mobgs_b200.deformation: forward only (see module docstring)")
+    pts, scales, rots = _f32c(pts[:, :3]), _f32c(scales[:, :3]), _f32c(rots[:, :4])
+    times = _f32c(times.reshape(-1))
+    N = pts.shape[0]
+    levels = len(planes)
+    if w0.shape != (NET_WIDTH, PLANE_FEATURES * levels) or levels > 4:
+        raise NotImplementedError(f"feature_out weight {tuple(w0.shape)} not covered (net_width 128, 32 feats/plane)")
+    a = L.HexMlpFwd()
+    a.N = N
+    a.pts, a.scales, a.rots, a.times = _p(pts), _p(scales), _p(rots), _p(times)
+    ab = aabb.detach().float().cpu().reshape(-1).tolist()
+    for i in range(6):
+        a.aabb[i] = ab[i]
+    a.levels, a.net_width, a.plane_features = levels, NET_WIDTH, PLANE_FEATURES
+    keep = []
+    for l, grids in enumerate(planes):
+        assert len(grids) == 6
+        for p, g in enumerate(grids):
+            if g.shape[0] != 1 or g.shape[1] != PLANE_FEATURES:
+                raise NotImplementedError(f"plane shape {tuple(g.shape)} not covered")
+            cl = g.detach()[0].permute(1, 2, 0).contiguous().float()     # channels-last [H,W,32]
+            keep.append(cl)
+            a.planes[l * 6 + p] = cl.data_ptr()
+            a.plane_h[l * 6 + p], a.plane_w[l * 6 + p] = cl.shape[0], cl.shape[1]
+    packed = pack_weights(w0.detach(), b0.detach(), [tuple(t.detach() for t in h) for h in heads])
+    a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in packed)
+    out_pts = torch.empty(N, 3, device=pts.device)
+    out_scales = torch.empty(N, 3, device=pts.device)
+    out_rots = torch.empty(N, 4, device=pts.device)
+    a.out_pts, a.out_scales, a.out_rots = _p(out_pts), _p(out_scales), _p(out_rots)
+    L.call("mobgs_hexplane_mlp_fwd", a, _stream())
+    del keep, packed
+    return out_pts, out_scales, out_rots
+
+
+def _check_args(args):
+    bad = [k for k in ("no_grid", "static_mlp", "empty_voxel", "apply_rotation", "no_dx", "no_ds", "no_dr")
+           if getattr(args, k, False)]
+    if bad or getattr(args, "grid_pe", 0) != 0 or getattr(args, "defor_depth", 1) != 1:
+        raise NotImplementedError(f"deformation options not covered by the fused kernel: {bad}")
+
+
+def fused_forward(net, point, scales, rotations, times_sel):
+    """Drop-in for `deform_network.forward` on a reference (or HexPlaneMLP) instance."""
+    d = net.deformation_net
+    _check_args(d.args)
+    fo = d.feature_out
+    if len(fo) != 1:
+        raise NotImplementedError("defor_depth != 1")
+    heads = []
+    for seq in (d.pos_deform, d.scales_deform, d.rotations_deform):
+        heads.append((seq[1].weight, seq[1].bias, seq[3].weight, seq[3].bias))
+    planes = [[p for p in level] for level in d.grid.grids]
+    return fused_forward_raw(point, scales, rotations, times_sel, d.grid.aabb, planes, fo[0].weight, fo[0].bias, heads)
+
+
+# ---------------------------------------------------------------------------------------------
+# Stand-alone module with the reference's parameter naming (for checkpoints / tests without
+# /root/reference).  Only the pieces of the reference classes that hold parameters are mirrored.
+# ---------------------------------------------------------------------------------------------
+class _Grid(nn.Module):
+    def __init__(self, bounds, config, multires):
+        super().__init__()
+        self.aabb = nn.Parameter(torch.tensor([[bounds] * 3, [-bounds] * 3], dtype=torch.float32), requires_grad=False)
+        self.grids = nn.ModuleList()
+        for res in multires:
+            reso = [r * res for r in config["resolution"][:3]] + list(config["resolution"][3:])
+            level = nn.ParameterList()
+            for comb in itertools.combinations(range(4), 2):
+                p = nn.Parameter(torch.empty([1, config["output_coordinate_dim"]] + [reso[c] for c in comb[::-1]]))
+                if 3 in comb:
+                    nn.init.ones_(p)
+                else:
+                    nn.init.uniform_(p, a=0.1, b=0.5)
+                level.append(p)
+            self.grids.append(level)
+
+    def set_aabb(self, xyz_max, xyz_min):
+        self.aabb = nn.Parameter(torch.tensor([xyz_max, xyz_min], dtype=torch.float32), requires_grad=False)
+
+
+class _Deformation(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        W = args.net_width
+        self.grid = _Grid(args.bounds, args.kplanes_config, args.multires)
+        feat = args.kplanes_config["output_coordinate_dim"] * len(args.multires)
+        self.feature_out = nn.Sequential(nn.Linear(feat, W))
+        self.pos_deform = nn.Sequential(nn.ReLU(), nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 7))
+        self.scales_deform = nn.Sequential(nn.ReLU(), nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 3))
+        self.rotations_deform = nn.Sequential(nn.ReLU(), nn.Linear(W, W), nn.ReLU(), nn.Linear(W, 4))
+
+
+class HexPlaneMLP(nn.Module):
+    """Same state_dict keys as the reference `deform_network` for the parts the forward uses
+    (`deformation_net.grid.*`, `.feature_out.*`, `.pos_deform.*`, `.scales_deform.*`,
+    `.rotations_deform.*`); load reference checkpoints with strict=False (timenet / poc buffers
+    are unused by forward_dynamic2)."""
+
+    def __init__(self, args):
+        super().__init__()
+        _check_args(args)
+        self.deformation_net = _Deformation(args)
+
+    def forward(self, point, scales, rotations, times_sel):
+        return fused_forward(self, point, scales, rotations, times_sel)
+
+    def set_aabb(self, xyz_max, xyz_min):
+        self.deformation_net.grid.set_aabb(xyz_max, xyz_min)

@@ -1,0 +1,54 @@
+"""a11: fused HexPlane + MLP forward (tcgen05, 3xTF32) vs the reference module's golden outputs
+and vs the oracle restatement at a larger size.  Tolerance 1e-4 abs / 1e-3 rel (fp32 bar)."""
+import numpy as np
+import pytest
+import torch
+
+from test_oracle import _hexplane_args, load_hexplane_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(got, want, name, atol=1e-4, rtol=1e-3):
+    got = got.detach().cpu().double()
+    want = torch.as_tensor(want).double()
+    err = (got - want).abs()
+    bad = err > atol + rtol * want.abs()
+    assert not bad.any(), (name, float(err.max()), int(bad.sum()))
+
+
+def test_fused_forward_matches_reference_golden():
+    net, gold = load_hexplane_golden("cuda")
+    ins = [torch.from_numpy(gold[k]).cuda() for k in ("in_pts", "in_scales", "in_rots", "in_t")]
+    with torch.no_grad():
+        p, s, r = net(*ins)
+    _cmp(p, gold["out_pts"], "out_pts")
+    _cmp(s, gold["out_scales"], "out_scales")
+    _cmp(r, gold["out_rots"], "out_rots")
+
+
+@pytest.mark.parametrize("n,base_res", [(5000, 64), (128, 16), (1, 16), (129, 32)])
+def test_fused_forward_matches_oracle(n, base_res):
+    from mobgs_b200.deformation import HexPlaneMLP
+    from oracle.hexplane_ref import deform_forward_ref
+    torch.manual_seed(n)
+    net = HexPlaneMLP(_hexplane_args(base_res))
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+            elif "grids" in name:
+                p.add_(0.1 * torch.randn_like(p))
+            elif p.requires_grad:
+                torch.nn.init.xavier_uniform_(p)
+    net.set_aabb([1.3, 1.1, 1.2], [-1.2, -1.0, -1.4])
+    pts = torch.rand(n, 3) * 3 - 1.5
+    scales = torch.randn(n, 3) * 0.3 - 3
+    rots = torch.randn(n, 4)
+    t = torch.rand(n, 1)
+    with torch.no_grad():
+        want = deform_forward_ref(net, pts, scales, rots, t)
+        net.cuda()
+        got = net(pts.cuda(), scales.cuda(), rots.cuda(), t.cuda())
+    for g, w, name in zip(got, want, ("pts", "scales", "rots")):
+        _cmp(g, w, name)
