@@ -254,7 +254,7 @@ int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream);
  *            bias-free 1x1 convs: W1 [6,12] = mlp1.weight, W2 [3,6] = mlp2.weight)
  *   mean   = (1/K) sum_k rgb_k + 1e-10                  train.py:540-541 (blur model)
  * img [K,H,W,10] and alpha [K,H,W] are the blend outputs; rays [K,6,H,W] (rays_per_k=1) or
- * [1,6,H,W] shared.  Outputs (each may be NULL): rgb [K,3,H,W], depth [K,H,W], mean [3,H,W]. */
+ * [1,6,H,W] shared.  Outputs: rgb [K,3,H,W] (required), depth [K,H,W] and mean [3,H,W] (may be NULL). */
 typedef struct {
   int32_t K, width, height;
   const float* img;

@@ -228,7 +228,7 @@ KERNELS_PER_CALL = {
     "mobgs_project_fwd": 1, "mobgs_project_bwd": 1, "mobgs_synth_project_fwd": 1,
     "mobgs_synth_project_bwd": 1, "mobgs_pack_records": 1, "mobgs_tile_count": 2,
     "mobgs_tile_emit_sort": 2, "mobgs_blend_fwd": 1, "mobgs_blend_bwd": 1,
-    "mobgs_decode_fwd": 1, "mobgs_decode_bwd": 1, "mobgs_hexplane_mlp_fwd": 1,
+    "mobgs_decode_fwd": 2, "mobgs_decode_bwd": 1, "mobgs_hexplane_mlp_fwd": 1,
 }
 LAUNCH_COUNT = 0
 # optional per-entry-point device timing: TIMING = {} enables it; values are lists of

@@ -16,6 +16,7 @@ namespace mobgs {
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortSmemCap = 4096;   // keys per segment sorted entirely in shared memory
+constexpr int kRankSortMax = 768;    // segments up to this size use the O(n^2 / 256) rank sort
 
 struct TileRect { int x0, y0, x1, y1; };
 
@@ -219,6 +220,20 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a
   uint64_t* gkeys = a.keys + beg;
   if (n == 1) {
     if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(gkeys[0] & 0xffffffffu);
+    return;
+  }
+  if (n <= kRankSortMax) {
+    // small segment (the common case): all-pairs rank sort out of shared memory — keys are unique
+    // (they embed the Gaussian index), so rank = #{keys smaller} is the final position.
+    for (int i = threadIdx.x; i < n; i += kSortThreads) bufA[i] = gkeys[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kSortThreads) {
+      const uint64_t key = bufA[i];
+      int rank = 0;
+#pragma unroll 4
+      for (int j = 0; j < n; ++j) rank += bufA[j] < key;
+      a.sorted_ids[beg + rank] = (int)(key & 0xffffffffu);
+    }
     return;
   }
   const bool in_smem = n <= kSortSmemCap;

@@ -49,15 +49,41 @@ __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, c
   }
 }
 
+// Each warp compacts the batch entries whose strip mask includes it (ascending order kept) into its
+// own byte list, so its inner loop visits only Gaussians that can reach its 16x2 pixel strip.
+__device__ __forceinline__ int build_strip_list(const unsigned* smask, unsigned char* wlist, unsigned wbit,
+                                                int lane, int t_begin, int bn) {
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < kBlendThreads / 32; ++j) {
+    const int t = j * 32 + lane;
+    const bool m = t >= t_begin && t < bn && (smask[t] & wbit);
+    const unsigned b = __ballot_sync(0xffffffffu, m);
+    if (m) wlist[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned char)t;
+    cnt += __popc(b);
+  }
+  __syncwarp();
+  return cnt;
+}
+
+__device__ __forceinline__ int lane_id() {
+  int l;
+  asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
+  return l;
+}
+
 template <int D>
 __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
+  __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x;
+  const int lane = lane_id();
   const unsigned wbit = 1u << (tid >> 5);
+  unsigned char* wlist = swl[tid >> 5];
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -84,8 +110,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd 
     }
     __syncthreads();
     const int bn = min(kBlendThreads, end - b0);
-    for (int t = 0; t < bn && !done; ++t) {
-      if (!(smask[t] & wbit)) continue;     // warp-uniform: this strip cannot reach alpha >= 1/255
+    const int cnt = build_strip_list(smask, wlist, wbit, lane, 0, bn);
+    for (int i = 0; i < cnt && !done; ++i) {
+      const int t = wlist[i];
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
       const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
@@ -126,17 +153,19 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd 
 }
 
 template <int D>
-__global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd a, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(MobgsBlendBwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
   __shared__ unsigned smask[kBlendThreads];
+  __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
   __shared__ int warp_max[kBlendThreads / 32];
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = lane_id();
   const unsigned wbit = 1u << (tid >> 5);
+  unsigned char* wlist = swl[tid >> 5];
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -198,8 +227,9 @@ __global__ void __launch_bounds__(kBlendThreads) blend_bwd_kernel(MobgsBlendBwd 
     for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
     __syncthreads();
     // entries above this warp's furthest pixel contribute nothing: skip them warp-uniformly
-    for (int t = max(0, hi - wmax); t < bn; ++t) {
-      if (!(smask[t] & wbit)) continue;     // warp-uniform strip cull
+    const int cnt = build_strip_list(smask, wlist, wbit, lane, max(0, hi - wmax), bn);
+    for (int i = 0; i < cnt; ++i) {
+      const int t = wlist[i];
       const int idx = hi - t;
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;

@@ -8,25 +8,19 @@
 
 namespace mobgs {
 
-constexpr int kDecThreads = 256;
+constexpr int kDecThreads = 128;
 constexpr float kEdFloor = 1e-10f;
 constexpr float kMeanEps = 1e-10f;
 
-struct DecW { float w1[72]; float w2[18]; };
+// The 90 decoder weights stay in shared memory (broadcast LDS.128 reads): the backward already
+// needs 90 registers per thread for the weight-gradient accumulators.
+struct DecW { const float* w1; const float* w2; };
 
 __device__ __forceinline__ void load_w(DecW& w, const float* w1, const float* w2, float* smem) {
   for (int i = threadIdx.x; i < 90; i += blockDim.x) smem[i] = i < 72 ? w1[i] : w2[i - 72];
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 72; ++i) w.w1[i] = smem[i];
-#pragma unroll
-  for (int i = 0; i < 18; ++i) w.w2[i] = smem[72 + i];
-}
-
-__device__ __forceinline__ void load_px(const float* img, float v[10]) {
-  const float2* p = reinterpret_cast<const float2*>(img);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) { const float2 t = p[i]; v[2 * i] = t.x; v[2 * i + 1] = t.y; }
+  w.w1 = smem;
+  w.w2 = smem + 72;
 }
 
 // x = [spec(3), timefeat(3), rays(6)]
@@ -50,69 +44,113 @@ __device__ __forceinline__ void sandwich_fwd(const DecW& w, const float v[10], c
   }
 }
 
-__global__ void __launch_bounds__(kDecThreads) decode_fwd_kernel(MobgsDecodeFwd a) {
-  __shared__ float sw[96];
+// img10 is channels-last (40 B per pixel): a CTA moves its 256-pixel block through shared memory
+// with coalesced 8-byte accesses instead of letting every thread walk its own 40-byte record.
+__device__ __forceinline__ void stage_in(float* simg, const float* gsrc, int npx) {
+  const float2* src = reinterpret_cast<const float2*>(gsrc);
+  float2* dst = reinterpret_cast<float2*>(simg);
+  for (int i = threadIdx.x; i < npx * 5; i += kDecThreads) dst[i] = __ldg(src + i);
+}
+__device__ __forceinline__ void stage_out(float* gdst, const float* simg, int npx) {
+  const float2* src = reinterpret_cast<const float2*>(simg);
+  float2* dst = reinterpret_cast<float2*>(gdst);
+  for (int i = threadIdx.x; i < npx * 5; i += kDecThreads) dst[i] = src[i];
+}
+
+// Work item = (sub-frame k, block of kDecThreads pixels); a persistent grid strides over K * nblk
+// items so that the sub-frames of a pixel are independent pieces of work in flight at once.
+__global__ void __launch_bounds__(kDecThreads, 4) decode_fwd_kernel(MobgsDecodeFwd a) {
+  __shared__ __align__(16) float sw[96];
+  __shared__ __align__(16) float simg[kDecThreads * 10];
   DecW w;
   load_w(w, a.w1, a.w2, sw);
   const size_t P = (size_t)a.width * a.height;
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
-    float mean[3] = {0.f, 0.f, 0.f};
-    for (int k = 0; k < a.K; ++k) {
-      float v[10], rays[6], x[12], hpre[6], out[3];
-      load_px(a.img + ((size_t)k * P + p) * 10, v);
+  const size_t nblk = (P + kDecThreads - 1) / kDecThreads;
+  for (size_t item = blockIdx.x; item < nblk * a.K; item += gridDim.x) {
+    const int k = (int)(item / nblk);
+    const size_t pb = item - (size_t)k * nblk;
+    const size_t p0 = pb * kDecThreads, p = p0 + threadIdx.x;
+    const int npx = (int)min((size_t)kDecThreads, P - p0);
+    const bool valid = threadIdx.x < npx;
+    float rays[6] = {0, 0, 0, 0, 0, 0}, al = 1.f;
+    if (valid) {     // issue the planar loads before the staging barrier so they overlap it
       const float* rp = a.rays + (a.rays_per_k ? (size_t)k * 6 * P : 0) + p;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) rays[i] = rp[i * P];
-      sandwich_fwd(w, v, rays, x, hpre, out);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (a.rgb) a.rgb[((size_t)k * 3 + c) * P + p] = out[c];
-        mean[c] += out[c];
-      }
-      if (a.depth) a.depth[(size_t)k * P + p] = v[9] / fmaxf(a.alpha[(size_t)k * P + p], kEdFloor);
+      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+      al = __ldg(a.alpha + (size_t)k * P + p);
     }
-    if (a.mean) {
-      const float inv = 1.0f / (float)a.K;
+    __syncthreads();
+    stage_in(simg, a.img + ((size_t)k * P + p0) * 10, npx);
+    __syncthreads();
+    if (!valid) continue;
+    float v[10], x[12], hpre[6], out[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a.mean[c * P + p] = mean[c] * inv + kMeanEps;
-    }
+    for (int i = 0; i < 10; ++i) v[i] = simg[threadIdx.x * 10 + i];
+    sandwich_fwd(w, v, rays, x, hpre, out);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a.rgb[((size_t)k * 3 + c) * P + p] = out[c];
+    if (a.depth) a.depth[(size_t)k * P + p] = v[9] / fmaxf(al, kEdFloor);
   }
 }
 
-__global__ void __launch_bounds__(kDecThreads) decode_bwd_kernel(MobgsDecodeBwd a) {
-  __shared__ float sw[96];
+// blur model: mean over the K decoded sub-frames + 1e-10 (train.py:540-541)
+__global__ void __launch_bounds__(256) subframe_mean_kernel(const float* __restrict__ rgb, float* __restrict__ mean,
+                                                            int K, size_t n) {
+  const float inv = 1.0f / (float)K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s += __ldg(rgb + (size_t)k * n + i);
+    mean[i] = s * inv + kMeanEps;
+  }
+}
+
+__global__ void __launch_bounds__(kDecThreads, 3) decode_bwd_kernel(MobgsDecodeBwd a) {
+  __shared__ __align__(16) float sw[96];
   __shared__ float sred[90];
+  __shared__ __align__(16) float simg[kDecThreads * 10];
   DecW w;
   load_w(w, a.w1, a.w2, sw);
   if (threadIdx.x < 90) sred[threadIdx.x] = 0.f;
-  __syncthreads();
   float gw[90];
 #pragma unroll
   for (int i = 0; i < 90; ++i) gw[i] = 0.f;
   const size_t P = (size_t)a.width * a.height;
+  const size_t nblk = (P + kDecThreads - 1) / kDecThreads;
   const float invK = 1.0f / (float)a.K;
-  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
-    float gm[3] = {0.f, 0.f, 0.f};
-    if (a.g_mean) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) gm[c] = a.g_mean[c * P + p] * invK;
-    }
-    float gr_shared[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < a.K; ++k) {
-      float v[10], rays[6], x[12], hpre[6], out[3];
-      const size_t kp = (size_t)k * P + p;
-      load_px(a.img + kp * 10, v);
+  for (size_t item = blockIdx.x; item < nblk * a.K; item += gridDim.x) {
+    const int k = (int)(item / nblk);
+    const size_t pb = item - (size_t)k * nblk;
+    const size_t p0 = pb * kDecThreads, p = p0 + threadIdx.x;
+    const int npx = (int)min((size_t)kDecThreads, P - p0);
+    const bool valid = threadIdx.x < npx;
+    const size_t kp0 = (size_t)k * P + p0, kp = kp0 + threadIdx.x;
+    float rays[6] = {0, 0, 0, 0, 0, 0}, al = 1.f, gd = 0.f, g_in[3] = {0.f, 0.f, 0.f};
+    if (valid) {
       const float* rp = a.rays + (a.rays_per_k ? (size_t)k * 6 * P : 0) + p;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) rays[i] = rp[i * P];
+      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+      al = __ldg(a.alpha + kp);
+      if (a.g_depth) gd = __ldg(a.g_depth + kp);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (a.g_mean) g_in[c] = __ldg(a.g_mean + c * P + p) * invK;
+        if (a.g_rgb) g_in[c] += __ldg(a.g_rgb + ((size_t)k * 3 + c) * P + p);
+      }
+    }
+    __syncthreads();
+    stage_in(simg, a.img + kp0 * 10, npx);
+    __syncthreads();
+    float gv[10];
+    if (valid) {
+      float v[10], x[12], hpre[6], out[3];
+#pragma unroll
+      for (int i = 0; i < 10; ++i) v[i] = simg[threadIdx.x * 10 + i];
       sandwich_fwd(w, v, rays, x, hpre, out);
-      float gv[10];
+      asm volatile("" ::: "memory");   // do not keep the forward's 90 weights live in registers
       float gpre[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        float g = gm[c];
-        if (a.g_rgb) g += a.g_rgb[((size_t)k * 3 + c) * P + p];
-        gpre[c] = g * out[c] * (1.f - out[c]);
+        gpre[c] = g_in[c] * out[c] * (1.f - out[c]);
         gv[c] = gpre[c];
       }
       float ghpre[6];
@@ -124,6 +162,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_bwd_kernel(MobgsDecodeBwd 
         for (int c = 0; c < 3; ++c) { gh += w.w2[6 * c + j] * gpre[c]; gw[72 + 6 * c + j] += gpre[c] * h; }
         ghpre[j] = hpre[j] > 0.f ? gh : 0.f;
       }
+      asm volatile("" ::: "memory");
       float gx[12];
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
@@ -134,29 +173,26 @@ __global__ void __launch_bounds__(kDecThreads) decode_bwd_kernel(MobgsDecodeBwd 
       }
 #pragma unroll
       for (int i = 0; i < 6; ++i) gv[3 + i] = gx[i];
-      // expected depth
-      const float al = a.alpha[kp];
       const float den = fmaxf(al, kEdFloor);
-      const float gd = a.g_depth ? a.g_depth[kp] : 0.f;
       gv[9] = gd / den;
       a.v_alpha[kp] = al > kEdFloor ? -gd * v[9] / (den * den) : 0.f;
-      float2* vo = reinterpret_cast<float2*>(a.v_img + kp * 10);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) vo[i] = make_float2(gv[2 * i], gv[2 * i + 1]);
       if (a.v_rays) {
         if (a.rays_per_k) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) a.v_rays[((size_t)k * 6 + i) * P + p] = gx[6 + i];
         } else {
 #pragma unroll
-          for (int i = 0; i < 6; ++i) gr_shared[i] += gx[6 + i];
+          for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + i * P + p, gx[6 + i]);
         }
       }
     }
-    if (a.v_rays && !a.rays_per_k) {
+    __syncthreads();            // everyone has read its pixel: reuse the buffer for the gradient
+    if (valid) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + i * P + p, gr_shared[i]);
+      for (int i = 0; i < 10; ++i) simg[threadIdx.x * 10 + i] = gv[i];
     }
+    __syncthreads();
+    stage_out(a.v_img + kp0 * 10, simg, npx);
   }
   // 90 weight gradients: warp shuffle -> shared -> one atomic per CTA
 #pragma unroll
@@ -175,18 +211,23 @@ __global__ void __launch_bounds__(kDecThreads) decode_bwd_kernel(MobgsDecodeBwd 
 
 using namespace mobgs;
 
-static int decode_grid(size_t P) {
-  const size_t want = (P + kDecThreads - 1) / kDecThreads;
-  const size_t cap = 148 * 8;   // persistent: 8 CTAs per SM
-  return (int)(want < cap ? want : cap);
+static int decode_grid(size_t items, int per_sm) {
+  const size_t cap = (size_t)148 * per_sm;   // persistent grid
+  return (int)(items < cap ? items : cap);
 }
 
 extern "C" int mobgs_decode_fwd(const MobgsDecodeFwd* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
   MOBGS_REQUIRE(a->K >= 1 && a->width > 0 && a->height > 0, "bad extents");
   MOBGS_REQUIRE(a->img && a->alpha && a->rays && a->w1 && a->w2, "NULL input");
+  MOBGS_REQUIRE(a->rgb, "rgb output must not be NULL (the mean is reduced from it)");
   const size_t P = (size_t)a->width * a->height;
-  decode_fwd_kernel<<<decode_grid(P), kDecThreads, 0, (cudaStream_t)stream>>>(*a);
+  const size_t nblk = (P + kDecThreads - 1) / kDecThreads;
+  decode_fwd_kernel<<<decode_grid(nblk * a->K, 16), kDecThreads, 0, (cudaStream_t)stream>>>(*a);
+  if (a->mean) {
+    const size_t n = 3 * P;
+    subframe_mean_kernel<<<decode_grid((n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(a->rgb, a->mean, a->K, n);
+  }
   return check_launch("decode_fwd");
 }
 
@@ -196,6 +237,7 @@ extern "C" int mobgs_decode_bwd(const MobgsDecodeBwd* a, void* stream) {
   MOBGS_REQUIRE(a->img && a->alpha && a->rays && a->w1 && a->w2, "NULL input");
   MOBGS_REQUIRE(a->v_img && a->v_alpha && a->v_w1 && a->v_w2, "NULL output");
   const size_t P = (size_t)a->width * a->height;
-  decode_bwd_kernel<<<decode_grid(P), kDecThreads, 0, (cudaStream_t)stream>>>(*a);
+  const size_t nblk = (P + kDecThreads - 1) / kDecThreads;
+  decode_bwd_kernel<<<decode_grid(nblk * a->K, 9), kDecThreads, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("decode_bwd");
 }

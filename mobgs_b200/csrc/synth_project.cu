@@ -15,6 +15,7 @@ struct CamSmem {
   Cam cam[kMaxK];
   float t_spline[kMaxK];
   float t_poly[kMaxK];
+  float v_view[kMaxK][12];   // backward: CTA-level accumulator of the view-matrix gradient
 };
 
 __device__ __forceinline__ void load_cams(CamSmem& sm, const MobgsCameras& c, const float* t_spline,
@@ -23,6 +24,8 @@ __device__ __forceinline__ void load_cams(CamSmem& sm, const MobgsCameras& c, co
     sm.cam[k] = load_cam(c.viewmats, c.Ks, k);
     sm.t_spline[k] = t_spline ? t_spline[k] : 0.f;
     sm.t_poly[k] = t_poly ? t_poly[k] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sm.v_view[k][i] = 0.f;
   }
   __syncthreads();
 }
@@ -65,25 +68,32 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(MobgsProjectF
   }
 }
 
-__device__ __forceinline__ void reduce_viewmat_grad(float* v_viewmats, int k, const ProjGrad& g, bool active) {
-  // 12 warp reductions; lanes that did not contribute pass zeros. One atomicAdd per warp.
+// 12 warp reductions per (warp, sub-frame); lanes that did not contribute pass zeros.  The warp sums
+// go to a shared-memory accumulator and leave the CTA as one atomicAdd per value at the very end:
+// thousands of CTAs hammering the same 12*K global addresses would serialise in L2.
+__device__ __forceinline__ void reduce_viewmat_grad(float (*v_view)[12], int k, const ProjGrad& g, bool active) {
+  if (!__any_sync(0xffffffffu, active)) return;
   float vals[12];
 #pragma unroll
   for (int i = 0; i < 9; ++i) vals[i] = active ? g.r[i] : 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) vals[9 + i] = active ? g.t[i] : 0.f;
-  if (!__any_sync(0xffffffffu, active)) return;
 #pragma unroll
   for (int i = 0; i < 12; ++i) vals[i] = warp_sum(vals[i]);
   if ((threadIdx.x & 31) == 0) {
-    float* v = v_viewmats + 16 * k;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      atomicAdd(v + 4 * i + 0, vals[3 * i + 0]);
-      atomicAdd(v + 4 * i + 1, vals[3 * i + 1]);
-      atomicAdd(v + 4 * i + 2, vals[3 * i + 2]);
-      atomicAdd(v + 4 * i + 3, vals[9 + i]);
-    }
+    for (int i = 0; i < 12; ++i) atomicAdd(&v_view[k][i], vals[i]);
+  }
+}
+
+__device__ __forceinline__ void flush_viewmat_grad(float (*v_view)[12], float* v_viewmats, int K) {
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * 12; i += blockDim.x) {
+    const int k = i / 12, j = i - 12 * k;
+    const float v = v_view[k][j];
+    // v_view row layout: r[0..8] row-major, t[0..2]  ->  viewmat [4,4] row-major
+    const int dst = j < 9 ? 4 * (j / 3) + (j % 3) : 4 * (j - 9) + 3;
+    if (v != 0.f) atomicAdd(v_viewmats + 16 * k + dst, v);
   }
 }
 
@@ -118,8 +128,9 @@ __global__ void __launch_bounds__(kProjThreads) project_bwd_kernel(MobgsProjectB
 #pragma unroll
       for (int j = 0; j < 4; ++j) vq[j] += gr.q[j];
     }
-    if (a.v_viewmats) reduce_viewmat_grad(a.v_viewmats, k, gr, active);
+    if (a.v_viewmats) reduce_viewmat_grad(sm.v_view, k, gr, active);
   }
+  if (a.v_viewmats) flush_viewmat_grad(sm.v_view, a.v_viewmats, a.cams.K);
   if (in_range) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) { a.v_means[3 * g + j] = vp[j]; a.v_scales[3 * g + j] = vs[j]; }
@@ -313,8 +324,9 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
         }
       }
     }
-    if (a.v_viewmats) reduce_viewmat_grad(a.v_viewmats, k, gr, active);
+    if (a.v_viewmats) reduce_viewmat_grad(sm.v_view, k, gr, active);
   }
+  if (a.v_viewmats) flush_viewmat_grad(sm.v_view, a.v_viewmats, K);
   if (!in_range) return;
   const float vo_logit = vop * opac * (1.f - opac);
   if (is_static) {
