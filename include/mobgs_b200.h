@@ -175,11 +175,24 @@ typedef struct {
 } MobgsPack;
 int mobgs_pack_records(const MobgsPack* a, void* stream);
 
+/* A launch of the binning / blend kernels renders K *lists*.  List k takes its Gaussians from
+ * record set rec_k[k] (a sub-frame of the projection launch) restricted to the index range
+ * [g_begin[k], g_end[k]).  Identity (rec_k[k] = k, full range) is the plain K-sub-frame render;
+ * {(0, 0..N), (0, Ns..N), (0, 0..Ns)} renders the combined / dynamic-only / static-only images
+ * of render() (gaussian_renderer/__init__.py:143,201,236) from ONE projection in ONE launch. */
+#define MOBGS_MAX_K 32
+typedef struct {
+  int32_t rec_k[MOBGS_MAX_K];
+  int32_t g_begin[MOBGS_MAX_K];
+  int32_t g_end[MOBGS_MAX_K];
+} MobgsLists;
+
 /* ------------------------------------------------------------------------------------------
  * Tile binning + per-tile depth sort (gsplat isect_tiles + radix sort + isect_offset_encode,
  * inside every rasterization()).  Tile lists are per (sub-frame, tile), sorted by
  * (depth, Gaussian index) ascending — the order gsplat's stable 64-bit sort produces.
  *
+ * K = number of lists; records / radii / depths hold the record sets the lists refer to.
  * Step 1 counts intersections per tile and writes the exclusive prefix sum
  * tile_offsets[K*T+1] (T = tiles_x*tiles_y); the caller reads tile_offsets[K*T] (= I) to size
  * the lists (or provides a capacity it knows is enough).  Step 2 emits and sorts.
@@ -190,8 +203,7 @@ typedef struct {
   const float* records;      /* [K,N,16] */
   const int32_t* radii;      /* [K,N] */
   int32_t tight;
-  int32_t g_begin, g_end;    /* only Gaussians g_begin <= g < g_end are listed (static-only /
-                                dynamic-only renders of render():143,236 share one projection) */
+  MobgsLists lists;          /* K lists over the record sets (see MobgsLists) */
   int32_t* tile_counts;      /* [K*T] workspace, overwritten */
   int32_t* tile_offsets;     /* [K*T+1] out */
 } MobgsTileCount;
@@ -203,7 +215,7 @@ typedef struct {
   const int32_t* radii;
   const float* depths;       /* [K,N] sort key */
   int32_t tight;
-  int32_t g_begin, g_end;
+  MobgsLists lists;
   const int32_t* tile_offsets; /* [K*T+1] from step 1 */
   int32_t* tile_cursor;      /* [K*T] workspace (zeroed inside) */
   int64_t capacity;          /* entries available in keys/keys_tmp/sorted_ids */
@@ -221,6 +233,7 @@ int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream);
  * entry, needed by the backward). */
 typedef struct {
   int32_t K, N, D, width, height;
+  MobgsLists lists;
   const float* records;
   const int32_t* tile_offsets;
   const int32_t* sorted_ids;
@@ -235,6 +248,7 @@ int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
  * vector atomics and must be zeroed by the caller. */
 typedef struct {
   int32_t K, N, D, width, height;
+  MobgsLists lists;
   const float* records;
   const int32_t* tile_offsets;
   const int32_t* sorted_ids;
@@ -243,7 +257,9 @@ typedef struct {
   const int32_t* last_idx;
   const float* v_out_colors;  /* [K,H,W,D] */
   const float* v_out_alphas;  /* [K,H,W] or NULL */
-  float* v_records;
+  float* v_records;           /* [record sets, N, 16], accumulated */
+  int32_t sep_list;           /* list whose d loss / d means2d is ALSO accumulated into v_means2d_sep, or -1 */
+  float* v_means2d_sep;       /* [N,2] zeroed by the caller (densification statistics), or NULL */
 } MobgsBlendBwd;
 int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream);
 

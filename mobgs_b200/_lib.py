@@ -113,17 +113,29 @@ class Pack(C.Structure):
                 ("colors_per_cam", C.c_int32), ("depths", C.c_void_p), ("records", C.c_void_p)]
 
 
+class Lists(C.Structure):
+    _fields_ = [("rec_k", C.c_int32 * MAX_K), ("g_begin", C.c_int32 * MAX_K), ("g_end", C.c_int32 * MAX_K)]
+
+
+def make_lists(specs):
+    """specs: [(record_set, g_begin, g_end)] per list"""
+    l = Lists()
+    for i, (rk, g0, g1) in enumerate(specs):
+        l.rec_k[i], l.g_begin[i], l.g_end[i] = int(rk), int(g0), int(g1)
+    return l
+
+
 class TileCount(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("tight", C.c_int32),
-                ("g_begin", C.c_int32), ("g_end", C.c_int32),
+                ("lists", Lists),
                 ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p)]
 
 
 class TileSort(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("depths", C.c_void_p),
-                ("tight", C.c_int32), ("g_begin", C.c_int32), ("g_end", C.c_int32),
+                ("tight", C.c_int32), ("lists", Lists),
                 ("tile_offsets", C.c_void_p), ("tile_cursor", C.c_void_p),
                 ("capacity", C.c_int64), ("keys", C.c_void_p), ("keys_tmp", C.c_void_p),
                 ("sorted_ids", C.c_void_p)]
@@ -131,17 +143,17 @@ class TileSort(C.Structure):
 
 class BlendFwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_colors", C.c_void_p),
                 ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p)]
 
 
 class BlendBwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_alphas", C.c_void_p),
                 ("last_idx", C.c_void_p), ("v_out_colors", C.c_void_p), ("v_out_alphas", C.c_void_p),
-                ("v_records", C.c_void_p)]
+                ("v_records", C.c_void_p), ("sep_list", C.c_int32), ("v_means2d_sep", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):

@@ -85,14 +85,15 @@ __device__ __forceinline__ void for_each_tile(const GaussGeom& g, int radius, in
     }
 }
 
-__global__ void __launch_bounds__(256) tile_count_kernel(MobgsTileCount a, int tiles_x, int tiles_y) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)a.K * a.N) return;
+__global__ void __launch_bounds__(256) tile_count_kernel(const __grid_constant__ MobgsTileCount a, int tiles_x, int tiles_y) {
+  const size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= (size_t)a.K * a.N) return;
+  const int k = (int)(iv / a.N);
+  const int gid = (int)(iv - (size_t)k * a.N);
+  if (gid < a.lists.g_begin[k] || gid >= a.lists.g_end[k]) return;
+  const size_t i = (size_t)a.lists.rec_k[k] * a.N + gid;     // physical record
   const int radius = a.radii[i];
   if (radius <= 0) return;
-  const int k = (int)(i / a.N);
-  const int gid = (int)(i - (size_t)k * a.N);
-  if (gid < a.g_begin || gid >= a.g_end) return;
   const GaussGeom g = load_geom(a.records + i * kRecFloats);
   int* counts = a.tile_counts + (size_t)k * tiles_x * tiles_y;
   for_each_tile(g, radius, a.width, a.height, tiles_x, tiles_y, a.tight,
@@ -131,14 +132,15 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, 
   if (threadIdx.x == 0) out[n] = carry;
 }
 
-__global__ void __launch_bounds__(256) tile_emit_kernel(MobgsTileSort a, int tiles_x, int tiles_y) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)a.K * a.N) return;
+__global__ void __launch_bounds__(256) tile_emit_kernel(const __grid_constant__ MobgsTileSort a, int tiles_x, int tiles_y) {
+  const size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (iv >= (size_t)a.K * a.N) return;
+  const int k = (int)(iv / a.N);
+  const int gid = (int)(iv - (size_t)k * a.N);
+  if (gid < a.lists.g_begin[k] || gid >= a.lists.g_end[k]) return;
+  const size_t i = (size_t)a.lists.rec_k[k] * a.N + gid;
   const int radius = a.radii[i];
   if (radius <= 0) return;
-  const int k = (int)(i / a.N);
-  const int gid = (int)(i - (size_t)k * a.N);
-  if (gid < a.g_begin || gid >= a.g_end) return;
   const GaussGeom g = load_geom(a.records + i * kRecFloats);
   const size_t tbase = (size_t)k * tiles_x * tiles_y;
   const uint64_t key = ((uint64_t)__float_as_uint(a.depths[i]) << 32) | (uint32_t)gid;
@@ -273,7 +275,7 @@ using namespace mobgs;
 
 extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
-  MOBGS_REQUIRE(a->K >= 1 && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->K >= 1 && a->K <= MOBGS_MAX_K && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
   MOBGS_REQUIRE(a->tile_counts && a->tile_offsets, "NULL workspace");
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
@@ -290,7 +292,7 @@ extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
 
 extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
-  MOBGS_REQUIRE(a->K >= 1 && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->K >= 1 && a->K <= MOBGS_MAX_K && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
   MOBGS_REQUIRE(a->tile_offsets && a->tile_cursor, "NULL workspace");
   if (a->N == 0 || a->capacity == 0) return MOBGS_OK;
   MOBGS_REQUIRE(a->records && a->radii && a->depths && a->keys && a->keys_tmp && a->sorted_ids, "NULL pointer");

@@ -73,7 +73,7 @@ __device__ __forceinline__ int lane_id() {
 }
 
 template <int D>
-__global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd a, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
   __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd 
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
   const int beg = a.tile_offsets[blockIdx.x], end = a.tile_offsets[blockIdx.x + 1];
-  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)k * a.N * 4;
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
 
   float T = 1.f;
   float pix[D];
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(MobgsBlendFwd 
 }
 
 template <int D>
-__global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(MobgsBlendBwd a, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(MobgsBlendB
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
   const int beg = a.tile_offsets[blockIdx.x];
-  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)k * a.N * 4;
-  float* v_recs = a.v_records + (size_t)k * a.N * kRecFloats;
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
+  float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
 
   float T_final = 1.f, v_a = 0.f, bg_dot = 0.f;
   float v_c[D];
@@ -305,6 +305,10 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(MobgsBlendB
       for (int v = 0; v < kVec; ++v) {
         const float4 s = s4[v];
         if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) red_add_v4(dst + 4 * v, s.x, s.y, s.z, s.w);
+        if (v == 0 && a.v_means2d_sep && k == a.sep_list && (s.x != 0.f || s.y != 0.f)) {
+          atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid], s.x);
+          atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid] + 1, s.y);
+        }
       }
     }
   }
@@ -339,7 +343,7 @@ static void launch_bwd(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStr
 
 extern "C" int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
-  MOBGS_REQUIRE(a->K >= 1 && a->width > 0 && a->height > 0, "bad extents");
+  MOBGS_REQUIRE(a->K >= 1 && a->K <= MOBGS_MAX_K && a->width > 0 && a->height > 0, "bad extents");
   MOBGS_REQUIRE(a->D >= 1 && a->D <= MOBGS_MAX_COLORS, "D=%d out of range", a->D);
   MOBGS_REQUIRE(a->tile_offsets && a->out_colors && a->out_alphas && a->last_idx, "NULL pointer");
   MOBGS_REQUIRE(a->N == 0 || (a->records && a->sorted_ids), "NULL records / sorted_ids");

@@ -9,7 +9,7 @@
 
 namespace mobgs {
 
-constexpr int kMaxK = 32;       // sub-frames per launch (reference num_warp = 9)
+constexpr int kMaxK = MOBGS_MAX_K;   // sub-frames per launch (reference num_warp = 9)
 constexpr int kTile = MOBGS_TILE;
 constexpr int kTilePix = kTile * kTile;
 

@@ -100,20 +100,22 @@ def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_sp
 
 class _BlendRecords(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, g_range, tight, vsp_k):
+    def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, specs, tight, vsp_list):
         records = _f32c(records)
-        K, N = radii.shape
+        Kr, N = radii.shape
         dev = records.device
-        lists = build_tile_lists(records, radii, depths, width, height, tight, g_range)
+        lists = build_tile_lists(records, radii, depths, width, height, tight, specs)
+        K = lists.K
         bg = _f32c(backgrounds) if backgrounds is not None else None
         out_c = torch.empty(K, height, width, D, device=dev)
         out_a = torch.empty(K, height, width, device=dev)
         last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
-        a = L.BlendFwd(K, N, D, width, height, _p(records), _p(lists.tile_offsets), _p(lists.sorted_ids),
-                       _p(bg), _p(out_c), _p(out_a), _p(last))
+        a = L.BlendFwd(K, N, D, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
+                       _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
         L.call("mobgs_blend_fwd", a, _stream())
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
-        ctx.meta = (K, N, D, width, height, vsp_k, vsp is not None)
+        ctx.lists = lists.lists
+        ctx.meta = (K, Kr, N, D, width, height, vsp_list, vsp is not None)
         ctx.n_isect = lists.n_isect
         ctx.mark_non_differentiable(last)
         return out_c, out_a, last
@@ -121,24 +123,32 @@ class _BlendRecords(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_c, g_a, _g_last):
         records, offsets, sorted_ids, bg, out_a, last = ctx.saved_tensors
-        K, N, D, width, height, vsp_k, has_vsp = ctx.meta
-        v_rec = torch.zeros(K, N, L.REC, device=records.device)
-        g_c = _f32c(g_c) if g_c is not None else torch.zeros(K, height, width, D, device=records.device)
+        K, Kr, N, D, width, height, vsp_list, has_vsp = ctx.meta
+        dev = records.device
+        g_c = _f32c(g_c) if g_c is not None else torch.zeros(K, height, width, D, device=dev)
         g_a = _f32c(g_a) if g_a is not None else None
-        a = L.BlendBwd(K, N, D, width, height, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
-                       _p(last), _p(g_c), _p(g_a), _p(v_rec))
+        v_rec = torch.zeros(Kr, N, L.REC, device=dev)
+        v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
+        a = L.BlendBwd(K, N, D, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
+                       _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
         L.call("mobgs_blend_bwd", a, _stream())
-        v_vsp = v_rec[vsp_k, :, 0:2].unsqueeze(0).clone() if has_vsp else None
         return v_rec, None, None, None, v_vsp, None, None, None, None, None, None
 
 
-def blend_records(records, radii, depths, backgrounds, D, width, height, g_range=None, tight=True,
+def blend_records(records, radii, depths, backgrounds, D, width, height, specs=None, g_range=None, tight=True,
                   vsp: Optional[torch.Tensor] = None, vsp_k: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-    """-> (colors [K,H,W,D] incl. background, alphas [K,H,W]).  `vsp` is an optional leaf [1,N,2]
-    that receives d loss / d means2d of sub-frame vsp_k as its .grad (densification statistics,
-    reference train.py:634-648)."""
+    """-> (colors [K,H,W,D] incl. background, alphas [K,H,W]) for K lists.
+
+    specs: [(record_set, g_begin, g_end)] per list (default: one full-range list per record set;
+    `g_range=(g0, g1)` is shorthand for restricting every record set to one range).
+    `vsp` is an optional leaf [1,N,2] that receives d loss / d means2d of list `vsp_k` as its .grad
+    (densification statistics, reference train.py:634-648)."""
+    if specs is None and g_range is not None:
+        specs = [(k, g_range[0], g_range[1]) for k in range(radii.shape[0])]
+    if specs is not None:
+        specs = tuple(tuple(int(v) for v in s) for s in specs)
     out_c, out_a, _ = _BlendRecords.apply(records, radii, depths, backgrounds, vsp, int(D), int(width),
-                                          int(height), g_range, bool(tight), int(vsp_k))
+                                          int(height), specs, bool(tight), int(vsp_k))
     return out_c, out_a
 
 

@@ -78,20 +78,33 @@ def render(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, scal
     # leaf carrying the projected means whose .grad receives d loss / d means2d of *this* render
     vsp = records[:, :, 0:2].detach().clone().requires_grad_(True)
 
-    img10, alpha = fused.blend_records(records, radii, depths, bg10, 10, W, H, tight=TIGHT_TILES, vsp=vsp)
-    rendered_image, depth = _decode(dyn_pc, img10, alpha, cam)
+    # one binning / blend / decode launch chain for every image this call returns: the combined
+    # render plus (optionally) the dynamic-only and static-only renders are lists over the same
+    # projected records (reference: five separate rasterization() pipelines, :143,:163,:201,:236,:255)
+    specs = [(0, 0, N)]
+    if get_dynamic:
+        specs.append((0, Ns, N))
+    if get_static:
+        specs.append((0, 0, Ns))
+    n_lists = len(specs)
+    img10, alpha = fused.blend_records(records, radii, depths, bg10.expand(n_lists, -1), 10, W, H, specs=specs,
+                                       tight=TIGHT_TILES, vsp=vsp, vsp_k=0)
+    dec = dyn_pc.rgbdecoder
+    rgb, depth_all, _ = fused.decode(img10, alpha, cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
+                                     dec.mlp2.weight.reshape(3, 6))
+    rendered_image, depth = rgb[0], depth_all[0:1]
     radii0 = radii[0]
 
     d_image = d_depth = d_alpha = s_image = s_depth = s_alpha = None
+    i = 1
     if get_dynamic:
-        d10, da = fused.blend_records(records, radii, depths, bg10, 10, W, H, g_range=(Ns, N), tight=TIGHT_TILES)
-        d_image, d_depth = _decode(dyn_pc, d10, da, cam)
-        d_alpha = _alpha_render(da, bg_color)
+        d_image, d_depth = rgb[i], depth_all[i:i + 1]
+        d_alpha = _alpha_render(alpha[i:i + 1], bg_color)
+        i += 1
     if get_static:
-        s10, sa = fused.blend_records(records, radii, depths, bg10, 10, W, H, g_range=(0, Ns), tight=TIGHT_TILES)
         s_depth = rendered_image[..., -1]   # reference quirk kept (:250)
-        s_image, _ = _decode(dyn_pc, s10, sa, cam)
-        s_alpha = _alpha_render(sa, bg_color)
+        s_image = rgb[i]
+        s_alpha = _alpha_render(alpha[i:i + 1], bg_color)
 
     rendered_flow = ori_coord_map = None
     if warped and get_flow:

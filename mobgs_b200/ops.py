@@ -111,26 +111,32 @@ class TileLists:
         self.K, self.width, self.height = K, width, height
 
 
-def build_tile_lists(records, radii, depths, width, height, tight=True, g_range=None) -> TileLists:
-    """mobgs_tile_count -> (one 4-byte read-back of I) -> mobgs_tile_emit_sort."""
-    K, N = radii.shape
+def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None) -> TileLists:
+    """mobgs_tile_count -> (one 4-byte read-back of I) -> mobgs_tile_emit_sort.
+    specs: [(record_set, g_begin, g_end)] per list; default = one full-range list per record set."""
+    Kr, N = radii.shape
+    if specs is None:
+        specs = [(k, 0, N) for k in range(Kr)]
+    K = len(specs)
+    lists = L.make_lists(specs)
     dev = records.device
     tiles = math.ceil(width / L.TILE) * math.ceil(height / L.TILE)
     nt = K * tiles
     counts = torch.empty(nt, dtype=torch.int32, device=dev)
     offsets = torch.empty(nt + 1, dtype=torch.int32, device=dev)
-    g0, g1 = (0, N) if g_range is None else (int(g_range[0]), int(g_range[1]))
-    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), g0, g1, _p(counts), _p(offsets))
+    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), lists, _p(counts), _p(offsets))
     L.call("mobgs_tile_count", a, _stream())
     n_isect = int(offsets[-1].item())
     cap = max(n_isect, 1)
     keys = torch.empty(cap, dtype=torch.int64, device=dev)
     keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
     sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
-    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), g0, g1, _p(offsets),
+    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), lists, _p(offsets),
                    _p(counts), n_isect, _p(keys), _p(keys_tmp), _p(sorted_ids))
     L.call("mobgs_tile_emit_sort", b, _stream())
-    return TileLists(offsets, sorted_ids, n_isect, K, width, height)
+    tl = TileLists(offsets, sorted_ids, n_isect, K, width, height)
+    tl.lists = lists
+    return tl
 
 
 class _Rasterize(torch.autograd.Function):
@@ -163,10 +169,11 @@ class _Rasterize(torch.autograd.Function):
         out_c = torch.empty(K, height, width, D, device=dev)
         out_a = torch.empty(K, height, width, device=dev)
         last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
-        a = L.BlendFwd(K, N, D, width, height, _p(records), _p(lists.tile_offsets), _p(lists.sorted_ids),
-                       _p(bg), _p(out_c), _p(out_a), _p(last))
+        a = L.BlendFwd(K, N, D, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
+                       _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
         L.call("mobgs_blend_fwd", a, _stream())
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
+        ctx.lists = lists.lists
         ctx.meta = (K, N, D0, D, width, height, per_cam, append_depth)
         ctx.n_isect = lists.n_isect
         return out_c, out_a.unsqueeze(-1)
@@ -179,8 +186,8 @@ class _Rasterize(torch.autograd.Function):
         v_rec = torch.zeros(K, N, L.REC, device=dev)
         g_c = _f32c(g_c)
         g_a = _f32c(g_a) if g_a is not None else None
-        a = L.BlendBwd(K, N, D, width, height, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
-                       _p(last), _p(g_c), _p(g_a), _p(v_rec))
+        a = L.BlendBwd(K, N, D, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg),
+                       _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), -1, None)
         L.call("mobgs_blend_bwd", a, _stream())
         v_means2d = v_rec[..., 0:2]
         v_conics = v_rec[..., 3:6]
