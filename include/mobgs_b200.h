@@ -241,6 +241,13 @@ typedef struct {
   float* out_colors;
   float* out_alphas;
   int32_t* last_idx;
+  /* Optional fused epilogue (dec_rays != NULL; D must be 10): the per-pixel work of
+   * mobgs_decode_fwd — expected depth + Sandwich decoder — done while the pixel is still in
+   * registers.  out_rgb [K,3,H,W], out_depth [K,H,W] (NULL = skip). */
+  const float* dec_rays; int32_t dec_rays_per_k;
+  const float* dec_w1; const float* dec_w2;
+  float* out_rgb;
+  float* out_depth;
 } MobgsBlendFwd;
 int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
 
@@ -260,7 +267,24 @@ typedef struct {
   float* v_records;           /* [record sets, N, 16], accumulated */
   int32_t sep_list;           /* list whose d loss / d means2d is ALSO accumulated into v_means2d_sep, or -1 */
   float* v_means2d_sep;       /* [N,2] zeroed by the caller (densification statistics), or NULL */
+  /* Optional fused prologue (dec_rays != NULL; D must be 10): the VJP of the fused epilogue is
+   * evaluated per pixel instead of reading v_out_colors / v_out_alphas (which may then be NULL).
+   * out_colors = the forward's [K,H,W,10]; g_rgb [K,3,H,W], g_depth [K,H,W], g_alpha [K,H,W],
+   * g_mean [3,H,W] (gradient of the K-sub-frame mean; scaled by 1/K inside) — each may be NULL.
+   * v_rays as in MobgsDecodeBwd (NULL = not needed).  v_w_partial [MOBGS_DEC_SLOTS,90]: partial
+   * sums of (v_w1 | v_w2), zeroed by the caller and summed over the first axis afterwards. */
+  const float* dec_rays; int32_t dec_rays_per_k;
+  const float* dec_w1; const float* dec_w2;
+  const float* out_colors;
+  const float* g_rgb; const float* g_depth; const float* g_alpha; const float* g_mean;
+  float* v_rays;
+  float* v_w_partial;
 } MobgsBlendBwd;
+
+#define MOBGS_DEC_SLOTS 1024
+
+/* mean[i] = (1/K) sum_k rgb[k][i] + 1e-10 for i < n  (train.py:540-541). */
+int mobgs_subframe_mean(const float* rgb, float* mean, int32_t K, int64_t n, void* stream);
 int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------

@@ -145,7 +145,9 @@ class BlendFwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
                 ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_colors", C.c_void_p),
-                ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p)]
+                ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p),
+                ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
+                ("dec_w2", C.c_void_p), ("out_rgb", C.c_void_p), ("out_depth", C.c_void_p)]
 
 
 class BlendBwd(C.Structure):
@@ -153,7 +155,11 @@ class BlendBwd(C.Structure):
                 ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_alphas", C.c_void_p),
                 ("last_idx", C.c_void_p), ("v_out_colors", C.c_void_p), ("v_out_alphas", C.c_void_p),
-                ("v_records", C.c_void_p), ("sep_list", C.c_int32), ("v_means2d_sep", C.c_void_p)]
+                ("v_records", C.c_void_p), ("sep_list", C.c_int32), ("v_means2d_sep", C.c_void_p),
+                ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
+                ("dec_w2", C.c_void_p), ("out_colors", C.c_void_p), ("g_rgb", C.c_void_p),
+                ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p), ("g_mean", C.c_void_p),
+                ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):
@@ -223,6 +229,8 @@ def load() -> C.CDLL:
                     "Run `python -c 'import __graft_entry__ as g; g.build()'`. There is no fallback path."
                 ) from e
         lib = C.CDLL(LIB_PATH)
+        lib.mobgs_subframe_mean.restype = C.c_int
+        lib.mobgs_subframe_mean.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
         for name, struct in ENTRY_POINTS.items():
             fn = getattr(lib, name)   # AttributeError => symbol missing: fail loudly
             if struct is None:
@@ -240,12 +248,24 @@ KERNELS_PER_CALL = {
     "mobgs_project_fwd": 1, "mobgs_project_bwd": 1, "mobgs_synth_project_fwd": 1,
     "mobgs_synth_project_bwd": 1, "mobgs_pack_records": 1, "mobgs_tile_count": 2,
     "mobgs_tile_emit_sort": 2, "mobgs_blend_fwd": 1, "mobgs_blend_bwd": 1,
-    "mobgs_decode_fwd": 2, "mobgs_decode_bwd": 1, "mobgs_hexplane_mlp_fwd": 1,
+    "mobgs_decode_fwd": 1, "mobgs_decode_bwd": 1, "mobgs_hexplane_mlp_fwd": 1,
 }
 LAUNCH_COUNT = 0
 # optional per-entry-point device timing: TIMING = {} enables it; values are lists of
 # (start_event, end_event) recorded on the launching stream (bench.py reads them after a sync)
 TIMING = None
+
+
+DEC_SLOTS = 1024
+
+
+def subframe_mean(rgb_ptr, mean_ptr, K, n, stream) -> None:
+    global LAUNCH_COUNT
+    lib = load()
+    LAUNCH_COUNT += 1
+    rc = lib.mobgs_subframe_mean(C.c_void_p(rgb_ptr), C.c_void_p(mean_ptr), C.c_int32(K), C.c_int64(n), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"mobgs_subframe_mean failed (code {rc}): {lib.mobgs_last_error().decode()}")
 
 
 def call(name: str, args: C.Structure, stream: int) -> None:

@@ -12,6 +12,7 @@
 // reductions (REDG.128) per (tile, Gaussian) — gsplat issues 16 scalar atomics per (warp,
 // Gaussian).
 #include "common.cuh"
+#include "decode_math.cuh"
 
 namespace mobgs {
 
@@ -72,11 +73,41 @@ __device__ __forceinline__ int lane_id() {
   return l;
 }
 
-template <int D>
+// Transposing butterfly over NV (8 or 16) per-lane values: each stage halves the number of live
+// values per lane while doubling the lanes summed, so NV values cost NV shuffles in total (not
+// 5 * NV).  Afterwards g[0] of lane l holds the complete warp sum of value index `vidx`(l); lanes
+// with (l & owner_mask) == 0 own distinct values.
+template <int NV>
+__device__ __forceinline__ int butterfly_reduce(float (&g)[NV], int lane) {
+  int vidx = 0;
+  int n = NV / 2;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    if (n >= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < NV / 2; ++i) {
+        if (i < n) {
+          const float send = up ? g[i] : g[i + n];
+          const float keep = up ? g[i + n] : g[i];
+          g[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      vidx += up ? n : 0;
+      n >>= 1;
+    } else {
+      g[0] += __shfl_xor_sync(0xffffffffu, g[0], o);
+    }
+  }
+  return vidx;
+}
+
+template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
   __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
+  __shared__ __align__(16) float sdec[DEC ? 96 : 4];
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -84,6 +115,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_c
   const int lane = lane_id();
   const unsigned wbit = 1u << (tid >> 5);
   unsigned char* wlist = swl[tid >> 5];
+  if (DEC && tid < 90) sdec[tid] = tid < 72 ? a.dec_w1[tid] : a.dec_w2[tid - 72];   // visible after the first barrier
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -148,11 +180,29 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_c
     float* oc = a.out_colors + p * D;
     const float* bg = a.backgrounds ? a.backgrounds + (size_t)k * D : nullptr;
 #pragma unroll
-    for (int c = 0; c < D; ++c) oc[c] = bg ? pix[c] + T * bg[c] : pix[c];
+    for (int c = 0; c < D; ++c) { pix[c] = bg ? pix[c] + T * bg[c] : pix[c]; oc[c] = pix[c]; }
+  }
+  if (DEC) {
+    // fused epilogue: expected depth + Sandwich decoder on the pixel still held in registers
+    __syncthreads();                       // sdec is complete even for tiles with an empty list
+    if (inside) {
+      const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
+      DecW w; w.w1 = sdec; w.w2 = sdec + 72;
+      float v[10], rays[6], x[12], hpre[6], out[3];
+#pragma unroll
+      for (int c = 0; c < 10; ++c) v[c] = pix[c % D];
+      const float* rp = a.dec_rays + (a.dec_rays_per_k ? (size_t)k * 6 * P : 0) + pp;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+      sandwich_fwd(w, v, rays, x, hpre, out);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.out_rgb[((size_t)k * 3 + c) * P + pp] = out[c];
+      if (a.out_depth) a.out_depth[(size_t)k * P + pp] = v[9] / fmaxf(1.f - T, kEdFloor);
+    }
   }
 }
 
-template <int D>
+template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
@@ -160,6 +210,8 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __gri
   __shared__ unsigned smask[kBlendThreads];
   __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
   __shared__ int warp_max[kBlendThreads / 32];
+  __shared__ __align__(16) float sdec[DEC ? 96 : 4];
+  __shared__ float swg[DEC ? 96 : 4];      // CTA-level decoder weight-gradient accumulator
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -178,14 +230,78 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __gri
   int last = -1;
 #pragma unroll
   for (int c = 0; c < D; ++c) v_c[c] = 0.f;
+  if (DEC) {
+    if (tid < 96) { sdec[tid] = tid < 72 ? a.dec_w1[tid] : (tid < 90 ? a.dec_w2[tid - 72] : 0.f); swg[tid] = 0.f; }
+    __syncthreads();
+  }
   if (inside) {
     const size_t p = ((size_t)k * a.height + iy) * a.width + ix;
     T_final = 1.f - a.out_alphas[p];
     last = a.last_idx[p];
-    const float* vc = a.v_out_colors + p * D;
+    if (!DEC) {
+      const float* vc = a.v_out_colors + p * D;
 #pragma unroll
-    for (int c = 0; c < D; ++c) v_c[c] = vc[c];
-    if (a.v_out_alphas) v_a = a.v_out_alphas[p];
+      for (int c = 0; c < D; ++c) v_c[c] = vc[c];
+      if (a.v_out_alphas) v_a = a.v_out_alphas[p];
+    }
+  }
+  if (DEC) {
+    // fused prologue: VJP of (expected depth, Sandwich decoder, sub-frame mean) for this pixel
+    const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
+    DecW w; w.w1 = sdec; w.w2 = sdec + 72;
+    float x[12], hpre[6], gpre[3], ghpre[6];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) x[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { hpre[j] = 0.f; ghpre[j] = 0.f; }
+    gpre[0] = gpre[1] = gpre[2] = 0.f;
+    if (inside) {
+      const size_t p = (size_t)k * P + pp;
+      float v[10], rays[6], out[3], g_out[3], gv[9], g_rays[6];
+      const float2* vp2 = reinterpret_cast<const float2*>(a.out_colors + p * 10);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) { const float2 t2 = __ldg(vp2 + i); v[2 * i] = t2.x; v[2 * i + 1] = t2.y; }
+      const float* rp = a.dec_rays + (a.dec_rays_per_k ? (size_t)k * 6 * P : 0) + pp;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+      const float invK = 1.0f / (float)a.K;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        g_out[c] = a.g_mean ? __ldg(a.g_mean + c * P + pp) * invK : 0.f;
+        if (a.g_rgb) g_out[c] += __ldg(a.g_rgb + ((size_t)k * 3 + c) * P + pp);
+      }
+      sandwich_fwd(w, v, rays, x, hpre, out);
+      sandwich_bwd(w, hpre, out, g_out, gv, g_rays, gpre, ghpre);
+#pragma unroll
+      for (int c = 0; c < 9; ++c) v_c[c % D] = gv[c];
+      const float al = 1.f - T_final, den = fmaxf(al, kEdFloor);
+      const float gd = a.g_depth ? __ldg(a.g_depth + p) : 0.f;
+      v_c[9 % D] = gd / den;
+      v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * v[9] / (den * den) : 0.f);
+      if (a.v_rays) {
+        if (a.dec_rays_per_k) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) a.v_rays[((size_t)k * 6 + i) * P + pp] = g_rays[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + i * P + pp, g_rays[i]);
+        }
+      }
+    }
+    // 90 weight-gradient terms of this warp's 32 pixels: six 16-value butterflies -> CTA accumulator
+#pragma unroll
+    for (int grp = 0; grp < 6; ++grp) {
+      float t16[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int i = grp * 16 + q;       // 0..71: W1[j][i'] = ghpre[j] * x[i'];  72..89: W2[c][j] = gpre[c] * relu(hpre[j])
+        t16[q] = i < 72 ? ghpre[i / 12] * x[i % 12] : (i < 90 ? gpre[(i - 72) / 6] * fmaxf(hpre[(i - 72) % 6], 0.f) : 0.f);
+      }
+      const int vi = butterfly_reduce<16>(t16, lane);
+      if ((lane & 1) == 0 && t16[0] != 0.f) atomicAdd(&swg[grp * 16 + vi], t16[0]);
+    }
+  }
+  if (inside) {
     if (a.backgrounds) {
       const float* bg = a.backgrounds + (size_t)k * D;
 #pragma unroll
@@ -203,6 +319,8 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __gri
   for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
   if (lane == 0) warp_max[tid >> 5] = wmax;
   __syncthreads();
+  if (DEC && tid < 90 && swg[tid] != 0.f)
+    atomicAdd(a.v_w_partial + (size_t)(blockIdx.x % MOBGS_DEC_SLOTS) * 90 + tid, swg[tid]);
   int tile_last = -1;
 #pragma unroll
   for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
@@ -268,31 +386,7 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __gri
           g[5] = 0.5f * v_sigma * dy * dy;
         }
       }
-      // Transposing butterfly: each stage halves the number of live values per lane while doubling
-      // the lanes summed, so NV values cost NV shuffles in total (not 5 * NV); afterwards lane l
-      // holds the complete sum of value index bits(l) and the lanes add to shared memory in parallel.
-      int vidx = 0;
-      {
-        int n = NV / 2;
-#pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) {
-          if (n >= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < NV / 2; ++i) {
-              if (i < n) {
-                const float send = up ? g[i] : g[i + n];
-                const float keep = up ? g[i + n] : g[i];
-                g[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-              }
-            }
-            vidx += up ? n : 0;
-            n >>= 1;
-          } else {
-            g[0] += __shfl_xor_sync(0xffffffffu, g[0], o);
-          }
-        }
-      }
+      const int vidx = butterfly_reduce<NV>(g, lane);
       constexpr int kOwnerMask = NV == 16 ? 1 : 3;   // lanes whose low bits are 0 own a value
       if ((lane & kOwnerMask) == 0 && g[0] != 0.f) atomicAdd(&sacc[t][vidx], g[0]);
     }
@@ -320,11 +414,11 @@ using namespace mobgs;
 
 template <int D>
 static void launch_fwd(const MobgsBlendFwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
-  blend_fwd_kernel<D><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+  blend_fwd_kernel<D, false><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
 }
 template <int D>
 static void launch_bwd(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
-  blend_bwd_kernel<D><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+  blend_bwd_kernel<D, false><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
 }
 
 #define MOBGS_DISPATCH_D(D, FN, ...)                                   \
@@ -348,6 +442,11 @@ extern "C" int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream) {
   MOBGS_REQUIRE(a->tile_offsets && a->out_colors && a->out_alphas && a->last_idx, "NULL pointer");
   MOBGS_REQUIRE(a->N == 0 || (a->records && a->sorted_ids), "NULL records / sorted_ids");
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  if (a->dec_rays) {
+    MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_rgb, "fused decode epilogue needs D=10, w1, w2, out_rgb");
+    blend_fwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+    return check_launch("blend_decode_fwd");
+  }
   MOBGS_DISPATCH_D(a->D, launch_fwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
   return check_launch("blend_fwd");
 }
@@ -357,9 +456,16 @@ extern "C" int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream) {
   MOBGS_REQUIRE(a->K >= 1 && a->width > 0 && a->height > 0, "bad extents");
   MOBGS_REQUIRE(a->D >= 1 && a->D <= MOBGS_MAX_COLORS, "D=%d out of range", a->D);
   if (a->N == 0) return MOBGS_OK;
-  MOBGS_REQUIRE(a->records && a->tile_offsets && a->sorted_ids && a->out_alphas && a->last_idx &&
-                    a->v_out_colors && a->v_records, "NULL pointer");
+  MOBGS_REQUIRE(a->records && a->tile_offsets && a->sorted_ids && a->out_alphas && a->last_idx && a->v_records,
+                "NULL pointer");
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
+  if (a->dec_rays) {
+    MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_colors && a->v_w_partial,
+                  "fused decode prologue needs D=10, w1, w2, out_colors, v_w_partial");
+    blend_bwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+    return check_launch("blend_decode_bwd");
+  }
+  MOBGS_REQUIRE(a->v_out_colors, "v_out_colors must not be NULL");
   MOBGS_DISPATCH_D(a->D, launch_bwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
   return check_launch("blend_bwd");
 }

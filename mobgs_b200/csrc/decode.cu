@@ -5,45 +5,11 @@
 // per pixel and sub-frame).  The 90 decoder-weight gradients are reduced warp -> CTA -> one
 // atomicAdd per CTA of a persistent grid.
 #include "common.cuh"
+#include "decode_math.cuh"
 
 namespace mobgs {
 
 constexpr int kDecThreads = 128;
-constexpr float kEdFloor = 1e-10f;
-constexpr float kMeanEps = 1e-10f;
-
-// The 90 decoder weights stay in shared memory (broadcast LDS.128 reads): the backward already
-// needs 90 registers per thread for the weight-gradient accumulators.
-struct DecW { const float* w1; const float* w2; };
-
-__device__ __forceinline__ void load_w(DecW& w, const float* w1, const float* w2, float* smem) {
-  for (int i = threadIdx.x; i < 90; i += blockDim.x) smem[i] = i < 72 ? w1[i] : w2[i - 72];
-  __syncthreads();
-  w.w1 = smem;
-  w.w2 = smem + 72;
-}
-
-// x = [spec(3), timefeat(3), rays(6)]
-__device__ __forceinline__ void sandwich_fwd(const DecW& w, const float v[10], const float rays[6],
-                                             float x[12], float hpre[6], float out[3]) {
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { x[i] = v[3 + i]; x[6 + i] = rays[i]; }
-#pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 12; ++i) s += w.w1[12 * j + i] * x[i];
-    hpre[j] = s;
-  }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    float s = v[c];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) s += w.w2[6 * c + j] * fmaxf(hpre[j], 0.f);
-    out[c] = 1.0f / (1.0f + expf(-s));
-  }
-}
-
 // img10 is channels-last (40 B per pixel): a CTA moves its 256-pixel block through shared memory
 // with coalesced 8-byte accesses instead of letting every thread walk its own 40-byte record.
 __device__ __forceinline__ void stage_in(float* simg, const float* gsrc, int npx) {
@@ -240,4 +206,11 @@ extern "C" int mobgs_decode_bwd(const MobgsDecodeBwd* a, void* stream) {
   const size_t nblk = (P + kDecThreads - 1) / kDecThreads;
   decode_bwd_kernel<<<decode_grid(nblk * a->K, 9), kDecThreads, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("decode_bwd");
+}
+
+extern "C" int mobgs_subframe_mean(const float* rgb, float* mean, int32_t K, int64_t n, void* stream) {
+  MOBGS_REQUIRE(rgb && mean && K >= 1 && n >= 0, "bad arguments");
+  if (n == 0) return MOBGS_OK;
+  subframe_mean_kernel<<<decode_grid((size_t)(n + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(rgb, mean, K, (size_t)n);
+  return check_launch("subframe_mean");
 }

@@ -196,3 +196,75 @@ def decode(img10, alpha, rays, w1, w2, want_mean=False):
     """img10 [K,H,W,10], alpha [K,H,W], rays [K|1,6,H,W], w1 [6,12], w2 [3,6]
     -> rgb [K,3,H,W], expected depth [K,H,W], blur-model mean [3,H,W] (or empty)."""
     return _Decode.apply(img10, alpha, rays, w1, w2, bool(want_mean))
+
+
+class _BlendDecode(torch.autograd.Function):
+    """Stage B + epilogue in one kernel pair: binning + sort + blend with the expected-depth
+    division and the Sandwich decoder applied while the pixel is in registers (forward), and their
+    VJP evaluated in the blend backward's prologue — img10 gradients never exist in HBM."""
+
+    @staticmethod
+    def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
+                vsp_list, want_mean):
+        records = _f32c(records)
+        rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
+        Kr, N = radii.shape
+        dev = records.device
+        lists = build_tile_lists(records, radii, depths, width, height, tight, specs)
+        K = lists.K
+        assert rays.shape[0] in (1, K) and rays.shape[1] == 6
+        per_k = int(rays.shape[0] == K and K > 1)
+        bg = _f32c(backgrounds) if backgrounds is not None else None
+        img10 = torch.empty(K, height, width, 10, device=dev)
+        alpha = torch.empty(K, height, width, device=dev)
+        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+        rgb = torch.empty(K, 3, height, width, device=dev)
+        depth = torch.empty(K, height, width, device=dev)
+        a = L.BlendFwd(K, N, 10, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
+                       _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
+                       _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth))
+        L.call("mobgs_blend_fwd", a, _stream())
+        if want_mean:
+            mean = torch.empty(3, height, width, device=dev)
+            L.subframe_mean(_p(rgb), _p(mean), K, 3 * height * width, _stream())
+        else:
+            mean = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(mean)
+        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
+        ctx.lists = lists.lists
+        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k)
+        ctx.n_isect = lists.n_isect
+        return rgb, depth, alpha, mean
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_alpha, g_mean):
+        records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2 = ctx.saved_tensors
+        K, Kr, N, width, height, vsp_list, has_vsp, per_k = ctx.meta
+        dev = records.device
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else None
+        g_depth = _f32c(g_depth) if g_depth is not None else None
+        g_alpha = _f32c(g_alpha) if g_alpha is not None else None
+        g_mean = _f32c(g_mean) if (g_mean is not None and g_mean.numel() > 0) else None
+        v_rec = torch.zeros(Kr, N, L.REC, device=dev)
+        v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
+        v_rays = None
+        if ctx.needs_input_grad[5]:
+            v_rays = torch.empty_like(rays) if per_k else torch.zeros_like(rays)
+        v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
+        a = L.BlendBwd(K, N, 10, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg),
+                       _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
+                       _p(rays), per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth), _p(g_alpha), _p(g_mean),
+                       _p(v_rays), _p(v_wp))
+        L.call("mobgs_blend_bwd", a, _stream())
+        v_w = v_wp.sum(0)
+        return (v_rec, None, None, None, v_vsp, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6),
+                None, None, None, None, None, None)
+
+
+def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, height, specs=None, tight=True,
+                 vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False):
+    """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty)."""
+    if specs is not None:
+        specs = tuple(tuple(int(v) for v in s) for s in specs)
+    return _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
+                              specs, bool(tight), int(vsp_k), bool(want_mean))

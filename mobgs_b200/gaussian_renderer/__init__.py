@@ -87,11 +87,10 @@ def render(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, scal
     if get_static:
         specs.append((0, 0, Ns))
     n_lists = len(specs)
-    img10, alpha = fused.blend_records(records, radii, depths, bg10.expand(n_lists, -1), 10, W, H, specs=specs,
-                                       tight=TIGHT_TILES, vsp=vsp, vsp_k=0)
     dec = dyn_pc.rgbdecoder
-    rgb, depth_all, _ = fused.decode(img10, alpha, cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
-                                     dec.mlp2.weight.reshape(3, 6))
+    rgb, depth_all, alpha, _ = fused.blend_decode(
+        records, radii, depths, bg10.expand(n_lists, -1), cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
+        dec.mlp2.weight.reshape(3, 6), W, H, specs=specs, tight=TIGHT_TILES, vsp=vsp, vsp_k=0)
     rendered_image, depth = rgb[0], depth_all[0:1]
     radii0 = radii[0]
 
@@ -173,8 +172,11 @@ def get_flow(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, de
                                 radii[mid], W, H, tight=TIGHT_TILES)
     mid2exp_coord_map = grid + m2e_flow
 
-    img10, a10 = fused.blend_records(rec[exp], radii[exp], depths[exp], bg10, 10, W, H, tight=TIGHT_TILES)
-    latent_img, _ = _decode(dyn_pc, img10, a10, cam)
+    dec = dyn_pc.rgbdecoder
+    rgb, _, _, _ = fused.blend_decode(rec[exp], radii[exp], depths[exp], bg10, cam.cam_ray,
+                                      dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6), W, H,
+                                      tight=TIGHT_TILES)
+    latent_img = rgb[0]
     return exp2mid_coord_map, mid2exp_coord_map, latent_img, latent_alpha
 
 

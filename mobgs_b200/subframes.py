@@ -3,7 +3,7 @@ view (train.py:441, :502-516, :540-541): K latent sub-frame `render()` calls fol
 `mean(stack(images)) + 1e-10`.  Here all K sub-frames share one launch of every kernel:
 
     synth+project (K cameras, K times)  ->  bin + per-tile sort (K*T segments)
-    ->  blend (K*T CTAs)  ->  decode + expected depth + sub-frame mean
+    ->  blend (K*T CTAs) with the expected-depth + decoder epilogue fused in  ->  sub-frame mean
 
 and the backward mirrors it, ending in one pass that writes every parameter gradient once.
 """
@@ -38,10 +38,9 @@ def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, 
         viewmats, Ks, t_spline, t_poly, width, height, offset=offset)
     vsp = records[ck:ck + 1, :, 0:2].detach().clone().requires_grad_(True)
     bg10 = _bg10(bg_color, dev).expand(K, -1)
-    img10, alpha = fused.blend_records(records, radii, depths, bg10, 10, width, height, tight=tight,
-                                       vsp=vsp, vsp_k=ck)
     dec = dyn_pc.rgbdecoder
-    rgb, depth, mean = fused.decode(img10, alpha, rays, dec.mlp1.weight.reshape(6, 12),
-                                    dec.mlp2.weight.reshape(3, 6), want_mean=True)
+    rgb, depth, alpha, mean = fused.blend_decode(
+        records, radii, depths, bg10, rays, dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6),
+        width, height, tight=tight, vsp=vsp, vsp_k=ck, want_mean=True)
     return {"render": mean, "subframes": rgb, "depth": depth, "alpha": alpha, "radii": radii,
             "viewspace_points": vsp, "visibility_filter": radii[ck] > 0}
