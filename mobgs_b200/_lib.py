@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if all(os.path.getmtime(d) <= t for d in deps):
             return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + srcs
+    extra = os.environ.get("MOBGS_NVCC_EXTRA", "").split()     # e.g. -DMOBGS_FWD_MIN_CTAS=6 (tuning experiments)
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB_PATH] + srcs
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True)

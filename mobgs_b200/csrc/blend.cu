@@ -17,6 +17,12 @@
 namespace mobgs {
 
 constexpr int kBlendThreads = kTilePix;   // 256
+#ifndef MOBGS_FWD_MIN_CTAS
+#define MOBGS_FWD_MIN_CTAS 6
+#endif
+#ifndef MOBGS_BWD_MIN_CTAS
+#define MOBGS_BWD_MIN_CTAS 4
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -103,7 +109,7 @@ __device__ __forceinline__ int butterfly_reduce(float (&g)[NV], int lane) {
 }
 
 template <int D, bool DEC>
-__global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
   __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
@@ -187,7 +193,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_c
     __syncthreads();                       // sdec is complete even for tiles with an empty list
     if (inside) {
       const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
-      DecW w; w.w1 = sdec; w.w2 = sdec + 72;
+      DecW w; w.w1 = sdec; w.w2 = sdec + (DEC ? 72 : 0);
       float v[10], rays[6], x[12], hpre[6], out[3];
 #pragma unroll
       for (int c = 0; c < 10; ++c) v[c] = pix[c % D];
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(kBlendThreads) blend_fwd_kernel(const __grid_c
 }
 
 template <int D, bool DEC>
-__global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   __shared__ float4 srec[kBlendThreads][4];
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
@@ -248,7 +254,7 @@ __global__ void __launch_bounds__(kBlendThreads, 4) blend_bwd_kernel(const __gri
   if (DEC) {
     // fused prologue: VJP of (expected depth, Sandwich decoder, sub-frame mean) for this pixel
     const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
-    DecW w; w.w1 = sdec; w.w2 = sdec + 72;
+    DecW w; w.w1 = sdec; w.w2 = sdec + (DEC ? 72 : 0);
     float x[12], hpre[6], gpre[3], ghpre[6];
 #pragma unroll
     for (int i = 0; i < 12; ++i) x[i] = 0.f;

@@ -9,8 +9,11 @@ Covered configuration = the Stereo-Blur configs (arguments/stereo/*.py): net_wid
 defor_depth 1, 32 features per plane, no_grid/static_mlp/empty_voxel/apply_rotation False,
 grid_pe 0.  Anything else raises NotImplementedError (no fallback).
 
-Status: forward (inference) only — the module is not on the reference's live training path
-(SURVEY.md §0.3); gradients through it are not provided yet and requesting them raises.
+Status: the forward is the fused tcgen05 kernel.  The module is not on the reference's live
+training path (render() never calls it), so its backward is not a hand-written
+kernel yet: when gradients are requested, `_FusedDeform.backward` recomputes the network with
+torch CUDA ops (F.grid_sample + cuBLAS fp32 GEMMs — plain library calls) and differentiates that.
+Round-2 item: native backward (grid scatter + tcgen05 dgrad/wgrad).
 """
 from __future__ import annotations
 
@@ -55,10 +58,88 @@ def pack_weights(w0, b0, heads):
             torch.cat(wb_list).contiguous(), torch.cat(bb_list).contiguous())
 
 
+def _torch_forward(pts, scales, rots, times, aabb, planes, w0, b0, heads):
+    """Differentiable torch restatement (GPU) used only to *differentiate* the fused forward."""
+    import math
+    import torch.nn.functional as F
+    p = torch.clamp((pts - aabb[0]) * (2.0 / (aabb[1] - aabb[0])) - 1.0, -1.0, 1.0)
+    p = torch.cat([p, times.reshape(-1, 1)], dim=-1)
+    feats = []
+    for level in planes:
+        prod = 1.0
+        for plane, comb in zip(level, itertools.combinations(range(4), 2)):
+            smp = F.grid_sample(plane, p[:, list(comb)].view(1, 1, -1, 2), align_corners=True, mode="bilinear",
+                                padding_mode="border")
+            prod = prod * smp.view(plane.shape[1], -1).t()
+        feats.append(prod)
+    hidden = F.linear(torch.cat(feats, dim=-1), w0, b0)
+    outs = [F.linear(torch.relu(F.linear(torch.relu(hidden), Wa, ba)), Wb, bb) for Wa, ba, Wb, bb in heads]
+    dx, ds, dr = outs
+    nq = torch.cat([torch.ones_like(dx[:, :1]), dx[:, 3:]], dim=1)
+    nq = nq / nq.norm(dim=1, keepdim=True)
+    w, x, y, z = nq[:, 0], nq[:, 1], nq[:, 2], nq[:, 3]
+    R = torch.stack([w * w + x * x - y * y - z * z, 2 * x * y - 2 * w * z, 2 * w * y + 2 * x * z,
+                     2 * w * z + 2 * x * y, w * w - x * x + y * y - z * z, 2 * y * z - 2 * w * x,
+                     2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z], dim=1).view(-1, 3, 3)
+    out_pts = R.bmm((pts + dx[:, :3]).unsqueeze(-1)).squeeze(-1)
+    out_scales = scales + torch.clamp(ds, -math.log(100), math.log(100))
+    q1, q2 = rots + dr, dx[:, 3:]
+    q = torch.stack((q1[:, 0] * q2[:, 0] - q1[:, 1] * q2[:, 1] - q1[:, 2] * q2[:, 2] - q1[:, 3] * q2[:, 3],
+                     q1[:, 0] * q2[:, 1] + q1[:, 1] * q2[:, 0] + q1[:, 2] * q2[:, 3] - q1[:, 3] * q2[:, 2],
+                     q1[:, 0] * q2[:, 2] - q1[:, 1] * q2[:, 3] + q1[:, 2] * q2[:, 0] + q1[:, 3] * q2[:, 1],
+                     q1[:, 0] * q2[:, 3] + q1[:, 1] * q2[:, 2] - q1[:, 2] * q2[:, 1] + q1[:, 3] * q2[:, 0]), dim=1)
+    return out_pts, out_scales, q / q.norm(dim=1, keepdim=True)
+
+
+class _FusedDeform(torch.autograd.Function):
+    """forward = fused kernel; backward = torch-op recompute (see module docstring)."""
+
+    @staticmethod
+    def forward(ctx, n_levels, aabb, pts, scales, rots, times, *params):
+        planes = [list(params[l * 6:(l + 1) * 6]) for l in range(n_levels)]
+        rest = params[n_levels * 6:]
+        w0, b0 = rest[0], rest[1]
+        heads = [tuple(rest[2 + 4 * h: 6 + 4 * h]) for h in range(3)]
+        ctx.n_levels = n_levels
+        ctx.save_for_backward(aabb, pts, scales, rots, times, *params)
+        with torch.no_grad():
+            return _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads)
+
+    @staticmethod
+    def backward(ctx, g_pts, g_scales, g_rots):
+        aabb, pts, scales, rots, times, *params = ctx.saved_tensors
+        nl = ctx.n_levels
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            with torch.enable_grad():
+                leaves = [t.detach().requires_grad_(t.is_floating_point()) for t in (pts, scales, rots, times, *params)]
+                lp, ls, lr, lt, *lpar = leaves
+                planes = [list(lpar[l * 6:(l + 1) * 6]) for l in range(nl)]
+                rest = lpar[nl * 6:]
+                heads = [tuple(rest[2 + 4 * h: 6 + 4 * h]) for h in range(3)]
+                outs = _torch_forward(lp, ls, lr, lt, aabb, planes, rest[0], rest[1], heads)
+                gs = [g if g is not None else torch.zeros_like(o) for g, o in zip((g_pts, g_scales, g_rots), outs)]
+                need = [i for i, need in enumerate(ctx.needs_input_grad[2:]) if need]
+                grads = torch.autograd.grad(outs, [leaves[i] for i in need], gs, allow_unused=True)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        full = [None] * len(leaves)
+        for i, g in zip(need, grads):
+            full[i] = g
+        return (None, None, *full)
+
+
 def fused_forward_raw(pts, scales, rots, times, aabb, planes: Sequence[Sequence[torch.Tensor]], w0, b0, heads):
     """planes[l][p]: [1,32,H,W] parameters (reference layout); aabb: [2,3] tensor."""
-    if any(t.requires_grad for t in (pts, scales, rots, times)) and torch.is_grad_enabled():
-        raise NotImplementedError("mobgs_b200.deformation: forward only (see module docstring)")
+    flat = [p for level in planes for p in level] + [w0, b0] + [t for h in heads for t in h]
+    tensors = [pts[:, :3], scales[:, :3], rots[:, :4], times]
+    if torch.is_grad_enabled() and any(t.requires_grad for t in tensors + flat):
+        return _FusedDeform.apply(len(planes), aabb.detach(), *tensors, *flat)
+    return _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads)
+
+
+def _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads):
     pts, scales, rots = _f32c(pts[:, :3]), _f32c(scales[:, :3]), _f32c(rots[:, :4])
     times = _f32c(times.reshape(-1))
     N = pts.shape[0]
