@@ -234,6 +234,7 @@ int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream);
 typedef struct {
   int32_t K, N, D, width, height;
   MobgsLists lists;
+  int64_t list_capacity;      /* entries valid in sorted_ids (the `capacity` given to mobgs_tile_emit_sort) */
   const float* records;
   const int32_t* tile_offsets;
   const int32_t* sorted_ids;
@@ -256,6 +257,7 @@ int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
 typedef struct {
   int32_t K, N, D, width, height;
   MobgsLists lists;
+  int64_t list_capacity;
   const float* records;
   const int32_t* tile_offsets;
   const int32_t* sorted_ids;

@@ -144,7 +144,8 @@ class TileSort(C.Structure):
 
 class BlendFwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("height", C.c_int32), ("lists", Lists), ("list_capacity", C.c_int64), ("records", C.c_void_p),
+                ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_colors", C.c_void_p),
                 ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p),
                 ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
@@ -153,7 +154,8 @@ class BlendFwd(C.Structure):
 
 class BlendBwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("width", C.c_int32),
-                ("height", C.c_int32), ("lists", Lists), ("records", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("height", C.c_int32), ("lists", Lists), ("list_capacity", C.c_int64), ("records", C.c_void_p),
+                ("tile_offsets", C.c_void_p),
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_alphas", C.c_void_p),
                 ("last_idx", C.c_void_p), ("v_out_colors", C.c_void_p), ("v_out_alphas", C.c_void_p),
                 ("v_records", C.c_void_p), ("sep_list", C.c_int32), ("v_means2d_sep", C.c_void_p),

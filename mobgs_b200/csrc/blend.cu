@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
-  const int beg = a.tile_offsets[blockIdx.x], end = a.tile_offsets[blockIdx.x + 1];
+  const int cap = (int)min(a.list_capacity, (int64_t)0x7fffffff);
+  const int beg = min(a.tile_offsets[blockIdx.x], cap), end = min(a.tile_offsets[blockIdx.x + 1], cap);
   const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
 
   float T = 1.f;
@@ -227,7 +228,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
-  const int beg = a.tile_offsets[blockIdx.x];
+  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
   const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
   float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
 

@@ -104,17 +104,21 @@ class _BlendRecords(torch.autograd.Function):
         records = _f32c(records)
         Kr, N = radii.shape
         dev = records.device
-        lists = build_tile_lists(records, radii, depths, width, height, tight, specs)
-        K = lists.K
+        K = Kr if specs is None else len(specs)
         bg = _f32c(backgrounds) if backgrounds is not None else None
-        out_c = torch.empty(K, height, width, D, device=dev)
-        out_a = torch.empty(K, height, width, device=dev)
-        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
-        a = L.BlendFwd(K, N, D, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
-                       _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
-        L.call("mobgs_blend_fwd", a, _stream())
+
+        def blend(lists):
+            out_c = torch.empty(K, height, width, D, device=dev)
+            out_a = torch.empty(K, height, width, device=dev)
+            last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+            a = L.BlendFwd(K, N, D, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
+                           _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
+            L.call("mobgs_blend_fwd", a, _stream())
+            return out_c, out_a, last
+
+        lists, (out_c, out_a, last) = build_tile_lists(records, radii, depths, width, height, tight, specs, consume=blend)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
-        ctx.lists = lists.lists
+        ctx.lists, ctx.capacity = lists.lists, lists.capacity
         ctx.meta = (K, Kr, N, D, width, height, vsp_list, vsp is not None)
         ctx.n_isect = lists.n_isect
         ctx.mark_non_differentiable(last)
@@ -129,8 +133,8 @@ class _BlendRecords(torch.autograd.Function):
         g_a = _f32c(g_a) if g_a is not None else None
         v_rec = torch.zeros(Kr, N, L.REC, device=dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
-        a = L.BlendBwd(K, N, D, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg), _p(out_a),
-                       _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
+        a = L.BlendBwd(K, N, D, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
+                       _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
         L.call("mobgs_blend_bwd", a, _stream())
         return v_rec, None, None, None, v_vsp, None, None, None, None, None, None
 
@@ -210,20 +214,25 @@ class _BlendDecode(torch.autograd.Function):
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
         dev = records.device
-        lists = build_tile_lists(records, radii, depths, width, height, tight, specs)
-        K = lists.K
+        K = Kr if specs is None else len(specs)
         assert rays.shape[0] in (1, K) and rays.shape[1] == 6
         per_k = int(rays.shape[0] == K and K > 1)
         bg = _f32c(backgrounds) if backgrounds is not None else None
-        img10 = torch.empty(K, height, width, 10, device=dev)
-        alpha = torch.empty(K, height, width, device=dev)
-        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
-        rgb = torch.empty(K, 3, height, width, device=dev)
-        depth = torch.empty(K, height, width, device=dev)
-        a = L.BlendFwd(K, N, 10, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
-                       _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
-                       _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth))
-        L.call("mobgs_blend_fwd", a, _stream())
+
+        def blend(lists):
+            img10 = torch.empty(K, height, width, 10, device=dev)
+            alpha = torch.empty(K, height, width, device=dev)
+            last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+            rgb = torch.empty(K, 3, height, width, device=dev)
+            depth = torch.empty(K, height, width, device=dev)
+            a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
+                           _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
+                           _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth))
+            L.call("mobgs_blend_fwd", a, _stream())
+            return img10, alpha, last, rgb, depth
+
+        lists, (img10, alpha, last, rgb, depth) = build_tile_lists(records, radii, depths, width, height, tight,
+                                                                   specs, consume=blend)
         if want_mean:
             mean = torch.empty(3, height, width, device=dev)
             L.subframe_mean(_p(rgb), _p(mean), K, 3 * height * width, _stream())
@@ -231,7 +240,7 @@ class _BlendDecode(torch.autograd.Function):
             mean = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(mean)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
-        ctx.lists = lists.lists
+        ctx.lists, ctx.capacity = lists.lists, lists.capacity
         ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k)
         ctx.n_isect = lists.n_isect
         return rgb, depth, alpha, mean
@@ -251,8 +260,8 @@ class _BlendDecode(torch.autograd.Function):
         if ctx.needs_input_grad[5]:
             v_rays = torch.empty_like(rays) if per_k else torch.zeros_like(rays)
         v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
-        a = L.BlendBwd(K, N, 10, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg),
-                       _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
+        a = L.BlendBwd(K, N, 10, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
+                       _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
                        _p(rays), per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth), _p(g_alpha), _p(g_mean),
                        _p(v_rays), _p(v_wp))
         L.call("mobgs_blend_bwd", a, _stream())

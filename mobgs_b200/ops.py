@@ -7,6 +7,7 @@ there is no CPU path and none is attempted.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -108,15 +109,31 @@ class TileLists:
         self.tile_offsets = tile_offsets
         self.sorted_ids = sorted_ids
         self.n_isect = n_isect
+        self.capacity = n_isect
         self.K, self.width, self.height = K, width, height
 
 
-def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None) -> TileLists:
-    """mobgs_tile_count -> (one 4-byte read-back of I) -> mobgs_tile_emit_sort.
-    specs: [(record_set, g_begin, g_end)] per list; default = one full-range list per record set."""
+# Speculative list sizing: the number of tile/Gaussian intersections I is only known on the device
+# after mobgs_tile_count.  Reading it back before sizing the lists stalls the launch pipeline in
+# the middle of the forward.  Instead the lists are sized from the last I seen for the same launch
+# shape (+25 %), emit/sort/blend are enqueued immediately (the kernels never write or read beyond
+# the capacity they are given), I travels to pinned host memory asynchronously, and only after
+# everything is enqueued does the host check it — redoing emit/sort/blend with the exact size in the
+# (rare) overflow case, so results are always those of the exactly-sized lists.
+_CAP_CACHE = {}
+SPECULATIVE_LISTS = os.environ.get("MOBGS_SPECULATIVE_LISTS", "1") != "0"
+
+
+def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None):
+    """mobgs_tile_count -> mobgs_tile_emit_sort (-> consume(lists)).
+
+    specs: [(record_set, g_begin, g_end)] per list; default = one full-range list per record set.
+    consume: optional callable(lists) that enqueues the kernels using the lists (blend); when given,
+    returns (lists, consume(lists)) and sizes the lists speculatively (see above); otherwise reads I
+    back synchronously and returns lists."""
     Kr, N = radii.shape
     if specs is None:
-        specs = [(k, 0, N) for k in range(Kr)]
+        specs = tuple((k, 0, N) for k in range(Kr))
     K = len(specs)
     lists = L.make_lists(specs)
     dev = records.device
@@ -126,17 +143,41 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     offsets = torch.empty(nt + 1, dtype=torch.int32, device=dev)
     a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), lists, _p(counts), _p(offsets))
     L.call("mobgs_tile_count", a, _stream())
-    n_isect = int(offsets[-1].item())
-    cap = max(n_isect, 1)
-    keys = torch.empty(cap, dtype=torch.int64, device=dev)
-    keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
-    sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
-    b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), lists, _p(offsets),
-                   _p(counts), n_isect, _p(keys), _p(keys_tmp), _p(sorted_ids))
-    L.call("mobgs_tile_emit_sort", b, _stream())
-    tl = TileLists(offsets, sorted_ids, n_isect, K, width, height)
-    tl.lists = lists
-    return tl
+
+    def emit_sort(cap):
+        cap = max(int(cap), 1)
+        keys = torch.empty(cap, dtype=torch.int64, device=dev)
+        keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
+        sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+        b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), lists, _p(offsets),
+                       _p(counts), cap, _p(keys), _p(keys_tmp), _p(sorted_ids))
+        L.call("mobgs_tile_emit_sort", b, _stream())
+        tl = TileLists(offsets, sorted_ids, None, K, width, height)
+        tl.lists, tl.capacity = lists, cap
+        return tl
+
+    key = (K, N, width, height, tuple(specs), bool(tight), dev.index)
+    guess = _CAP_CACHE.get(key)
+    if consume is None or guess is None or not SPECULATIVE_LISTS:
+        n_isect = int(offsets[-1].item())
+        tl = emit_sort(n_isect)
+        tl.n_isect = n_isect
+        _CAP_CACHE[key] = int(n_isect * 1.25) + 4096
+        return tl if consume is None else (tl, consume(tl))
+    host_n = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host_n.copy_(offsets[-1:], non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    tl = emit_sort(guess)
+    out = consume(tl)
+    ev.synchronize()
+    n_isect = int(host_n[0])
+    if n_isect > tl.capacity:           # overflow: redo with the exact size
+        tl = emit_sort(n_isect)
+        out = consume(tl)
+    tl.n_isect = n_isect
+    _CAP_CACHE[key] = max(int(n_isect * 1.25) + 4096, int(guess * 0.9))
+    return tl, out
 
 
 class _Rasterize(torch.autograd.Function):
@@ -160,18 +201,23 @@ class _Rasterize(torch.autograd.Function):
         pk = L.Pack(K, N, D0, _p(means2d), _p(conics), _p(opacities), _p(colors), int(per_cam),
                     _p(depths) if append_depth else None, _p(records))
         L.call("mobgs_pack_records", pk, _stream())
-        lists = build_tile_lists(records, radii, depths, width, height, tight)
         bg = None
         if backgrounds is not None:
             bg = _f32c(backgrounds)
             if append_depth:
                 bg = torch.cat([bg, torch.zeros_like(bg[:, :1])], dim=-1).contiguous()
-        out_c = torch.empty(K, height, width, D, device=dev)
-        out_a = torch.empty(K, height, width, device=dev)
-        last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
-        a = L.BlendFwd(K, N, D, width, height, lists.lists, _p(records), _p(lists.tile_offsets),
-                       _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
-        L.call("mobgs_blend_fwd", a, _stream())
+
+        def blend(lists):
+            out_c = torch.empty(K, height, width, D, device=dev)
+            out_a = torch.empty(K, height, width, device=dev)
+            last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+            a = L.BlendFwd(K, N, D, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
+                           _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
+            L.call("mobgs_blend_fwd", a, _stream())
+            return out_c, out_a, last
+
+        lists, (out_c, out_a, last) = build_tile_lists(records, radii, depths, width, height, tight, consume=blend)
+        ctx.capacity = lists.capacity
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
         ctx.lists = lists.lists
         ctx.meta = (K, N, D0, D, width, height, per_cam, append_depth)
@@ -186,8 +232,8 @@ class _Rasterize(torch.autograd.Function):
         v_rec = torch.zeros(K, N, L.REC, device=dev)
         g_c = _f32c(g_c)
         g_a = _f32c(g_a) if g_a is not None else None
-        a = L.BlendBwd(K, N, D, width, height, ctx.lists, _p(records), _p(offsets), _p(sorted_ids), _p(bg),
-                       _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), -1, None)
+        a = L.BlendBwd(K, N, D, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
+                       _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), -1, None)
         L.call("mobgs_blend_bwd", a, _stream())
         v_means2d = v_rec[..., 0:2]
         v_conics = v_rec[..., 3:6]

@@ -193,3 +193,28 @@ def test_decode_epilogue_fwd_bwd(K, per_k):
     ((rgb0 * wr).sum() + (depth0 * wd).sum() + (mean0 * wm).sum()).backward()
     for a, b, n in zip(lc, lo, ("v_img", "v_alpha", "v_rays", "v_w1", "v_w2")):
         _close(a.grad, b.grad, n, max_outlier_frac=1e-4)
+
+
+def test_speculative_list_capacity_overflow_is_redone_exactly():
+    """Lists are sized from the previous launch of the same shape; when that guess is too small the
+    emit/sort/blend chain is redone with the exact size — results must be identical."""
+    from mobgs_b200 import ops, rendering as R
+    R.TIGHT_TILES = True
+    n, W, H = 3000, 160, 96
+    means, quats, scales, opac, colors, view, Kmat = _scene(n, W, H, 77, 3)
+    args = [t.cuda() for t in (means, quats, scales, opac, colors)]
+
+    def run():
+        img, alpha, _ = R.rasterization(*args, view.cuda()[None], Kmat.cuda()[None], W, H, packed=False)
+        return img.clone(), alpha.clone()
+
+    ops._CAP_CACHE.clear()
+    ref_img, ref_alpha = run()                 # synchronous sizing (no guess yet)
+    assert len(ops._CAP_CACHE) == 1
+    img2, alpha2 = run()                       # speculative, guess large enough
+    assert torch.equal(ref_img, img2) and torch.equal(ref_alpha, alpha2)
+    for k in list(ops._CAP_CACHE):
+        ops._CAP_CACHE[k] = 7                  # far too small -> overflow path
+    img3, alpha3 = run()
+    assert torch.equal(ref_img, img3) and torch.equal(ref_alpha, alpha3)
+    assert all(v > 7 for v in ops._CAP_CACHE.values())
