@@ -13,12 +13,18 @@
 // Gaussian).
 #include "common.cuh"
 #include "decode_math.cuh"
+#include "tma.cuh"
 
 namespace mobgs {
 
 constexpr int kBlendThreads = kTilePix;   // 256
 #ifndef MOBGS_FWD_MIN_CTAS
 #define MOBGS_FWD_MIN_CTAS 6
+#endif
+// 1: stage each batch of records with per-record TMA bulk copies (cp.async.bulk -> UBLKCP) that
+// complete on an mbarrier; 0: LDG.128 -> STS.128 through registers.
+#ifndef MOBGS_TMA_STAGE
+#define MOBGS_TMA_STAGE 1
 #endif
 #ifndef MOBGS_BWD_MIN_CTAS
 #define MOBGS_BWD_MIN_CTAS 4
@@ -110,10 +116,11 @@ __device__ __forceinline__ int butterfly_reduce(float (&g)[NV], int lane) {
 
 template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
-  __shared__ float4 srec[kBlendThreads][4];
+  __shared__ __align__(128) float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
   __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
   __shared__ __align__(16) float sdec[DEC ? 96 : 4];
+  __shared__ __align__(8) uint64_t sbar;
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
@@ -121,6 +128,11 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   const int lane = lane_id();
   const unsigned wbit = 1u << (tid >> 5);
   unsigned char* wlist = swl[tid >> 5];
+  uint32_t bar_phase = 0;
+  if (MOBGS_TMA_STAGE && tid == 0) {
+    mbar_init(&sbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // made visible by the first barrier below
+  }
   if (DEC && tid < 90) sdec[tid] = tid < 72 ? a.dec_w1[tid] : a.dec_w2[tid - 72];   // visible after the first barrier
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
@@ -139,6 +151,15 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   for (int b0 = beg; b0 < end; b0 += kBlendThreads) {
     if (__syncthreads_count(done) == kBlendThreads) break;
     const int idx = b0 + tid;
+    const int bn = min(kBlendThreads, end - b0);
+#if MOBGS_TMA_STAGE
+    constexpr uint32_t kRecBytes = D > 6 ? 64 : (D > 2 ? 48 : 32);
+    if (tid == 0) mbar_expect_tx(&sbar, (uint32_t)bn * kRecBytes);
+    if (idx < end) bulk_g2s(&srec[tid][0], recs + (size_t)a.sorted_ids[idx] * 4, kRecBytes, &sbar);
+    mbar_wait(&sbar, bar_phase);
+    bar_phase ^= 1;
+    if (idx < end) smask[tid] = strip_mask(srec[tid][0], srec[tid][1], (float)(ty * kTile));
+#else
     if (idx < end) {
       const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
       const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
@@ -147,8 +168,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
       if (D > 6) srec[tid][3] = __ldg(r + 3);
       smask[tid] = strip_mask(q0, q1, (float)(ty * kTile));
     }
+#endif
     __syncthreads();
-    const int bn = min(kBlendThreads, end - b0);
     const int cnt = build_strip_list(smask, wlist, wbit, lane, 0, bn);
     for (int i = 0; i < cnt && !done; ++i) {
       const int t = wlist[i];
@@ -211,7 +232,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
 
 template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
-  __shared__ float4 srec[kBlendThreads][4];
+  __shared__ __align__(128) float4 srec[kBlendThreads][4];
+  __shared__ __align__(8) uint64_t sbar;
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
   __shared__ unsigned smask[kBlendThreads];
@@ -225,6 +247,11 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   const int tid = threadIdx.x, lane = lane_id();
   const unsigned wbit = 1u << (tid >> 5);
   unsigned char* wlist = swl[tid >> 5];
+  uint32_t bar_phase = 0;
+  if (MOBGS_TMA_STAGE && tid == 0) {
+    mbar_init(&sbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible after the barrier that follows
+  }
   const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
@@ -338,6 +365,20 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     const int lo = max(beg, hi - kBlendThreads + 1);
     const int bn = hi - lo + 1;
     __syncthreads();   // previous batch fully flushed
+#if MOBGS_TMA_STAGE
+    constexpr uint32_t kRecBytes = D > 6 ? 64 : (D > 2 ? 48 : 32);
+    if (tid == 0) mbar_expect_tx(&sbar, (uint32_t)bn * kRecBytes);
+    if (tid < bn) {
+      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      sid[tid] = g;
+      bulk_g2s(&srec[tid][0], recs + (size_t)g * 4, kRecBytes, &sbar);
+    }
+#pragma unroll
+    for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
+    mbar_wait(&sbar, bar_phase);
+    bar_phase ^= 1;
+    if (tid < bn) smask[tid] = strip_mask(srec[tid][0], srec[tid][1], (float)(ty * kTile));
+#else
     if (tid < bn) {
       const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
       sid[tid] = g;
@@ -350,6 +391,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     }
 #pragma unroll
     for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
+#endif
     __syncthreads();
     // entries above this warp's furthest pixel contribute nothing: skip them warp-uniformly
     const int cnt = build_strip_list(smask, wlist, wbit, lane, max(0, hi - wmax), bn);
