@@ -218,3 +218,47 @@ def test_speculative_list_capacity_overflow_is_redone_exactly():
     img3, alpha3 = run()
     assert torch.equal(ref_img, img3) and torch.equal(ref_alpha, alpha3)
     assert all(v > 7 for v in ops._CAP_CACHE.values())
+
+
+@pytest.mark.parametrize("n,note", [(500, "rank sort (<= 768 per tile)"), (2500, "shared-memory radix (<= 4096)"),
+                                    (7000, "global-memory radix (> 4096)")])
+def test_dense_tiles_exercise_every_sort_path(n, note):
+    """All Gaussians overlap every tile of a small image, so each per-tile list has ~n entries:
+    covers the three segment-sort implementations (and multi-batch blending, and depth ties)."""
+    from mobgs_b200 import ops, rendering as R
+    R.TIGHT_TILES = True
+    W = H = 48
+    g = torch.Generator().manual_seed(n)
+    z = 2 + 6 * torch.rand(n, generator=g)
+    m7 = 7 * (n // 7)
+    z[0:m7:7] = z[1:m7:7]                                 # exact depth ties -> index order decides
+    means = torch.stack([(torch.rand(n, generator=g) - 0.5) * 0.5 * z, (torch.rand(n, generator=g) - 0.5) * 0.5 * z, z], -1)
+    quats = torch.randn(n, 4, generator=g)
+    scales = (0.15 + 0.3 * torch.rand(n, 3, generator=g)) * z[:, None] * 0.5     # footprints of tens of pixels
+    opac = 0.02 + 0.1 * torch.rand(n, generator=g)
+    colors = torch.rand(n, 3, generator=g)
+    view = torch.eye(4)
+    Kmat = torch.tensor([[40.0, 0, W / 2], [0, 40.0, H / 2], [0, 0, 1.0]])
+    cu = [t.cuda().requires_grad_(True) for t in (means, quats, scales, opac, colors)]
+    cp = [t.clone().requires_grad_(True) for t in (means, quats, scales, opac, colors)]
+    img, alpha, meta = R.rasterization(*cu, view.cuda()[None], Kmat.cuda()[None], W, H, packed=False)
+    img0, alpha0, _ = G.rasterization(*cp, view[None], Kmat[None], W, H, packed=False)
+    # the lists really are that long
+    radii, m2d, dep, con = meta["radii"], meta["means2d"], meta["depths"], meta["conics"]
+    rec = torch.zeros(1, n, 16, device="cuda")
+    rec[..., 0:2], rec[..., 2], rec[..., 3:6] = m2d.detach(), cu[3].detach(), con.detach()
+    lists = ops.build_tile_lists(rec, radii, dep.detach(), W, H, tight=True)
+    per_tile = (lists.tile_offsets[1:] - lists.tile_offsets[:-1]).float()
+    assert per_tile.max() > 0.6 * n, (note, per_tile.max())
+    off, ids, d = lists.tile_offsets.cpu().numpy(), lists.sorted_ids.cpu().numpy(), dep[0].detach().cpu().numpy()
+    for t in range(len(off) - 1):
+        seg = ids[off[t]:off[t + 1]]
+        keyed = list(zip(d[seg].tolist(), seg.tolist()))
+        assert keyed == sorted(keyed), (note, t)
+    _close(img, img0, "render_colors", scale_atol=False, max_outlier_frac=1e-3)
+    _close(alpha, alpha0, "render_alphas", scale_atol=False, max_outlier_frac=1e-3)
+    wi = torch.rand(img0.shape, generator=g)
+    (img * wi.cuda()).sum().backward()
+    (img0 * wi).sum().backward()
+    for a, b, name in zip(cu, cp, ("means", "quats", "scales", "opacities", "colors")):
+        _close(a.grad, b.grad, "v_" + name, max_outlier_frac=2e-3)
