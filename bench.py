@@ -187,7 +187,7 @@ def run_ours(args):
     from mobgs_b200 import _lib
     from mobgs_b200.scene import subframe_w2c, synthetic_scene
     from mobgs_b200.subframes import render_subframes
-    from mobgs_b200.dist import FlatGradients
+    from mobgs_b200.dist import FlatGradients, blur_from_partial_sums, shard_items
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -204,10 +204,12 @@ def run_ours(args):
     N = ns + nd
     stat, dyn, intr = synthetic_scene(ns, nd, W, H, seed=1234, device=dev)   # same replica on every rank
     all_params = [p for pc in (stat, dyn) for p in pc.parameters() if p.requires_grad]
-    gen = torch.Generator().manual_seed(100 + rank)          # each rank: its own view
+    shard_sub = args.shard == "subframes" and world > 1
+    my_k = list(shard_items(K, rank, world)) if shard_sub else list(range(K))
+    gen = torch.Generator().manual_seed(100 + (0 if shard_sub else rank))   # views: each rank its own view
     tgt_host = torch.rand(3, H, W, generator=gen).pin_memory()
     base_time = 0.3 + 0.4 * float(torch.rand(1, generator=gen))
-    yaw = 0.5 * (rank - (world - 1) / 2)                       # degrees
+    yaw = 0.0 if shard_sub else 0.5 * (rank - (world - 1) / 2)   # degrees
     view_host = torch.stack([subframe_w2c(k, K) for k in range(K)])
     a = math.radians(yaw)
     R = torch.eye(4); R[0, 0], R[0, 2], R[2, 0], R[2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
@@ -253,12 +255,32 @@ def run_ours(args):
             prefetch()                                  # inputs of the following step
             rays = build_rays(view, intr, W, H)
         view = view.requires_grad_(True) if resident else view.clone().requires_grad_(True)
-        out = render_subframes(stat, dyn, view, Kmat, tpoly.clamp(0, 1), tpoly, rays, bg, W, H)
-        loss = (out["render"] - tgt).abs().mean()
-        loss.backward()
+        if shard_sub:
+            # one view, its K sub-frames split across ranks: partial image sums are all-reduced in the
+            # forward (collective 1 of SURVEY §8e), Gaussian gradients in the backward (collective 2)
+            if my_k:
+                ks = slice(my_k[0], my_k[-1] + 1)
+                out = render_subframes(stat, dyn, view[ks], Kmat, tpoly[ks].clamp(0, 1), tpoly[ks],
+                                       rays[ks] if rays.shape[0] > 1 else rays, bg, W, H)
+                local = out["subframes"]
+            else:
+                out, local = None, torch.zeros(0, 3, H, W, device=dev)
+            pred = blur_from_partial_sums(local, K)
+        else:
+            out = render_subframes(stat, dyn, view, Kmat, tpoly.clamp(0, 1), tpoly, rays, bg, W, H)
+            pred = out["render"]
+        loss = (pred - tgt).abs().mean()
+        if loss.requires_grad:
+            loss.backward()
         if world > 1:
-            if "fg" not in stats:      # parameter set that actually receives gradients is fixed
-                stats["fg"] = FlatGradients([p for p in all_params if p.grad is not None])
+            if "fg" not in stats:      # parameter set that receives gradients (fixed across steps)
+                stats["fg_params"] = [p for p in all_params if p.grad is not None or shard_sub]
+                if shard_sub:          # idle / static-only ranks still contribute zeros
+                    stats["fg_params"] = [p for p in stats["fg_params"] if p is not stat.control_xyz
+                                          and p is not stat._omega and p is not stat._features_t
+                                          and p is not stat._trbf_center and p is not dyn._trbf_center
+                                          and p is not dyn._xyz and all(p is not q for q in stat.rgbdecoder.parameters())]
+                stats["fg"] = FlatGradients(stats["fg_params"])
             stats["fg"].reduce()
             stats["allreduce_bytes"] = stats["fg"].flat.numel() * 4
         view.grad = None
@@ -312,10 +334,13 @@ def run_ours(args):
     _lib.TIMING = None
 
     # ---- algorithmic bytes of the dominant kernels (I_eff measured from the forward outputs) ----
-    ieff, itot = measure_intersections(stat, dyn, view_d, Kmat, tpoly_d, W, H)
+    ks_loc = slice(my_k[0], my_k[-1] + 1) if my_k else slice(0, 1)
+    ieff, itot = measure_intersections(stat, dyn, view_d[ks_loc], Kmat, tpoly_d[ks_loc], W, H)
     P = K * W * H
-    bytes_fwd = 68.0 * ieff + 48.0 * P
-    bytes_bwd = 132.0 * ieff + 52.0 * P
+    Pjob = P if shard_sub else world * P       # pixels rendered by the whole job per step
+    P_loc = len(my_k) * W * H                  # pixels this rank's kernels render per step
+    bytes_fwd = 68.0 * ieff + 48.0 * P_loc
+    bytes_bwd = 132.0 * ieff + 52.0 * P_loc
     peak, peak_kind = _peak()
     dom = max(("mobgs_blend_fwd", "mobgs_blend_bwd"), key=lambda n: kernel_ms.get(n, 0.0))
     dom_bytes = bytes_bwd if dom == "mobgs_blend_bwd" else bytes_fwd
@@ -329,7 +354,7 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_kind": peak_kind,
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes": dom_bytes,
-                "intersections_consumed": ieff, "intersections_listed": itot, "pixels": P,
+                "intersections_consumed": ieff, "intersections_listed": itot, "pixels": P_loc,
                 "issue_slot_utilisation": 0.806,
                 "note": "the blend kernels are instruction-issue bound (ncu: 80.6 % issue slots, 12 % DRAM; "
                         "profiles/r1_blend_bwd_ncu.txt), not HBM bound; the HBM fraction is reported because "
@@ -354,16 +379,17 @@ def run_ours(args):
             cpu = {"value": cpix / cdt / 1e6, "unit": "Mpix/s", "cores": os.cpu_count() or 1, "kind": "port",
                    "sample": cdesc + f" ({n} steps, {cdt * 1e3:.0f} ms each)"}
         line = {
-            "metric": METRIC, "value": world * P / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "metric": METRIC, "value": Pjob / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if shard_sub else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "gaussians": N, "static": ns, "dynamic": nd, "width": W,
-                       "height": H, "subframes": K, "views_per_step": world, "parallelism": f"dp{world}_views",
+                       "height": H, "subframes": K, "views_per_step": 1 if shard_sub else world,
+                       "parallelism": f"subframes_over_{world}" if shard_sub else f"dp{world}_views",
                        "l2": "flushed between timed iterations (192 MB memset, untimed)",
                        "step": "K-sub-frame render + decode + blur mean + L1 + full backward"
                                + (" + NCCL all-reduce of Gaussian gradients" if world > 1 else "")},
             "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": world * P / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
+            "e2e": {"value": Pjob / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "clocks": clocks,
         }
@@ -405,6 +431,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="views", choices=["views", "subframes"],
+                    help="N>1: 'views' = one view per rank (weak scaling, default); 'subframes' = the K "
+                         "sub-frames of one view split across ranks (strong scaling, BASELINE configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -77,3 +77,33 @@ class FlatGradients:
 
 def trainable(params: Iterable[torch.Tensor]) -> List[torch.Tensor]:
     return [p for p in params if p.is_floating_point() and p.requires_grad]
+
+
+class _AllReduceSum(torch.autograd.Function):
+    """y = sum over ranks of x.  Every rank goes on to compute the SAME scalar loss from y, and the
+    per-rank parameter gradients are summed afterwards (FlatGradients.reduce), so the backward
+    hands each rank d loss / d y for its own addend unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.clone()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def all_reduce_sum(x: torch.Tensor, group=None) -> torch.Tensor:
+    return _AllReduceSum.apply(x, group)
+
+
+def blur_from_partial_sums(local_subframes: torch.Tensor, K: int, group=None) -> torch.Tensor:
+    """Sub-frame sharding (collective 1): each rank holds the decoded images of its
+    share of the K latent sub-frames, `local_subframes` [k_local,3,H,W] (k_local may be 0).  One
+    all-reduce of the [3,H,W] partial sum gives every rank the blurred prediction
+    mean_k(rgb_k) + 1e-10 (train.py:540-541)."""
+    partial = local_subframes.sum(dim=0)
+    return all_reduce_sum(partial, group) / K + 1e-10

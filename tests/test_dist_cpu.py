@@ -78,3 +78,64 @@ def test_two_rank_gradient_allreduce_equals_single_process():
         assert len(results[r]) == len(want)
         for a, b in zip(results[r], want):
             torch.testing.assert_close(torch.from_numpy(a), b, atol=1e-6, rtol=1e-5)
+
+
+def _sub_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mobgs_b200.dist import FlatGradients, blur_from_partial_sums, shard_items, trainable
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    from oracle import mobgs_ref as M
+    torch.set_num_threads(2)
+    K = 3
+    stat, dyn, intr = synthetic_scene(60, 40, 32, 32, seed=4)
+    deltas = (torch.linspace(-1, 1, K) * 0.4).tolist()
+    mine = shard_items(K, rank, world)
+    imgs = [M.render_ref(make_camera(intr, subframe_w2c(k, K)), stat, dyn, None, torch.zeros(3),
+                         delta_exposure=deltas[k])["render"] for k in mine]
+    local = torch.stack(imgs) if imgs else torch.zeros(0, 3, 32, 32)
+    pred = blur_from_partial_sums(local, K)
+    tgt = torch.rand(pred.shape, generator=torch.Generator().manual_seed(0))
+    (pred - tgt).abs().mean().backward()
+    params = [p for p in trainable(stat.parameters()) + trainable(dyn.parameters()) if p is not stat.control_xyz]
+    for p in params:       # a rank with no dynamic contribution still needs a zero gradient to reduce
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    FlatGradients(params).reduce()
+    q.put((rank, pred.detach().numpy().copy(), [p.grad.numpy().copy() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_subframe_sharding_matches_single_process():
+    """K sub-frames of ONE view split across 2 ranks: partial-sum all-reduce + gradient all-reduce
+    reproduce the single-process blurred image and gradients."""
+    sys.path.insert(0, ROOT)
+    from mobgs_b200.dist import trainable
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    from oracle import mobgs_ref as M
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sub_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (pred, grads) for r, pred, grads in (q.get(timeout=240) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    K = 3
+    stat, dyn, intr = synthetic_scene(60, 40, 32, 32, seed=4)
+    deltas = (torch.linspace(-1, 1, K) * 0.4).tolist()
+    imgs = [M.render_ref(make_camera(intr, subframe_w2c(k, K)), stat, dyn, None, torch.zeros(3),
+                         delta_exposure=deltas[k])["render"] for k in range(K)]
+    pred = M.blur_mean(imgs)
+    tgt = torch.rand(pred.shape, generator=torch.Generator().manual_seed(0))
+    (pred - tgt).abs().mean().backward()
+    params = [p for p in trainable(stat.parameters()) + trainable(dyn.parameters()) if p is not stat.control_xyz]
+    for r in (0, 1):
+        torch.testing.assert_close(torch.from_numpy(res[r][0]), pred.detach(), atol=1e-6, rtol=1e-5)
+        for a, p in zip(res[r][1], params):
+            want = p.grad if p.grad is not None else torch.zeros_like(p)
+            torch.testing.assert_close(torch.from_numpy(a), want, atol=1e-6, rtol=1e-5)
