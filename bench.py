@@ -32,6 +32,7 @@ WORKLOADS = {
     "c3_500k_960x540_K7": (350_000, 150_000, 960, 540, 7),    # configs[2]
     "c4_1M_1080p_K7": (700_000, 300_000, 1920, 1080, 7),      # the metric's "1M Gaussians K=7"
     "c4_1M_1080p_K9": (700_000, 300_000, 1920, 1080, 9),      # configs[3]
+    "sb_150k_512x288_K9": (100_000, 50_000, 512, 288, 9),     # the reference's real training shape (Stereo-Blur loader size, num_warp=9)
 }
 DEFAULT_WORKLOAD = "c4_1M_1080p_K7"
 METRIC = "rendered_Mpix_per_s_train_step"   # K*H*W / (fwd+loss+bwd time); ms_per_step = train-step ms

@@ -190,3 +190,36 @@ def test_render_subframes_batched_equals_looped_oracle():
     _check_param_grads(sc, dc, so, do)
     _close(view_c.grad[:, :3], torch.stack([w.grad for w in w2c_o])[:, :3], "v_viewmats", rtol=5e-3)
     _close(out_c["viewspace_points"].grad, vsp_o.grad, "viewspace grad", max_outlier_frac=1e-3)
+
+
+@pytest.mark.parametrize("ns,nd,W,H,K", [(0, 300, 50, 34, 2), (300, 0, 50, 34, 2), (123, 77, 97, 61, 9),
+                                         (40, 40, 16, 16, 1), (5, 3, 200, 40, 4)])
+def test_render_subframes_edge_shapes(ns, nd, W, H, K):
+    """Empty static / dynamic sets, image sizes that are not tile multiples, K = 1..9."""
+    from mobgs_b200.subframes import render_subframes
+    so, do, intr = synthetic_scene(ns, nd, W, H, seed=ns + nd + K)
+    sc, dc, _ = synthetic_scene(ns, nd, W, H, seed=ns + nd + K, device="cuda")
+    bg = torch.tensor([0.3, 0.1, 0.6])
+    deltas = (torch.linspace(-1, 1, K) * 0.4).tolist() if K > 1 else [0.25]
+    cams = [make_camera(intr, subframe_w2c(k, K), time=0.6) for k in range(K)]
+    imgs, deps = [], []
+    for k in range(K):
+        out = M.render_ref(cams[k], so, do, None, bg, delta_exposure=deltas[k])
+        imgs.append(out["render"]); deps.append(out["depth"])
+    pred_o = M.blur_mean(imgs)
+    view = torch.stack([subframe_w2c(k, K) for k in range(K)]).cuda()
+    t_poly = torch.tensor([0.6 + d / 23 for d in deltas]).cuda()
+    rays = torch.cat([c.cam_ray for c in cams]).cuda()
+    out_c = render_subframes(sc, dc, view, cams[0].K.cuda(), t_poly.clamp(0, 1), t_poly, rays, bg.cuda(), W, H)
+    assert out_c["render"].shape == (3, H, W) and out_c["radii"].shape == (K, ns + nd)
+    _close(out_c["render"], pred_o, "blurred render", scale_atol=False, max_outlier_frac=2e-3)
+    _close(out_c["depth"], torch.cat(deps), "depth", atol=2e-4, scale_atol=False, max_outlier_frac=2e-3)
+    tgt = torch.rand(pred_o.shape, generator=torch.Generator().manual_seed(0))
+    (out_c["render"] - tgt.cuda()).abs().mean().backward()
+    (pred_o - tgt).abs().mean().backward()
+    if ns:
+        for n in PARAMS:
+            _close(getattr(sc, n).grad, getattr(so, n).grad, "stat" + n, max_outlier_frac=3e-3)
+    if nd:
+        for n in DPARAMS:
+            _close(getattr(dc, n).grad, getattr(do, n).grad, "dyn" + n, max_outlier_frac=3e-3)
