@@ -244,7 +244,9 @@ typedef struct {
   int32_t* last_idx;
   /* Optional fused epilogue (dec_rays != NULL; D must be 10): the per-pixel work of
    * mobgs_decode_fwd — expected depth + Sandwich decoder — done while the pixel is still in
-   * registers.  out_rgb [K,3,H,W], out_depth [K,H,W] (NULL = skip). */
+   * registers.  out_rgb [K,3,H,W], out_depth [K,H,W] (NULL = skip).
+   * dec_rays_per_k: 0 = one shared [1,6,H,W]; 1 = one per list [K,6,H,W]; 2 = one per record set,
+   * indexed by lists.rec_k[k] (lists that share a projection share its camera rays). */
   const float* dec_rays; int32_t dec_rays_per_k;
   const float* dec_w1; const float* dec_w2;
   float* out_rgb;
@@ -279,6 +281,7 @@ typedef struct {
   const float* dec_w1; const float* dec_w2;
   const float* out_colors;
   const float* g_rgb; const float* g_depth; const float* g_alpha; const float* g_mean;
+  int32_t mean_K;             /* the mean is over the first mean_K lists (0 = all K) */
   float* v_rays;
   float* v_w_partial;
 } MobgsBlendBwd;

@@ -162,7 +162,7 @@ class BlendBwd(C.Structure):
                 ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
                 ("dec_w2", C.c_void_p), ("out_colors", C.c_void_p), ("g_rgb", C.c_void_p),
                 ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p), ("g_mean", C.c_void_p),
-                ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p)]
+                ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):

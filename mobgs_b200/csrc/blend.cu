@@ -219,7 +219,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
       float v[10], rays[6], x[12], hpre[6], out[3];
 #pragma unroll
       for (int c = 0; c < 10; ++c) v[c] = pix[c % D];
-      const float* rp = a.dec_rays + (a.dec_rays_per_k ? (size_t)k * 6 * P : 0) + pp;
+      const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+      const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
 #pragma unroll
       for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
       sandwich_fwd(w, v, rays, x, hpre, out);
@@ -295,13 +296,15 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       const float2* vp2 = reinterpret_cast<const float2*>(a.out_colors + p * 10);
 #pragma unroll
       for (int i = 0; i < 5; ++i) { const float2 t2 = __ldg(vp2 + i); v[2 * i] = t2.x; v[2 * i + 1] = t2.y; }
-      const float* rp = a.dec_rays + (a.dec_rays_per_k ? (size_t)k * 6 * P : 0) + pp;
+      const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+      const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
 #pragma unroll
       for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
-      const float invK = 1.0f / (float)a.K;
+      const int meanK = a.mean_K > 0 ? a.mean_K : a.K;
+      const float invK = 1.0f / (float)meanK;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        g_out[c] = a.g_mean ? __ldg(a.g_mean + c * P + pp) * invK : 0.f;
+        g_out[c] = (a.g_mean && k < meanK) ? __ldg(a.g_mean + c * P + pp) * invK : 0.f;
         if (a.g_rgb) g_out[c] += __ldg(a.g_rgb + ((size_t)k * 3 + c) * P + pp);
       }
       sandwich_fwd(w, v, rays, x, hpre, out);
@@ -313,12 +316,12 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       v_c[9 % D] = gd / den;
       v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * v[9] / (den * den) : 0.f);
       if (a.v_rays) {
-        if (a.dec_rays_per_k) {
+        if (a.dec_rays_per_k == 1) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) a.v_rays[((size_t)k * 6 + i) * P + pp] = g_rays[i];
-        } else {
+        } else {   // rays shared between lists: accumulate
 #pragma unroll
-          for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + i * P + pp, g_rays[i]);
+          for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + ((size_t)rk * 6 + i) * P + pp, g_rays[i]);
         }
       }
     }

@@ -209,14 +209,22 @@ class _BlendDecode(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
-                vsp_list, want_mean):
+                vsp_list, want_mean, mean_K=0):
         records = _f32c(records)
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
         dev = records.device
         K = Kr if specs is None else len(specs)
-        assert rays.shape[0] in (1, K) and rays.shape[1] == 6
-        per_k = int(rays.shape[0] == K and K > 1)
+        assert rays.shape[1] == 6
+        if rays.shape[0] == 1:
+            per_k = 0
+        elif rays.shape[0] == K:
+            per_k = 1
+        elif rays.shape[0] == Kr:
+            per_k = 2          # one camera per record set, shared by the lists over it
+        else:
+            raise ValueError(f"rays has {rays.shape[0]} cameras for {K} lists over {Kr} record sets")
+        mK = mean_K if mean_K > 0 else K
         bg = _f32c(backgrounds) if backgrounds is not None else None
 
         def blend(lists):
@@ -235,20 +243,20 @@ class _BlendDecode(torch.autograd.Function):
                                                                    specs, consume=blend)
         if want_mean:
             mean = torch.empty(3, height, width, device=dev)
-            L.subframe_mean(_p(rgb), _p(mean), K, 3 * height * width, _stream())
+            L.subframe_mean(_p(rgb), _p(mean), mK, 3 * height * width, _stream())
         else:
             mean = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(mean)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
-        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k)
+        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK)
         ctx.n_isect = lists.n_isect
         return rgb, depth, alpha, mean
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_alpha, g_mean):
         records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2 = ctx.saved_tensors
-        K, Kr, N, width, height, vsp_list, has_vsp, per_k = ctx.meta
+        K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK = ctx.meta
         dev = records.device
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
         g_depth = _f32c(g_depth) if g_depth is not None else None
@@ -258,22 +266,24 @@ class _BlendDecode(torch.autograd.Function):
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
         v_rays = None
         if ctx.needs_input_grad[5]:
-            v_rays = torch.empty_like(rays) if per_k else torch.zeros_like(rays)
+            v_rays = torch.empty_like(rays) if per_k == 1 else torch.zeros_like(rays)
         v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
         a = L.BlendBwd(K, N, 10, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
                        _p(rays), per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth), _p(g_alpha), _p(g_mean),
-                       _p(v_rays), _p(v_wp))
+                       mK, _p(v_rays), _p(v_wp))
         L.call("mobgs_blend_bwd", a, _stream())
         v_w = v_wp.sum(0)
         return (v_rec, None, None, None, v_vsp, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6),
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, height, specs=None, tight=True,
-                 vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False):
-    """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty)."""
+                 vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False, mean_K: int = 0):
+    """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty).
+    rays: [1,6,H,W] shared, [K,6,H,W] per list, or [record sets,6,H,W] per projection.
+    mean_K: the blur mean is taken over the first mean_K lists (0 = all)."""
     if specs is not None:
         specs = tuple(tuple(int(v) for v in s) for s in specs)
     return _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
-                              specs, bool(tight), int(vsp_k), bool(want_mean))
+                              specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K))

@@ -223,3 +223,41 @@ def test_render_subframes_edge_shapes(ns, nd, W, H, K):
     if nd:
         for n in DPARAMS:
             _close(getattr(dc, n).grad, getattr(do, n).grad, "dyn" + n, max_outlier_frac=3e-3)
+
+
+def test_render_blurry_view_equals_reference_loop():
+    """render_blurry_view == the reference's per-view loop (train.py:441, :497-541): centre render with
+    get_static / get_dynamic + K-1 warped renders + blur mean; outputs and all gradients."""
+    from mobgs_b200.subframes import render_blurry_view
+    K, W, H = 5, 96, 64
+    so, do, intr = synthetic_scene(350, 250, W, H, seed=31)
+    sc, dc, _ = synthetic_scene(350, 250, W, H, seed=31, device="cuda")
+    bg = torch.tensor([0.15, 0.3, 0.45])
+    expo = torch.linspace(-1, 1, K) * 0.4
+    half = K // 2
+    base_o = make_camera(intr, subframe_w2c(half, K), time=0.55)
+    warped_o = [make_camera(intr, subframe_w2c(k, K) @ subframe_w2c(1, 3), time=0.55) for k in range(K)]
+    base_c = make_camera(intr, subframe_w2c(half, K, device="cuda"), time=0.55)
+    warped_c = [make_camera(intr, (subframe_w2c(k, K) @ subframe_w2c(1, 3)).cuda(), time=0.55) for k in range(K)]
+
+    pkg = M.render_ref(base_o, so, do, None, bg, get_static=True, get_dynamic=True)
+    imgs = []
+    for k in range(K):
+        imgs.append(pkg["render"] if k == half else
+                    M.render_ref(warped_o[k], so, do, None, bg, get_static=True, get_dynamic=True,
+                                 delta_exposure=expo[k])["render"])
+    pred_o = M.blur_mean(imgs)
+
+    out = render_blurry_view(base_c, warped_c, expo.cuda(), sc, dc, None, bg.cuda())
+    _close(out["render"], pred_o, "blurred", scale_atol=False)
+    for key in ("depth", "s_render", "d_render", "d_depth", "d_alpha", "s_alpha", "s_depth"):
+        assert out[key].shape == pkg[key].shape, key
+        _close(out[key], pkg[key], key, atol=2e-4, scale_atol=False, max_outlier_frac=1e-3)
+    _close(out["render_center"], pkg["render"], "centre render", scale_atol=False)
+    g = torch.Generator().manual_seed(5)
+    tgt = torch.rand(pred_o.shape, generator=g)
+    ws = {k: torch.rand(pkg[k].shape, generator=g) * 0.2 for k in ("depth", "d_alpha", "s_alpha", "s_render", "d_depth")}
+    ((out["render"] - tgt.cuda()).abs().mean() + sum((out[k] * w.cuda()).mean() for k, w in ws.items())).backward()
+    ((pred_o - tgt).abs().mean() + sum((pkg[k] * w).mean() for k, w in ws.items())).backward()
+    _check_param_grads(sc, dc, so, do)
+    _close(out["viewspace_points"].grad, pkg["viewspace_points"].grad, "viewspace grad", max_outlier_frac=1e-3)
