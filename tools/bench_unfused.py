@@ -89,6 +89,17 @@ def main():
             imgs.append(out["render"])
         (M.blur_mean(imgs) - tgt).abs().mean().backward()
 
+    from mobgs_b200.subframes import render_blurry_view
+    expo = torch.tensor(deltas, device=dev)
+
+    def blurry_view():
+        """same outputs as the train.py pattern (blurred image + the centre's s/d renders), one launch chain"""
+        for p in params:
+            p.grad = None
+        out = render_blurry_view(cams[K // 2], cams, expo, stat, dyn, None, bg)
+        (out["render"] - tgt).abs().mean().backward()
+
+    ms_bview = timed(blurry_view, steps)
     ms_dropin = timed(dropin_loop, steps)
     ms_full = timed(reference_pattern(True), steps)
     ms_min = timed(reference_pattern(False), steps)
@@ -98,7 +109,9 @@ def main():
         "reference_call_pattern_train_py_ms": ms_full,       # 5 rasterisations per sub-frame (train.py:441,:512)
         "reference_call_pattern_minimal_ms": ms_min,         # 1 rasterisation per sub-frame
         "dropin_render_loop_ms": ms_dropin,                  # mobgs_b200.gaussian_renderer.render x K, train.py unchanged
+        "fused_blurry_view_ms": ms_bview,                    # render_blurry_view: K sub-frames + centre s/d lists
         "fused_k_batched_ms": ms_fused,
+        "speedup_blurry_view_vs_train_py_pattern": ms_full / ms_bview,
         "speedup_vs_train_py_pattern": ms_full / ms_fused, "speedup_vs_minimal_pattern": ms_min / ms_fused,
         "note": "same sm_100a kernels underneath both arms; the reference arm keeps the reference's per-call "
                 "structure (sequential K, 5 pipelines per render, torch-op attribute synthesis)"}))
