@@ -40,7 +40,12 @@ constexpr float kNegLog2e = -1.4426950408889634f;
 // Which of the tile's eight 16x2-pixel strips (= warps) can a Gaussian reach with alpha >= 1/255?
 // The ellipse sigma <= tau = log(255 opac) has vertical half-extent sqrt(2 tau * ca / det(conic)).
 // A strip outside it contributes nothing, so its warp skips the Gaussian without evaluating it.
+// Ablation switches (tools/ablation.sh): rebuild with -DMOBGS_ABL_NO_STRIP_MASK / -DMOBGS_ABL_NAIVE_REDUCE
+// to measure what the strip culling and the transposing butterfly buy.  Never set in the product build.
 __device__ __forceinline__ unsigned strip_mask(const float4& r0, const float4& r1, float tile_y0) {
+#ifdef MOBGS_ABL_NO_STRIP_MASK
+  return 0xffu;
+#endif
   const float tau = __logf(255.f * r0.z) + 0.01f;
   if (!(tau >= 0.f)) return 0u;
   const float det = r0.w * r1.y - r1.x * r1.x;
@@ -438,9 +443,19 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
           g[5] = 0.5f * v_sigma * dy * dy;
         }
       }
+#ifdef MOBGS_ABL_NAIVE_REDUCE
+      // gsplat-style: one full 5-step shuffle reduction per value, lane 0 adds them one by one
+#pragma unroll
+      for (int c = 0; c < 6 + D; ++c) g[c] = warp_sum(g[c]);
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 6 + D; ++c) atomicAdd(&sacc[t][c], g[c]);
+      }
+#else
       const int vidx = butterfly_reduce<NV>(g, lane);
       constexpr int kOwnerMask = NV == 16 ? 1 : 3;   // lanes whose low bits are 0 own a value
       if ((lane & kOwnerMask) == 0 && g[0] != 0.f) atomicAdd(&sacc[t][vidx], g[0]);
+#endif
     }
     __syncthreads();
     if (tid < bn) {

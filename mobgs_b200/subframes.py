@@ -13,13 +13,19 @@ from typing import Dict, Optional
 
 import torch
 
+import os
+
 from . import fused
 from .gaussian_renderer import _bg10, _dynamic_params, _static_params
+
+# ablation only (tools/ablation.sh): MOBGS_ABL_AABB_TILES=1 lists every tile of gsplat's 3-sigma
+# square instead of pruning the provably empty ones
+_DEFAULT_TIGHT = os.environ.get("MOBGS_ABL_AABB_TILES", "0") != "1"
 
 
 def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, t_spline: torch.Tensor,
                      t_poly: torch.Tensor, rays: torch.Tensor, bg_color: torch.Tensor, width: int,
-                     height: int, center_k: Optional[int] = None, tight: bool = True,
+                     height: int, center_k: Optional[int] = None, tight: Optional[bool] = None,
                      offset: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """viewmats [K,4,4] (may require grad: they come from the BLCE pose network), Ks [K,3,3] or
     [3,3], t_spline / t_poly [K] device tensors (see gaussian_renderer._times), rays [K,6,H,W]
@@ -30,6 +36,7 @@ def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, 
     .grad receives d loss / d means2d of sub-frame `center_k`, default K//2)."""
     K = viewmats.shape[0]
     dev = viewmats.device
+    tight = _DEFAULT_TIGHT if tight is None else tight
     if Ks.dim() == 2:
         Ks = Ks[None].expand(K, -1, -1)
     ck = K // 2 if center_k is None else center_k
