@@ -286,61 +286,96 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     }
   }
   if (DEC) {
-    // fused prologue: VJP of (expected depth, Sandwich decoder, sub-frame mean) for this pixel
+    // fused prologue: VJP of (expected depth, Sandwich decoder, sub-frame mean) for this pixel.
+    // The 90 decoder weight-gradient terms are products of per-pixel factors (x[12]; ghpre[6],
+    // gpre[3], relu(h)[6]); every pixel parks its factors in shared memory as soon as they exist —
+    // the record / accumulator buffers are idle during the prologue — and 180 threads then sum one
+    // product each over half of the tile's pixels.  Live ranges are kept short on purpose: holding
+    // the factors in registers spilled ~460 B per thread (4.9 GB of local-memory DRAM writes).
+    constexpr int kPad = kBlendThreads + 1;              // row stride: distinct rows hit distinct banks
+    float* sx = reinterpret_cast<float*>(&srec[0][0]);   // [12][kPad]
+    float* sg = &sacc[0][0];                             // [15][kPad]: ghpre 0..5 | gpre 6..8 | relu(h) 9..14
     const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
-    DecW w; w.w1 = sdec; w.w2 = sdec + (DEC ? 72 : 0);
-    float x[12], hpre[6], gpre[3], ghpre[6];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) x[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) { hpre[j] = 0.f; ghpre[j] = 0.f; }
-    gpre[0] = gpre[1] = gpre[2] = 0.f;
+    const float* w1 = sdec;
+    const float* w2 = sdec + (DEC ? 72 : 0);
     if (inside) {
       const size_t p = (size_t)k * P + pp;
-      float v[10], rays[6], out[3], g_out[3], gv[9], g_rays[6];
-      const float2* vp2 = reinterpret_cast<const float2*>(a.out_colors + p * 10);
-#pragma unroll
-      for (int i = 0; i < 5; ++i) { const float2 t2 = __ldg(vp2 + i); v[2 * i] = t2.x; v[2 * i + 1] = t2.y; }
       const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
-      const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
+      const float2* vp2 = reinterpret_cast<const float2*>(a.out_colors + p * 10);
+      float albedo[3], depth_acc, hpre[6];
+      {
+        float x[12];
+        const float2 t0 = __ldg(vp2), t1 = __ldg(vp2 + 1), t2 = __ldg(vp2 + 2), t3 = __ldg(vp2 + 3), t4 = __ldg(vp2 + 4);
+        albedo[0] = t0.x; albedo[1] = t0.y; albedo[2] = t1.x;
+        x[0] = t1.y; x[1] = t2.x; x[2] = t2.y; x[3] = t3.x; x[4] = t3.y; x[5] = t4.x;
+        depth_acc = t4.y;
+        const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+        for (int i = 0; i < 6; ++i) x[6 + i] = __ldg(rp + i * P);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sx[i * kPad + tid] = x[i];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          float h = 0.f;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) h += w1[12 * j + i] * x[i];
+          hpre[j] = h;
+          sg[(9 + j) * kPad + tid] = fmaxf(h, 0.f);
+        }
+      }
       const int meanK = a.mean_K > 0 ? a.mean_K : a.K;
       const float invK = 1.0f / (float)meanK;
+      float gpre[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        g_out[c] = (a.g_mean && k < meanK) ? __ldg(a.g_mean + c * P + pp) * invK : 0.f;
-        if (a.g_rgb) g_out[c] += __ldg(a.g_rgb + ((size_t)k * 3 + c) * P + pp);
-      }
-      sandwich_fwd(w, v, rays, x, hpre, out);
-      sandwich_bwd(w, hpre, out, g_out, gv, g_rays, gpre, ghpre);
+        float sc = albedo[c];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) v_c[c % D] = gv[c];
+        for (int j = 0; j < 6; ++j) sc += w2[6 * c + j] * fmaxf(hpre[j], 0.f);
+        const float o = 1.0f / (1.0f + expf(-sc));
+        float go = (a.g_mean && k < meanK) ? __ldg(a.g_mean + c * P + pp) * invK : 0.f;
+        if (a.g_rgb) go += __ldg(a.g_rgb + ((size_t)k * 3 + c) * P + pp);
+        gpre[c] = go * o * (1.f - o);
+        v_c[c % D] = gpre[c];
+        sg[(6 + c) * kPad + tid] = gpre[c];
+      }
+      float ghpre[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float gh = w2[j] * gpre[0] + w2[6 + j] * gpre[1] + w2[12 + j] * gpre[2];
+        ghpre[j] = hpre[j] > 0.f ? gh : 0.f;
+        sg[j * kPad + tid] = ghpre[j];
+      }
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        float gx = 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) gx += w1[12 * j + i] * ghpre[j];
+        if (i < 6) {
+          v_c[(3 + i) % D] = gx;
+        } else if (a.v_rays) {
+          if (a.dec_rays_per_k == 1) a.v_rays[((size_t)k * 6 + (i - 6)) * P + pp] = gx;
+          else atomicAdd(a.v_rays + ((size_t)rk * 6 + (i - 6)) * P + pp, gx);   // rays shared between lists
+        }
+      }
       const float al = 1.f - T_final, den = fmaxf(al, kEdFloor);
       const float gd = a.g_depth ? __ldg(a.g_depth + p) : 0.f;
       v_c[9 % D] = gd / den;
-      v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * v[9] / (den * den) : 0.f);
-      if (a.v_rays) {
-        if (a.dec_rays_per_k == 1) {
+      v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * depth_acc / (den * den) : 0.f);
+    } else {
 #pragma unroll
-          for (int i = 0; i < 6; ++i) a.v_rays[((size_t)k * 6 + i) * P + pp] = g_rays[i];
-        } else {   // rays shared between lists: accumulate
+      for (int i = 0; i < 12; ++i) sx[i * kPad + tid] = 0.f;
 #pragma unroll
-          for (int i = 0; i < 6; ++i) atomicAdd(a.v_rays + ((size_t)rk * 6 + i) * P + pp, g_rays[i]);
-        }
-      }
+      for (int i = 0; i < 15; ++i) sg[i * kPad + tid] = 0.f;
     }
-    // 90 weight-gradient terms of this warp's 32 pixels: six 16-value butterflies -> CTA accumulator
-#pragma unroll
-    for (int grp = 0; grp < 6; ++grp) {
-      float t16[16];
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int i = grp * 16 + q;       // 0..71: W1[j][i'] = ghpre[j] * x[i'];  72..89: W2[c][j] = gpre[c] * relu(hpre[j])
-        t16[q] = i < 72 ? ghpre[i / 12] * x[i % 12] : (i < 90 ? gpre[(i - 72) / 6] * fmaxf(hpre[(i - 72) % 6], 0.f) : 0.f);
-      }
-      const int vi = butterfly_reduce<16>(t16, lane);
-      if ((lane & 1) == 0 && t16[0] != 0.f) atomicAdd(&swg[grp * 16 + vi], t16[0]);
+    __syncthreads();
+    if (tid < 180) {
+      const int o = tid % 90, p0 = (tid / 90) * (kBlendThreads / 2);
+      const float* fa = o < 72 ? sg + (o / 12) * kPad : sg + (6 + (o - 72) / 6) * kPad;
+      const float* fb = o < 72 ? sx + (o % 12) * kPad : sg + (9 + (o - 72) % 6) * kPad;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int p = p0; p < p0 + kBlendThreads / 2; ++p) acc += fa[p] * fb[p];
+      if (acc != 0.f) atomicAdd(&swg[o], acc);
     }
   }
   if (inside) {
