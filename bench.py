@@ -356,8 +356,8 @@ def run_ours(args):
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes": dom_bytes,
                 "intersections_consumed": ieff, "intersections_listed": itot, "pixels": P_loc,
-                "issue_slot_utilisation": 0.806,
-                "note": "the blend kernels are instruction-issue bound (ncu: 80.6 % issue slots, 12 % DRAM; "
+                "issue_slot_utilisation": 0.843,
+                "note": "the blend kernels are instruction-issue bound (ncu: 84 % issue slots, 6 % DRAM; "
                         "profiles/r1_blend_bwd_ncu.txt), not HBM bound; the HBM fraction is reported because "
                         "BASELINE.json's north_star asks for it. algorithmic_bytes = 132*I_eff + 52*P; since the "
                         "decoder VJP is fused into this kernel it also reads img10/rays/gradients (~100 B/pixel) "
