@@ -373,6 +373,28 @@ typedef struct {
 } MobgsHexMlpFwd;
 int mobgs_hexplane_mlp_fwd(const MobgsHexMlpFwd* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Flow records for get_flow() (gaussian_renderer/__init__.py:435-471), K exposure offsets at once.
+ * records [K+1,N,16]: set 0 = geometry at the mid time, sets 1..K = geometry at the K exposure
+ * times (same camera).  For every k two record sets are written to flow_records [2K,N,16]:
+ *   set 2k   : geometry of exposure k, colours (c0,c1) = means2d_mid - means2d_exp_k   (exp2mid flow)
+ *   set 2k+1 : geometry of mid,        colours (c0,c1) = means2d_exp_k - means2d_mid   (mid2exp flow)
+ * (the reference builds them with two fully_fused_projection calls + tensor arithmetic per k).
+ * The VJP accumulates v_flow_records back into v_records [K+1,N,16] (written, not accumulated). */
+typedef struct {
+  int32_t K, N;
+  const float* records;
+  float* flow_records;
+} MobgsFlowRecFwd;
+int mobgs_flow_records_fwd(const MobgsFlowRecFwd* a, void* stream);
+
+typedef struct {
+  int32_t K, N;
+  const float* v_flow_records;   /* [2K,N,16] */
+  float* v_records;              /* [K+1,N,16] */
+} MobgsFlowRecBwd;
+int mobgs_flow_records_bwd(const MobgsFlowRecBwd* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

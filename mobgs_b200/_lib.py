@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -190,6 +190,14 @@ class HexMlpFwd(C.Structure):
                 ("out_scales", C.c_void_p), ("out_rots", C.c_void_p)]
 
 
+class FlowRecFwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("records", C.c_void_p), ("flow_records", C.c_void_p)]
+
+
+class FlowRecBwd(C.Structure):
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("v_flow_records", C.c_void_p), ("v_records", C.c_void_p)]
+
+
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
 ENTRY_POINTS = {
@@ -207,6 +215,8 @@ ENTRY_POINTS = {
     "mobgs_decode_fwd": DecodeFwd,
     "mobgs_decode_bwd": DecodeBwd,
     "mobgs_hexplane_mlp_fwd": HexMlpFwd,
+    "mobgs_flow_records_fwd": FlowRecFwd,
+    "mobgs_flow_records_bwd": FlowRecBwd,
 }
 
 _lib = None

@@ -287,3 +287,28 @@ def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, heigh
         specs = tuple(tuple(int(v) for v in s) for s in specs)
     return _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
                               specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K))
+
+
+class _FlowRecords(torch.autograd.Function):
+    """records [K+1,N,16] (set 0 = mid time, 1..K = exposure times) -> flow records [2K,N,16]."""
+
+    @staticmethod
+    def forward(ctx, records):
+        records = _f32c(records)
+        K, N = records.shape[0] - 1, records.shape[1]
+        out = torch.empty(2 * K, N, L.REC, device=records.device)
+        L.call("mobgs_flow_records_fwd", L.FlowRecFwd(K, N, _p(records), _p(out)), _stream())
+        ctx.shape = (K, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        K, N = ctx.shape
+        g = _f32c(g)
+        v = torch.empty(K + 1, N, L.REC, device=g.device)
+        L.call("mobgs_flow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v)), _stream())
+        return v
+
+
+def flow_records(records):
+    return _FlowRecords.apply(records)

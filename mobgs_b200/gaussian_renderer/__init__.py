@@ -180,6 +180,43 @@ def get_flow(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, de
     return exp2mid_coord_map, mid2exp_coord_map, latent_img, latent_alpha
 
 
+def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposures):
+    """K get_flow() calls (train.py:563-579 issues one per latent sub-frame) as ONE projection
+    launch (K+1 record sets: the mid time once + the K exposure times) and TWO binning/blend launch
+    chains: 2K flow lists (two colour channels) and 2K image lists (latent image + dynamic-only
+    alpha of every exposure time).  Returns (exp2mid_coord [K,H,W,2], mid2exp_coord [K,H,W,2],
+    latent_img [K,3,H,W], latent_alpha [K,H,W]) — `torch.cat` of what K reference calls return."""
+    cam = viewpoint_camera
+    dev = dyn_pc._scaling.device
+    W, H = int(cam.image_width), int(cam.image_height)
+    viewmat = cam.world_view_transform.transpose(0, 1)
+    Ns, Nd = stat_pc.get_xyz.shape[0], dyn_pc.get_xyz.shape[0]
+    N = Ns + Nd
+    t0 = torch.as_tensor(float(cam.time), dtype=torch.float32, device=dev)
+    de = torch.as_tensor(delta_exposures, dtype=torch.float32, device=dev).reshape(-1)
+    K = de.numel()
+    t_poly = torch.cat([t0[None], t0 + de / cam.max_time])
+    rec, radii, depths, _ = fused.synth_project(
+        _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
+        viewmat[None].expand(K + 1, -1, -1), cam.K[None].expand(K + 1, -1, -1), t_poly.clamp(0, 1), t_poly, W, H)
+
+    # flows: set 2k = exposure-k geometry carrying (mid - exp), set 2k+1 = mid geometry carrying (exp - mid)
+    frec = fused.flow_records(rec)
+    sel = torch.tensor([v for k in range(K) for v in (k + 1, 0)], device=dev)
+    flows, _ = fused.blend_records(frec, radii[sel], depths[sel], None, 2, W, H, tight=TIGHT_TILES)
+    grid = torch.tensor(cam.get_pixels(W, H, use_center=False), device=dev, dtype=torch.float32)
+    exp2mid = grid + flows[0::2]
+    mid2exp = grid + flows[1::2]
+
+    # latent images (all Gaussians) and latent alphas (dynamic only) of the K exposure times
+    specs = [(k + 1, 0, N) for k in range(K)] + [(k + 1, Ns, N) for k in range(K)]
+    dec = dyn_pc.rgbdecoder
+    rgb, _, alpha, _ = fused.blend_decode(rec, radii, depths, _bg10(bg_color, dev).expand(2 * K, -1), cam.cam_ray,
+                                          dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6), W, H,
+                                          specs=specs, tight=TIGHT_TILES)
+    return exp2mid, mid2exp, rgb[:K], _alpha_render(alpha[K:], bg_color)
+
+
 def get_flow_static(source_camera, target_camera, splat_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor):
     """Reference: gaussian_renderer/__init__.py:494-552."""
     means, quats = stat_pc.get_xyz, stat_pc._rotation

@@ -261,3 +261,25 @@ def test_render_blurry_view_equals_reference_loop():
     ((pred_o - tgt).abs().mean() + sum((pkg[k] * w).mean() for k, w in ws.items())).backward()
     _check_param_grads(sc, dc, so, do)
     _close(out["viewspace_points"].grad, pkg["viewspace_points"].grad, "viewspace grad", max_outlier_frac=1e-3)
+
+
+def test_get_flow_batched_equals_k_reference_calls():
+    """get_flow_batched == K oracle get_flow calls (train.py:563-579), outputs and gradients."""
+    from mobgs_b200.gaussian_renderer import get_flow_batched
+    K = 5
+    (so, do, cam_o), (sc, dc, cam_c) = _pair(ns=500, nd=400, W=96, H=64, time=0.45)
+    bg = torch.tensor([0.0, 0.0, 0.0])
+    half = K // 2
+    deltas = [(k - half) / half for k in range(K)]
+    ref = [M.get_flow_ref(cam_o, so, do, None, bg, delta_exposure=d) for d in deltas]
+    got = get_flow_batched(cam_c, sc, dc, None, bg.cuda(), deltas)
+    want = [torch.cat([r[0] for r in ref]), torch.cat([r[1] for r in ref]),
+            torch.stack([r[2] for r in ref]), torch.cat([r[3] for r in ref])]
+    for a, b, n in zip(got, want, ["exp2mid", "mid2exp", "latent_img", "latent_alpha"]):
+        assert a.shape == b.shape, (n, a.shape, b.shape)
+        _close(a, b, n, atol=2e-4, scale_atol=False, max_outlier_frac=1e-3)
+    g = torch.Generator().manual_seed(2)
+    ws = [torch.rand(b.shape, generator=g) for b in want]
+    sum((a * w.cuda()).sum() for a, w in zip(got, ws)).backward()
+    sum((b * w).sum() for b, w in zip(want, ws)).backward()
+    _check_param_grads(sc, dc, so, do)

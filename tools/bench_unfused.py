@@ -100,6 +100,37 @@ def main():
         (out["render"] - tgt).abs().mean().backward()
 
     ms_bview = timed(blurry_view, steps)
+
+    # the flow half of the step (train.py:563-579): K get_flow calls per view
+    from mobgs_b200.gaussian_renderer import get_flow as dropin_get_flow, get_flow_batched
+    half = max(K // 2, 1)
+    fdeltas = [(k - K // 2) / half for k in range(K)]
+
+    def flow_loss(outs):
+        return sum(o.mean() for o in outs)
+
+    def ref_flows():
+        for p in params:
+            p.grad = None
+        tot = 0
+        for d in fdeltas:
+            tot = tot + flow_loss(M.get_flow_ref(cams[K // 2], stat, dyn, None, bg, delta_exposure=d))
+        tot.backward()
+
+    def dropin_flows():
+        for p in params:
+            p.grad = None
+        tot = 0
+        for d in fdeltas:
+            tot = tot + flow_loss(dropin_get_flow(cams[K // 2], stat, dyn, None, bg, delta_exposure=d))
+        tot.backward()
+
+    def batched_flows():
+        for p in params:
+            p.grad = None
+        flow_loss(get_flow_batched(cams[K // 2], stat, dyn, None, bg, fdeltas)).backward()
+
+    ms_flow_ref, ms_flow_dropin, ms_flow_batched = timed(ref_flows, steps), timed(dropin_flows, steps), timed(batched_flows, steps)
     ms_dropin = timed(dropin_loop, steps)
     ms_full = timed(reference_pattern(True), steps)
     ms_min = timed(reference_pattern(False), steps)
@@ -111,6 +142,10 @@ def main():
         "dropin_render_loop_ms": ms_dropin,                  # mobgs_b200.gaussian_renderer.render x K, train.py unchanged
         "fused_blurry_view_ms": ms_bview,                    # render_blurry_view: K sub-frames + centre s/d lists
         "fused_k_batched_ms": ms_fused,
+        "get_flow_reference_pattern_ms": ms_flow_ref,        # K x get_flow: 4 rasterisations + 2 projections each
+        "get_flow_dropin_loop_ms": ms_flow_dropin,
+        "get_flow_batched_ms": ms_flow_batched,
+        "speedup_get_flow_batched_vs_reference_pattern": ms_flow_ref / ms_flow_batched,
         "speedup_blurry_view_vs_train_py_pattern": ms_full / ms_bview,
         "speedup_vs_train_py_pattern": ms_full / ms_fused, "speedup_vs_minimal_pattern": ms_min / ms_fused,
         "note": "same sm_100a kernels underneath both arms; the reference arm keeps the reference's per-call "
