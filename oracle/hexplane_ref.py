@@ -3,7 +3,7 @@
 :417-438; scene/hexplane.py:19-108 normalize_aabb / grid_sample_wrapper / interpolate_ms_features;
 utils/graphics_utils.py:117-140 batch_quaternion_multiply) for the Stereo-Blur configuration.
 Pinned: tests/golden/hexplane_w128.npz holds inputs / state_dict / outputs of the reference module
-itself (tools/make_golden.py); tests/test_oracle.py::test_hexplane_ref_matches_reference_golden."""
+itself (tests/golden/make_golden.py); tests/test_oracle.py::test_hexplane_ref_matches_reference_golden."""
 import itertools
 import math
 

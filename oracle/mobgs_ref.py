@@ -1,7 +1,7 @@
 """ORACLE — test infrastructure only (see oracle/gsplat_ref.py header; parity unpinned
 for the gsplat half, pinned against the reference's own Python for this half by
-tests/test_reference_parity.py + tests/golden/ fixtures generated with
-tools/make_golden.py from /root/reference).
+tests/test_oracle.py + tests/golden/ fixtures generated with
+tests/golden/make_golden.py from /root/reference).
 
 CPU restatement of the MoBGS renderer layer that sits on top of the two gsplat
 operators:

@@ -5,7 +5,7 @@ travels to the GPU box.  Two families:
 
   render_*.npz   reference gaussian_renderer.render / get_flow / get_flow_static (source file
                  executed as-is) on the seeded stand-in scene of mobgs_b200.scene, with
-                 `gsplat.rendering` routed to the CPU oracle (compat/gsplat, backend "oracle") and
+                 `gsplat.rendering` replaced by the CPU oracle (injected into sys.modules by this script) and
                  the reference's own helper_model.Sandwich as the decoder.  This pins everything
                  *around* the two gsplat operators (spline, activations, concat order, decoder,
                  flow wiring, dict keys) to the reference's own code.
@@ -18,16 +18,23 @@ The reference hard-codes `.cuda()` / device="cuda" in the renderer (SURVEY.md Ap
 GPU-less container those calls are redirected to the CPU through a proxy of the `torch` module
 object *inside the imported reference module only* — the reference source is not edited.
 
-    MOBGS_GSPLAT_BACKEND=oracle python tools/make_golden.py
+    python tests/golden/make_golden.py
 """
 import os
 import sys
 import types
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF = "/root/reference"
-os.environ["MOBGS_GSPLAT_BACKEND"] = "oracle"
 sys.path[:0] = [os.path.join(ROOT, "compat"), ROOT, REF]
+
+# `gsplat.rendering` as seen by the reference renderer = the CPU oracle (test infrastructure; the
+# compat/ shim itself only ever routes to the CUDA library)
+import oracle.gsplat_ref as _oracle_gsplat  # noqa: E402
+_pkg = types.ModuleType("gsplat")
+_pkg.rendering = _oracle_gsplat
+sys.modules["gsplat"] = _pkg
+sys.modules["gsplat.rendering"] = _oracle_gsplat
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402

@@ -8,13 +8,13 @@ The orchestration is oracle/mobgs_ref.py's restatement of gaussian_renderer/__in
 the reference source by tests/golden) with its operator module swapped for the CUDA one.  It
 measures what fusion + K-batching buy on identical kernels; it is NOT gsplat's own kernels.
 
-    python tools/bench_unfused.py [workload] [steps]
+    python tests/perf/bench_unfused.py [workload] [steps]
 """
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

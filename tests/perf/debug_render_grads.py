@@ -1,6 +1,6 @@
 """Debug aid: per-output-key gradient error of the drop-in render() vs the fp32 and fp64 oracle."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle import mobgs_ref as M
 from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene

@@ -1,5 +1,5 @@
 """GPU parity against the committed outputs of the UNMODIFIED reference renderer
-(tests/golden/*.npz, tools/make_golden.py) — no oracle in the loop."""
+(tests/golden/*.npz, tests/golden/make_golden.py) — no oracle in the loop."""
 import os
 
 import numpy as np
