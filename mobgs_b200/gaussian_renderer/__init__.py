@@ -27,17 +27,33 @@ def _dynamic_params(pc):
             pc._features_t, pc._trbf_center)
 
 
+_BG_CACHE = {}
+
+
 def _bg10(bg_color, dev):
-    b3 = bg_color[:3].to(device=dev, dtype=torch.float32)
-    return torch.cat([b3, b3, b3, b3.new_zeros(1)])[None]
+    """bg[:3] tiled over the 9 feature channels + 0 for the depth channel (render():90-91), cached per
+    background tensor (identity + version) — it is the same tensor on every call of a training run."""
+    key = (bg_color.data_ptr(), bg_color._version, str(dev))
+    hit = _BG_CACHE.get("bg")
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    b3 = bg_color[:3].detach().to(device=dev, dtype=torch.float32)
+    out = torch.cat([b3, b3, b3, b3.new_zeros(1)])[None]
+    _BG_CACHE["bg"] = (key, out)
+    return out
 
 
 def _times(cam, delta_exposure, dev, clamp):
     """(t_spline, t_poly) as 0-d device tensors, built without a host sync."""
-    t0 = torch.as_tensor(float(cam.time), dtype=torch.float32, device=dev)
+    t0 = float(cam.time)
     if delta_exposure is None:
-        return t0, t0
-    t = t0 + torch.as_tensor(delta_exposure, dtype=torch.float32, device=dev) / cam.max_time
+        t = torch.tensor(t0, dtype=torch.float32, device=dev)
+        return t, t
+    if not torch.is_tensor(delta_exposure):      # host number: one 8-byte upload instead of a chain of tiny kernels
+        tp = t0 + float(delta_exposure) / cam.max_time
+        both = torch.tensor([min(max(tp, 0.0), 1.0) if clamp else tp, tp], dtype=torch.float32, device=dev)
+        return both[0], both[1]
+    t = t0 + delta_exposure.detach().to(device=dev, dtype=torch.float32) / cam.max_time
     return (torch.clamp(t, 0, 1) if clamp else t), t
 
 
@@ -142,42 +158,15 @@ def render(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, scal
 
 
 def get_flow(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposure=None):
-    """Reference: gaussian_renderer/__init__.py:318-492.  One K=2 projection launch (mid / exposure
-    time) feeds all four rasterisations."""
-    cam = viewpoint_camera
+    """Reference: gaussian_renderer/__init__.py:318-492.  One projection launch (mid + exposure time)
+    and two binning/blend launch chains feed all four rasterisations (the K = 1 case of
+    get_flow_batched).  Returns (exp2mid_coord_map [1,H,W,2], mid2exp_coord_map [1,H,W,2],
+    latent_img [3,H,W], latent_alpha [1,H,W])."""
     dev = dyn_pc._scaling.device
-    W, H = int(cam.image_width), int(cam.image_height)
-    viewmat = cam.world_view_transform.transpose(0, 1)
-    Kmat = cam.K
-    Ns, Nd = stat_pc.get_xyz.shape[0], dyn_pc.get_xyz.shape[0]
-    N = Ns + Nd
-    bg10 = _bg10(bg_color, dev)
-    ts_mid, tp_mid = _times(cam, 0.0, dev, clamp=True)
-    ts_exp, tp_exp = _times(cam, delta_exposure, dev, clamp=True)
-    rec, radii, depths, _ = fused.synth_project(
-        _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
-        torch.stack([viewmat, viewmat]), torch.stack([Kmat, Kmat]),
-        torch.stack([ts_mid, ts_exp]), torch.stack([tp_mid, tp_exp]), W, H)
-    mid, exp = slice(0, 1), slice(1, 2)
-
-    _, la = fused.blend_records(rec[exp], radii[exp], depths[exp], None, 1, W, H, g_range=(Ns, N), tight=TIGHT_TILES)
-    latent_alpha = _alpha_render(la, bg_color)
-
-    e2m = rec[0, :, 0:2] - rec[1, :, 0:2]
-    grid = torch.tensor(cam.get_pixels(W, H, use_center=False), device=dev, dtype=torch.float32)
-    e2m_flow, _ = ops.rasterize(rec[exp, :, 0:2], rec[exp, :, 3:6], e2m, rec[1, :, 2], None, depths[exp],
-                                radii[exp], W, H, tight=TIGHT_TILES)
-    exp2mid_coord_map = grid + e2m_flow
-    m2e_flow, _ = ops.rasterize(rec[mid, :, 0:2], rec[mid, :, 3:6], -e2m, rec[0, :, 2], None, depths[mid],
-                                radii[mid], W, H, tight=TIGHT_TILES)
-    mid2exp_coord_map = grid + m2e_flow
-
-    dec = dyn_pc.rgbdecoder
-    rgb, _, _, _ = fused.blend_decode(rec[exp], radii[exp], depths[exp], bg10, cam.cam_ray,
-                                      dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6), W, H,
-                                      tight=TIGHT_TILES)
-    latent_img = rgb[0]
-    return exp2mid_coord_map, mid2exp_coord_map, latent_img, latent_alpha
+    de = torch.as_tensor(delta_exposure, dtype=torch.float32, device=dev).reshape(1)
+    exp2mid, mid2exp, latent_img, latent_alpha = get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe,
+                                                                  bg_color, de)
+    return exp2mid, mid2exp, latent_img[0], latent_alpha
 
 
 def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposures):
