@@ -395,6 +395,31 @@ typedef struct {
 } MobgsFlowRecBwd;
 int mobgs_flow_records_bwd(const MobgsFlowRecBwd* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * HexPlane feature gather and its VJP as stand-alone kernels (the first stage of a11, used by the
+ * backward of the deformation module: scene/hexplane.py:19-108 interpolate_ms_features).
+ *   fwd: feat[n, l*32 + c] = prod_p bilinear(planes[l*6+p], coords_p(n))[c]
+ *   bwd: g_feat -> g_planes (channels-last, accumulated with vector atomics; zeroed by the caller),
+ *        g_pts [N,3] and g_times [N] (written; zero where normalize_aabb / the border clamp clipped).
+ * planes / plane_w / plane_h / aabb as in MobgsHexMlpFwd. */
+typedef struct {
+  int32_t N;
+  const float* pts;     /* [N,3] */
+  const float* times;   /* [N]   */
+  float aabb[6];
+  int32_t levels;
+  const float* planes[24];
+  int32_t plane_w[24];
+  int32_t plane_h[24];
+  float* feat;           /* fwd out [N, 32*levels] */
+  const float* g_feat;   /* bwd in  [N, 32*levels] */
+  float* g_planes[24];   /* bwd out, same shapes as planes */
+  float* g_pts;          /* bwd out [N,3] */
+  float* g_times;        /* bwd out [N]   */
+} MobgsHexFeat;
+int mobgs_hexplane_features_fwd(const MobgsHexFeat* a, void* stream);
+int mobgs_hexplane_features_bwd(const MobgsHexFeat* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -198,6 +198,13 @@ class FlowRecBwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("v_flow_records", C.c_void_p), ("v_records", C.c_void_p)]
 
 
+class HexFeat(C.Structure):
+    _fields_ = [("N", C.c_int32), ("pts", C.c_void_p), ("times", C.c_void_p), ("aabb", C.c_float * 6),
+                ("levels", C.c_int32), ("planes", C.c_void_p * 24), ("plane_w", C.c_int32 * 24),
+                ("plane_h", C.c_int32 * 24), ("feat", C.c_void_p), ("g_feat", C.c_void_p),
+                ("g_planes", C.c_void_p * 24), ("g_pts", C.c_void_p), ("g_times", C.c_void_p)]
+
+
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
 ENTRY_POINTS = {
@@ -217,6 +224,8 @@ ENTRY_POINTS = {
     "mobgs_hexplane_mlp_fwd": HexMlpFwd,
     "mobgs_flow_records_fwd": FlowRecFwd,
     "mobgs_flow_records_bwd": FlowRecBwd,
+    "mobgs_hexplane_features_fwd": HexFeat,
+    "mobgs_hexplane_features_bwd": HexFeat,
 }
 
 _lib = None

@@ -39,7 +39,8 @@ def test_ctypes_struct_sizes_match_header(tmp_path):
              "MobgsTileCount": _lib.TileCount, "MobgsTileSort": _lib.TileSort, "MobgsBlendFwd": _lib.BlendFwd,
              "MobgsBlendBwd": _lib.BlendBwd, "MobgsDecodeFwd": _lib.DecodeFwd, "MobgsDecodeBwd": _lib.DecodeBwd,
              "MobgsHexMlpFwd": _lib.HexMlpFwd, "MobgsLists": _lib.Lists,
-             "MobgsFlowRecFwd": _lib.FlowRecFwd, "MobgsFlowRecBwd": _lib.FlowRecBwd}
+             "MobgsFlowRecFwd": _lib.FlowRecFwd, "MobgsFlowRecBwd": _lib.FlowRecBwd,
+             "MobgsHexFeat": _lib.HexFeat}
     for name in re.findall(r"\}\s*(Mobgs[A-Za-z]+)\s*;", open(HDR).read()):
         assert name in pairs or hasattr(_lib, "EXTRA_STRUCTS") and name in _lib.EXTRA_STRUCTS, \
             f"struct {name} has no ctypes mirror listed in this test"
