@@ -26,6 +26,9 @@ constexpr int kBlendThreads = kTilePix;   // 256
 #ifndef MOBGS_TMA_STAGE
 #define MOBGS_TMA_STAGE 1
 #endif
+#ifndef MOBGS_BWD_PREDICATED
+#define MOBGS_BWD_PREDICATED 1
+#endif
 #ifndef MOBGS_BWD_MIN_CTAS
 #define MOBGS_BWD_MIN_CTAS 4
 #endif
@@ -451,6 +454,40 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       // v_x v_y v_opac v_ca v_cb v_cc v_col[D], zero-padded to a power of two
       constexpr int NV = (6 + D) <= 8 ? 8 : 16;
       float g[NV];
+#if MOBGS_BWD_PREDICATED
+      // branch-free: lanes whose pixel does not blend this Gaussian run the same arithmetic with
+      // alpha = 0, which leaves T and S unchanged and makes every gradient term exactly zero
+      {
+        float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
+        if (D > 2) r2 = srec[t][2];
+        if (D > 6) r3 = srec[t][3];
+        const float al = valid ? alpha : 0.f;
+        const float ra = __fdividef(1.f, 1.f - al);
+        T *= ra;
+        const float fac = al * T;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          d += rec_color(r1, r2, r3, c) * v_c[c];
+          g[6 + c] = fac * v_c[c];
+        }
+#pragma unroll
+        for (int c = 6 + D; c < NV; ++c) g[c] = 0.f;
+        const float v_alpha = d * T + (tf_term - S) * ra;
+        S += d * fac;
+        const float visv = valid ? vis : 0.f;          // (sigma < 0 lanes may hold vis = inf)
+        const float ov = r0.z * visv;
+        const float gate = ov <= kAlphaMax ? 1.f : 0.f;
+        const float v_sigma = -ov * v_alpha * gate;
+        const float sx = v_sigma * dx, sy = v_sigma * dy;
+        g[0] = r0.w * sx + r1.x * sy;
+        g[1] = r1.x * sx + r1.y * sy;
+        g[2] = visv * v_alpha * gate;
+        g[3] = sx * dx;            // the 1/2 of d sigma / d conic_a, conic_c is applied once, at the flush
+        g[4] = sx * dy;
+        g[5] = sy * dy;
+      }
+#else
 #pragma unroll
       for (int c = 0; c < NV; ++c) g[c] = 0.f;
       if (valid) {
@@ -470,14 +507,16 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
         S += d * fac;
         if (r0.z * vis <= kAlphaMax) {
           const float v_sigma = -r0.z * vis * v_alpha;
-          g[0] = v_sigma * (r0.w * dx + r1.x * dy);
-          g[1] = v_sigma * (r1.x * dx + r1.y * dy);
+          const float sx = v_sigma * dx, sy = v_sigma * dy;
+          g[0] = r0.w * sx + r1.x * sy;
+          g[1] = r1.x * sx + r1.y * sy;
           g[2] = vis * v_alpha;
-          g[3] = 0.5f * v_sigma * dx * dx;
-          g[4] = v_sigma * dx * dy;
-          g[5] = 0.5f * v_sigma * dy * dy;
+          g[3] = sx * dx;
+          g[4] = sx * dy;
+          g[5] = sy * dy;
         }
       }
+#endif
 #ifdef MOBGS_ABL_NAIVE_REDUCE
       // gsplat-style: one full 5-step shuffle reduction per value, lane 0 adds them one by one
 #pragma unroll
@@ -499,7 +538,9 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       constexpr int kVec = (6 + D + 3) / 4;
 #pragma unroll
       for (int v = 0; v < kVec; ++v) {
-        const float4 s = s4[v];
+        float4 s = s4[v];
+        if (v == 0) s.w *= 0.5f;           // conic_a   (record layout: x y opac ca | cb cc ...)
+        if (v == 1) s.y *= 0.5f;           // conic_c
         if (s.x != 0.f || s.y != 0.f || s.z != 0.f || s.w != 0.f) red_add_v4(dst + 4 * v, s.x, s.y, s.z, s.w);
         if (v == 0 && a.v_means2d_sep && k == a.sep_list && (s.x != 0.f || s.y != 0.f)) {
           atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid], s.x);
