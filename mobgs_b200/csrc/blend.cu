@@ -12,6 +12,7 @@
 // reductions (REDG.128) per (tile, Gaussian) — gsplat issues 16 scalar atomics per (warp,
 // Gaussian).
 #include "common.cuh"
+#include "blend_units.cuh"
 #include "decode_math.cuh"
 #include "tma.cuh"
 
@@ -40,26 +41,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 constexpr float kNegLog2e = -1.4426950408889634f;
 
-// Which of the tile's eight 16x2-pixel strips (= warps) can a Gaussian reach with alpha >= 1/255?
-// The ellipse sigma <= tau = log(255 opac) has vertical half-extent sqrt(2 tau * ca / det(conic)).
-// A strip outside it contributes nothing, so its warp skips the Gaussian without evaluating it.
-// Ablation switches (tools/ablation.sh): rebuild with -DMOBGS_ABL_NO_STRIP_MASK / -DMOBGS_ABL_NAIVE_REDUCE
-// to measure what the strip culling and the transposing butterfly buy.  Never set in the product build.
-__device__ __forceinline__ unsigned strip_mask(const float4& r0, const float4& r1, float tile_y0) {
-#ifdef MOBGS_ABL_NO_STRIP_MASK
-  return 0xffu;
+// Sub-warp units (blend_units.cuh): MOBGS_UNIT_LANES = 32 / 16 / 8 lanes per unit.
+#ifndef MOBGS_UNIT_LANES
+#define MOBGS_UNIT_LANES 16
 #endif
-  const float tau = __logf(255.f * r0.z) + 0.01f;
-  if (!(tau >= 0.f)) return 0u;
-  const float det = r0.w * r1.y - r1.x * r1.x;
-  if (!(det > 0.f)) return 0xffu;
-  const float ey = sqrtf(2.f * tau * r0.w / det) + 1e-3f;
-  const float lo = r0.y - ey - tile_y0, hi = r0.y + ey - tile_y0;   // tile-local pixel-centre range
-  unsigned m = 0u;
-#pragma unroll
-  for (int w = 0; w < 8; ++w)
-    if (hi >= 2.f * w + 0.5f && lo <= 2.f * w + 1.5f) m |= 1u << w;
-  return m;
+constexpr int kUL = MOBGS_UNIT_LANES;              // lanes (= pixels) per unit
+using UG = UnitGeom<kUL>;
+constexpr int kUW = UG::kUW, kUH = UG::kUH, kUX = UG::kUX, kUnits = UG::kUnits, kUPW = UG::kUPW;
+
+// Ablation switches (tools/ablation.sh): rebuild with -DMOBGS_ABL_NO_STRIP_MASK / -DMOBGS_ABL_NAIVE_REDUCE
+// to measure what the unit culling and the transposing butterfly buy.  Never set in the product build.
+__device__ __forceinline__ unsigned unit_mask(const float4& r0, const float4& r1, float tile_x0, float tile_y0) {
+#ifdef MOBGS_ABL_NO_STRIP_MASK
+  return UG::kAll;
+#else
+  return unit_mask<kUL>(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, tile_x0, tile_y0);
+#endif
 }
 
 __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, const float4& r3, int c) {
@@ -70,21 +67,35 @@ __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, c
   }
 }
 
-// Each warp compacts the batch entries whose strip mask includes it (ascending order kept) into its
-// own byte list, so its inner loop visits only Gaussians that can reach its 16x2 pixel strip.
-__device__ __forceinline__ int build_strip_list(const unsigned* smask, unsigned char* wlist, unsigned wbit,
+// Each warp compacts, for each of its kUPW units, the batch entries whose mask includes the unit
+// (ascending order kept) into the unit's byte list, so a unit's inner loop visits only Gaussians that
+// can reach its pixels.  `wl` = the list of the warp's first unit (lists are kBlendThreads bytes
+// apart), `t_begin` = first batch slot this lane's unit still needs.  Returns this lane's unit's count.
+__device__ __forceinline__ int build_unit_lists(const unsigned* smask, unsigned char* wl, int warp,
                                                 int lane, int t_begin, int bn) {
-  int cnt = 0;
+  int cnt[kUPW], tb[kUPW];
 #pragma unroll
-  for (int j = 0; j < kBlendThreads / 32; ++j) {
-    const int t = j * 32 + lane;
-    const bool m = t >= t_begin && t < bn && (smask[t] & wbit);
-    const unsigned b = __ballot_sync(0xffffffffu, m);
-    if (m) wlist[cnt + __popc(b & ((1u << lane) - 1u))] = (unsigned char)t;
-    cnt += __popc(b);
+  for (int s = 0; s < kUPW; ++s) {
+    cnt[s] = 0;
+    tb[s] = kUPW == 1 ? t_begin : __shfl_sync(0xffffffffu, t_begin, s * kUL);
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  for (int t0 = 0; t0 < bn; t0 += 32) {
+    const int t = t0 + lane;
+    const unsigned m = t < bn ? smask[t] >> (warp * kUPW) : 0u;
+#pragma unroll
+    for (int s = 0; s < kUPW; ++s) {
+      const bool hit = ((m >> s) & 1u) && t >= tb[s];
+      const unsigned b = __ballot_sync(0xffffffffu, hit);
+      if (hit) wl[s * kBlendThreads + cnt[s] + __popc(b & lt)] = (unsigned char)t;
+      cnt[s] += __popc(b);
+    }
   }
   __syncwarp();
-  return cnt;
+  int mine = cnt[0];
+#pragma unroll
+  for (int s = 1; s < kUPW; ++s) mine = (lane / kUL) == s ? cnt[s] : mine;
+  return mine;
 }
 
 __device__ __forceinline__ int lane_id() {
@@ -93,16 +104,17 @@ __device__ __forceinline__ int lane_id() {
   return l;
 }
 
-// Transposing butterfly over NV (8 or 16) per-lane values: each stage halves the number of live
-// values per lane while doubling the lanes summed, so NV values cost NV shuffles in total (not
-// 5 * NV).  Afterwards g[0] of lane l holds the complete warp sum of value index `vidx`(l); lanes
-// with (l & owner_mask) == 0 own distinct values.
+// Transposing butterfly over NV (8 or 16) per-lane values within each unit of kUL lanes: every
+// stage halves the number of live values per lane while doubling the lanes summed, so NV values cost
+// about NV shuffles in total (not log2(kUL) * NV).  Afterwards g[0 .. R-1] (R = max(1, NV / kUL)) of
+// lane l hold the complete unit sums of value indices vidx .. vidx + R - 1; when NV < kUL only lanes
+// with (l & (kUL / NV - 1)) == 0 own distinct values.
 template <int NV>
 __device__ __forceinline__ int butterfly_reduce(float (&g)[NV], int lane) {
   int vidx = 0;
   int n = NV / 2;
 #pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) {
+  for (int o = kUL / 2; o >= 1; o >>= 1) {
     if (n >= 1) {
       const bool up = (lane & o) != 0;
 #pragma unroll
@@ -122,11 +134,18 @@ __device__ __forceinline__ int butterfly_reduce(float (&g)[NV], int lane) {
   return vidx;
 }
 
+// tile-local pixel of thread `tid`: unit u = tid / kUL at (u % kUX, u / kUX), lane q = tid % kUL inside it
+__device__ __forceinline__ void unit_pixel(int tid, int& lx, int& ly) {
+  const int u = tid / kUL, q = tid % kUL;
+  lx = (u % kUX) * kUW + (q % kUW);
+  ly = (u / kUX) * kUH + (q / kUW);
+}
+
 template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ __align__(128) float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
-  __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
+  __shared__ unsigned char swl[kUnits][kBlendThreads];
   __shared__ __align__(16) float sdec[DEC ? 96 : 4];
   __shared__ __align__(8) uint64_t sbar;
   const int tiles = tiles_x * tiles_y;
@@ -134,15 +153,17 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x;
   const int lane = lane_id();
-  const unsigned wbit = 1u << (tid >> 5);
-  unsigned char* wlist = swl[tid >> 5];
+  const unsigned char* ulist = swl[tid / kUL];          // this lane's unit's list
+  unsigned char* wl0 = swl[(tid >> 5) * kUPW];          // list of the warp's first unit
   uint32_t bar_phase = 0;
   if (MOBGS_TMA_STAGE && tid == 0) {
     mbar_init(&sbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // made visible by the first barrier below
   }
   if (DEC && tid < 90) sdec[tid] = tid < 72 ? a.dec_w1[tid] : a.dec_w2[tid - 72];   // visible after the first barrier
-  const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
+  int lx, ly;
+  unit_pixel(tid, lx, ly);
+  const int ix = tx * kTile + lx, iy = ty * kTile + ly;
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
   const int cap = (int)min(a.list_capacity, (int64_t)0x7fffffff);
@@ -166,7 +187,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
     if (idx < end) bulk_g2s(&srec[tid][0], recs + (size_t)a.sorted_ids[idx] * 4, kRecBytes, &sbar);
     mbar_wait(&sbar, bar_phase);
     bar_phase ^= 1;
-    if (idx < end) smask[tid] = strip_mask(srec[tid][0], srec[tid][1], (float)(ty * kTile));
+    if (idx < end) smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
 #else
     if (idx < end) {
       const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
@@ -174,13 +195,13 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
       srec[tid][0] = q0; srec[tid][1] = q1;
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
-      smask[tid] = strip_mask(q0, q1, (float)(ty * kTile));
+      smask[tid] = unit_mask(q0, q1, (float)(tx * kTile), (float)(ty * kTile));
     }
 #endif
     __syncthreads();
-    const int cnt = build_strip_list(smask, wlist, wbit, lane, 0, bn);
+    const int cnt = build_unit_lists(smask, wl0, tid >> 5, lane, 0, bn);
     for (int i = 0; i < cnt && !done; ++i) {
-      const int t = wlist[i];
+      const int t = ulist[i];
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
       const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
   __shared__ int sid[kBlendThreads];
   __shared__ unsigned smask[kBlendThreads];
-  __shared__ unsigned char swl[kBlendThreads / 32][kBlendThreads];
+  __shared__ unsigned char swl[kUnits][kBlendThreads];
   __shared__ int warp_max[kBlendThreads / 32];
   __shared__ __align__(16) float sdec[DEC ? 96 : 4];
   __shared__ float swg[DEC ? 96 : 4];      // CTA-level decoder weight-gradient accumulator
@@ -254,14 +275,16 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x, lane = lane_id();
-  const unsigned wbit = 1u << (tid >> 5);
-  unsigned char* wlist = swl[tid >> 5];
+  const unsigned char* ulist = swl[tid / kUL];          // this lane's unit's list
+  unsigned char* wl0 = swl[(tid >> 5) * kUPW];          // list of the warp's first unit
   uint32_t bar_phase = 0;
   if (MOBGS_TMA_STAGE && tid == 0) {
     mbar_init(&sbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible after the barrier that follows
   }
-  const int ix = tx * kTile + (tid & (kTile - 1)), iy = ty * kTile + (tid >> 4);
+  int lx, ly;
+  unit_pixel(tid, lx, ly);
+  const int ix = tx * kTile + lx, iy = ty * kTile + ly;
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
   const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
@@ -396,7 +419,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   // last list entry any pixel of this tile blended
   int wmax = last;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  for (int o = kUL / 2; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  const int umax = wmax;                   // furthest entry any pixel of this lane's unit blended
+#pragma unroll
+  for (int o = 16; o >= kUL; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
   if (lane == 0) warp_max[tid >> 5] = wmax;
   __syncthreads();
   if (DEC && tid < 90 && swg[tid] != 0.f)
@@ -423,7 +449,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
     mbar_wait(&sbar, bar_phase);
     bar_phase ^= 1;
-    if (tid < bn) smask[tid] = strip_mask(srec[tid][0], srec[tid][1], (float)(ty * kTile));
+    if (tid < bn) smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
 #else
     if (tid < bn) {
       const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
@@ -433,23 +459,27 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       srec[tid][0] = q0; srec[tid][1] = q1;
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
-      smask[tid] = strip_mask(q0, q1, (float)(ty * kTile));
+      smask[tid] = unit_mask(q0, q1, (float)(tx * kTile), (float)(ty * kTile));
     }
 #pragma unroll
     for (int c = 0; c < kRecFloats; ++c) sacc[tid][c] = 0.f;
 #endif
     __syncthreads();
-    // entries above this warp's furthest pixel contribute nothing: skip them warp-uniformly
-    const int cnt = build_strip_list(smask, wlist, wbit, lane, max(0, hi - wmax), bn);
-    for (int i = 0; i < cnt; ++i) {
-      const int t = wlist[i];
+    // entries above this unit's furthest pixel contribute nothing: they never enter its list
+    const int cnt = build_unit_lists(smask, wl0, tid >> 5, lane, max(0, hi - umax), bn);
+    int cnt_warp = cnt;                    // the warp runs until its longest unit list is exhausted;
+#pragma unroll                             // a unit that is through idles on slot 0 with valid = false
+    for (int o = 16; o >= kUL; o >>= 1) cnt_warp = max(cnt_warp, __shfl_xor_sync(0xffffffffu, cnt_warp, o));
+    for (int i = 0; i < cnt_warp; ++i) {
+      const bool act = i < cnt;
+      const int t = act ? ulist[i] : 0;
       const int idx = hi - t;
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
       const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
       const float vis = ex2_approx(sigma * kNegLog2e);
       const float alpha = fminf(kAlphaMax, r0.z * vis);
-      const bool valid = inside && idx <= last && sigma >= 0.f && alpha >= kAlphaMin;
+      const bool valid = act && inside && idx <= last && sigma >= 0.f && alpha >= kAlphaMin;
       if (!__any_sync(0xffffffffu, valid)) continue;
       // v_x v_y v_opac v_ca v_cb v_cc v_col[D], zero-padded to a power of two
       constexpr int NV = (6 + D) <= 8 ? 8 : 16;
@@ -520,15 +550,23 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 #ifdef MOBGS_ABL_NAIVE_REDUCE
       // gsplat-style: one full 5-step shuffle reduction per value, lane 0 adds them one by one
 #pragma unroll
-      for (int c = 0; c < 6 + D; ++c) g[c] = warp_sum(g[c]);
-      if (lane == 0) {
+      for (int c = 0; c < 6 + D; ++c) {
+#pragma unroll
+        for (int o = kUL / 2; o > 0; o >>= 1) g[c] += __shfl_xor_sync(0xffffffffu, g[c], o);
+      }
+      if ((lane & (kUL - 1)) == 0) {
 #pragma unroll
         for (int c = 0; c < 6 + D; ++c) atomicAdd(&sacc[t][c], g[c]);
       }
 #else
       const int vidx = butterfly_reduce<NV>(g, lane);
-      constexpr int kOwnerMask = NV == 16 ? 1 : 3;   // lanes whose low bits are 0 own a value
-      if ((lane & kOwnerMask) == 0 && g[0] != 0.f) atomicAdd(&sacc[t][vidx], g[0]);
+      constexpr int kOwnerMask = NV < kUL ? kUL / NV - 1 : 0;   // lanes whose low bits are 0 own values
+      constexpr int kLeft = NV > kUL ? NV / kUL : 1;            // values left per lane
+      if ((lane & kOwnerMask) == 0) {
+#pragma unroll
+        for (int r = 0; r < kLeft; ++r)
+          if (g[r] != 0.f) atomicAdd(&sacc[t][vidx + r], g[r]);
+      }
 #endif
     }
     __syncthreads();

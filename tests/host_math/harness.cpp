@@ -2,9 +2,30 @@
 // arithmetic (projection fwd/VJP, Hermite taps) can be checked against the PyTorch oracle's
 // autograd on a machine without a GPU.  Nothing in mobgs_b200/ loads this library.
 #include "../../mobgs_b200/csrc/gs_math.cuh"
+#include "../../mobgs_b200/csrc/blend_units.cuh"
 
 using namespace mobgs;
 
+// geom per Gaussian: mx my opac ca cb cc (tile-local frame: tile origin (0,0)); lanes in {32,16,8}.
+// out_mask[g] = unit_mask<lanes>; out_need[g] = bit u set iff some pixel of unit u has
+// opac * exp(-sigma) >= 1/255 with sigma >= 0 (what the blend inner loop would accept), in double.
+template <int L>
+static void unit_mask_case(int n, const float* geom, unsigned* out_mask, unsigned* out_need) {
+  using G = UnitGeom<L>;
+  for (int g = 0; g < n; ++g) {
+    const float* r = geom + 6 * g;
+    out_mask[g] = unit_mask<L>(r[0], r[1], r[2], r[3], r[4], r[5], 0.f, 0.f);
+    unsigned need = 0;
+    for (int u = 0; u < G::kUnits; ++u)
+      for (int q = 0; q < L; ++q) {
+        const int lx = (u % G::kUX) * G::kUW + q % G::kUW, ly = (u / G::kUX) * G::kUH + q / G::kUW;
+        const double dx = (double)r[0] - (lx + 0.5), dy = (double)r[1] - (ly + 0.5);
+        const double sigma = 0.5 * ((double)r[3] * dx * dx + (double)r[5] * dy * dy) + (double)r[4] * dx * dy;
+        if (sigma >= 0 && (double)r[2] * exp(-sigma) >= 1.0 / 255.0) need |= 1u << u;
+      }
+    out_need[g] = need;
+  }
+}
 extern "C" {
 
 // viewmat: 16 floats row-major; K: 9 floats. out per Gaussian: mx my depth ca cb cc radius(as float)
@@ -61,6 +82,12 @@ void hm_project_bwd(int n, const float* means, const float* quats, const float* 
 void hm_hermite_taps(float t, int n, float* out) {
   SplineTaps s = hermite_taps(t, n);
   for (int i = 0; i < 4; ++i) { out[i] = (float)s.idx[i]; out[4 + i] = s.w[i]; }
+}
+
+void hm_unit_mask(int lanes, int n, const float* geom, unsigned* out_mask, unsigned* out_need) {
+  if (lanes == 32) unit_mask_case<32>(n, geom, out_mask, out_need);
+  else if (lanes == 16) unit_mask_case<16>(n, geom, out_mask, out_need);
+  else unit_mask_case<8>(n, geom, out_mask, out_need);
 }
 
 }

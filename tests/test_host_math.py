@@ -106,3 +106,28 @@ def test_hermite_taps_match_reference_formula(host_math):
             w = torch.from_numpy(out[4:].astype(np.float64))
             got = sum(w[i] * ctrl[:, idx[i], :] for i in range(4))
             assert torch.allclose(got, ref, atol=2e-5), (n, t)
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+def test_unit_mask_never_culls_a_contributing_pixel(host_math, lanes):
+    """blend_units.cuh unit_mask: every pixel the blend loop would accept (alpha >= 1/255) lies in a
+    unit whose bit is set; and the mask is tight (few units flagged that hold no such pixel)."""
+    rng = np.random.default_rng(lanes)
+    n = 40000
+    # centres in and around the tile, 1-sigma sizes 0.3 .. 12 px, any orientation, opacities down to ~1/255
+    mx, my = rng.uniform(-12, 28, n), rng.uniform(-12, 28, n)
+    s1, s2 = np.exp(rng.uniform(np.log(0.3), np.log(12), n)), np.exp(rng.uniform(np.log(0.3), np.log(12), n))
+    th = rng.uniform(0, np.pi, n)
+    c, s = np.cos(th), np.sin(th)
+    cov = np.stack([c * c * s1**2 + s * s * s2**2, c * s * (s1**2 - s2**2), s * s * s1**2 + c * c * s2**2], -1)
+    det = cov[:, 0] * cov[:, 2] - cov[:, 1] ** 2
+    conic = np.stack([cov[:, 2] / det, -cov[:, 1] / det, cov[:, 0] / det], -1)
+    opac = np.where(rng.random(n) < 0.2, rng.uniform(0.003, 0.01, n), rng.uniform(0.01, 1.0, n))
+    geom = np.ascontiguousarray(np.concatenate([mx[:, None], my[:, None], opac[:, None], conic], 1), np.float32)
+    mask, need = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    up = C.POINTER(C.c_uint32)
+    host_math.hm_unit_mask(lanes, n, _fp(geom), mask.ctypes.data_as(up), need.ctypes.data_as(up))
+    assert ((need & ~mask) == 0).all(), "a contributing pixel was culled"
+    pop = lambda a: sum(int(bin(int(v)).count("1")) for v in a)
+    extra = pop(mask & ~need) / max(1, pop(need))
+    assert pop(need) > 10000 and extra < 0.08, extra
