@@ -69,8 +69,9 @@ __device__ __forceinline__ float rec_color(const float4& r1, const float4& r2, c
 
 // Each warp compacts, for each of its kUPW units, the batch entries whose mask includes the unit
 // (ascending order kept) into the unit's byte list, so a unit's inner loop visits only Gaussians that
-// can reach its pixels.  `wl` = the list of the warp's first unit (lists are kBlendThreads bytes
+// can reach its pixels.  `wl` = the list of the warp's first unit (lists are STRIDE bytes
 // apart), `t_begin` = first batch slot this lane's unit still needs.  Returns this lane's unit's count.
+template <int STRIDE = kBlendThreads>
 __device__ __forceinline__ int build_unit_lists(const unsigned* smask, unsigned char* wl, int warp,
                                                 int lane, int t_begin, int bn) {
   int cnt[kUPW], tb[kUPW];
@@ -87,7 +88,7 @@ __device__ __forceinline__ int build_unit_lists(const unsigned* smask, unsigned 
     for (int s = 0; s < kUPW; ++s) {
       const bool hit = ((m >> s) & 1u) && t >= tb[s];
       const unsigned b = __ballot_sync(0xffffffffu, hit);
-      if (hit) wl[s * kBlendThreads + cnt[s] + __popc(b & lt)] = (unsigned char)t;
+      if (hit) wl[s * STRIDE + cnt[s] + __popc(b & lt)] = (unsigned char)t;
       cnt[s] += __popc(b);
     }
   }
@@ -260,40 +261,18 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   }
 }
 
+// Start state of one pixel's backward walk: T_final, the last blended list entry, the gradient of the
+// loss w.r.t. the pixel's D blended channels (v_c) and alpha (v_a).  Plain path: read from
+// v_out_colors / v_out_alphas.  DEC: VJP of (expected depth, Sandwich decoder, sub-frame mean)
+// evaluated here, with the decoder weight gradients of the whole tile summed into swg[90].
+// sx [12][kBlendThreads + 1] and sg [15][kBlendThreads + 1] (ghpre 0..5 | gpre 6..8 | relu(h) 9..14)
+// are scratch that may alias buffers which are idle until the list walk starts.  Called by all
+// threads of the CTA (contains barriers).
 template <int D, bool DEC>
-__global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
-  __shared__ __align__(128) float4 srec[kBlendThreads][4];
-  __shared__ __align__(8) uint64_t sbar;
-  __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
-  __shared__ int sid[kBlendThreads];
-  __shared__ unsigned smask[kBlendThreads];
-  __shared__ unsigned char swl[kUnits][kBlendThreads];
-  __shared__ int warp_max[kBlendThreads / 32];
-  __shared__ __align__(16) float sdec[DEC ? 96 : 4];
-  __shared__ float swg[DEC ? 96 : 4];      // CTA-level decoder weight-gradient accumulator
-  const int tiles = tiles_x * tiles_y;
-  const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
-  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-  const int tid = threadIdx.x, lane = lane_id();
-  const unsigned char* ulist = swl[tid / kUL];          // this lane's unit's list
-  unsigned char* wl0 = swl[(tid >> 5) * kUPW];          // list of the warp's first unit
-  uint32_t bar_phase = 0;
-  if (MOBGS_TMA_STAGE && tid == 0) {
-    mbar_init(&sbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible after the barrier that follows
-  }
-  int lx, ly;
-  unit_pixel(tid, lx, ly);
-  const int ix = tx * kTile + lx, iy = ty * kTile + ly;
-  const bool inside = ix < a.width && iy < a.height;
-  const float px = ix + 0.5f, py = iy + 0.5f;
-  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
-  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
-  float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
-
-  float T_final = 1.f, v_a = 0.f, bg_dot = 0.f;
-  float v_c[D];
-  int last = -1;
+__device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k, int tid, bool inside, int ix, int iy,
+                                                   float* sx, float* sg, float* sdec, float* swg,
+                                                   float& T_final, int& last, float (&v_c)[D], float& v_a) {
+  T_final = 1.f; v_a = 0.f; last = -1;
 #pragma unroll
   for (int c = 0; c < D; ++c) v_c[c] = 0.f;
   if (DEC) {
@@ -319,8 +298,6 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     // product each over half of the tile's pixels.  Live ranges are kept short on purpose: holding
     // the factors in registers spilled ~460 B per thread (4.9 GB of local-memory DRAM writes).
     constexpr int kPad = kBlendThreads + 1;              // row stride: distinct rows hit distinct banks
-    float* sx = reinterpret_cast<float*>(&srec[0][0]);   // [12][kPad]
-    float* sg = &sacc[0][0];                             // [15][kPad]: ghpre 0..5 | gpre 6..8 | relu(h) 9..14
     const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
     const float* w1 = sdec;
     const float* w2 = sdec + (DEC ? 72 : 0);
@@ -404,6 +381,44 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
       if (acc != 0.f) atomicAdd(&swg[o], acc);
     }
   }
+}
+
+template <int D, bool DEC>
+__global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
+  __shared__ __align__(128) float4 srec[kBlendThreads][4];
+  __shared__ __align__(8) uint64_t sbar;
+  __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
+  __shared__ int sid[kBlendThreads];
+  __shared__ unsigned smask[kBlendThreads];
+  __shared__ unsigned char swl[kUnits][kBlendThreads];
+  __shared__ int warp_max[kBlendThreads / 32];
+  __shared__ __align__(16) float sdec[DEC ? 96 : 4];
+  __shared__ float swg[DEC ? 96 : 4];      // CTA-level decoder weight-gradient accumulator
+  const int tiles = tiles_x * tiles_y;
+  const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int tid = threadIdx.x, lane = lane_id();
+  const unsigned char* ulist = swl[tid / kUL];          // this lane's unit's list
+  unsigned char* wl0 = swl[(tid >> 5) * kUPW];          // list of the warp's first unit
+  uint32_t bar_phase = 0;
+  if (MOBGS_TMA_STAGE && tid == 0) {
+    mbar_init(&sbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible after the barrier that follows
+  }
+  int lx, ly;
+  unit_pixel(tid, lx, ly);
+  const int ix = tx * kTile + lx, iy = ty * kTile + ly;
+  const bool inside = ix < a.width && iy < a.height;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
+  float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
+
+  float T_final, v_a, bg_dot = 0.f;
+  float v_c[D];
+  int last;
+  bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, reinterpret_cast<float*>(&srec[0][0]), &sacc[0][0], sdec, swg,
+                             T_final, last, v_c, v_a);
   if (inside) {
     if (a.backgrounds) {
       const float* bg = a.backgrounds + (size_t)k * D;
@@ -589,6 +604,263 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Backward, transposing variant (kUL == 16).  The butterfly above spends ~45 % of the kernel's
+// instructions moving per-(pixel, Gaussian) terms between lanes.  Here the reduction over pixels
+// is done by changing ownership instead: a unit walks its list in blocks of kBlk = 8 entries.
+//   Phase A (lane = pixel): the usual back-to-front recurrence (T, S) per entry, but only the two
+//     scalars every gradient of the pair is linear in — fac = alpha T (colours) and v_sigma
+//     (geometry, opacity) — are produced, and parked in a per-warp [8 entries][32 pixels] matrix.
+//   Phase B (lane = (entry j, half of the unit's pixels)): reads row j of both matrices and sums
+//     over its 8 pixels the colour gradients fac * v_c[p] (v_c of the unit's pixels sits in shared
+//     memory, written once per tile) and the moments sum v_sigma {dx, dy, 1, dx^2, dx dy, dy^2};
+//     one butterfly stage joins the two halves, the 16 sums go to the tile accumulator.
+// The flush turns moments into gradients (v_x = a Ax + b Ay, v_y = b Ax + c Ay, v_opac = -A0 / opac,
+// conic = (Axx / 2, Axy, Ayy / 2)) — linear, so summing moments over units first is equivalent.
+constexpr int kBwdBatch = 128;                 // list entries staged per batch (shared-memory budget)
+constexpr int kBlk = 8;                        // entries per Phase A / Phase B block
+constexpr int kFRow = 36;                      // row stride of the per-warp F / VS matrices (32 pixels + 4: the
+                                               // 8 rows a quarter-warp reads in Phase B start 4 banks apart)
+constexpr int kVPix = 12;                      // floats per pixel in sV (10 used; 3 x LDS.128)
+constexpr int kVHalf = 8 * kVPix + 4;          // second half of a unit's pixels: +4 banks
+constexpr int kVUnit = 2 * kVHalf + 8;         // second unit of the warp: +16 banks -> the four (unit, half)
+constexpr int kVWarp = 2 * kVUnit;             //   groups of a warp read four different 16-byte bank groups
+constexpr int kAccRow = 17;                    // accumulator row stride: row t starts at bank 17 t
+constexpr int kTrScratch = kBwdBatch * kRecFloats + kBwdBatch * kAccRow + 8 * 2 * kBlk * kFRow;   // floats
+static_assert(kTrScratch >= 27 * (kBlendThreads + 1), "prologue scratch must fit the aliased buffers");
+constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kBwdBatch + 8 * 4 + 16;
+
+template <int D, bool DEC>
+__global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_tr_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
+  static_assert(kUL == 16, "transposing backward is written for 4x4-pixel units");
+  extern __shared__ __align__(128) float smem[];
+  float* srec = smem;                                            // [kBwdBatch][16]   (TMA destination)
+  float* sacc = srec + kBwdBatch * kRecFloats;                   // [kBwdBatch][kAccRow]
+  float* sF = sacc + kBwdBatch * kAccRow;                        // [8 warps][F | VS][kBlk][kFRow]
+  float* sV = smem + kTrScratch;                                 // [8 warps][kVWarp]
+  float* sdec = sV + 8 * kVWarp;                                 // [96]
+  float* swg = sdec + 96;                                        // [96]
+  int* sid = reinterpret_cast<int*>(swg + 96);                   // [kBwdBatch]
+  unsigned* smask = reinterpret_cast<unsigned*>(sid + kBwdBatch);   // [kBwdBatch]
+  int* warp_max = reinterpret_cast<int*>(smask + kBwdBatch);     // [8]
+  uint64_t* sbar = reinterpret_cast<uint64_t*>(warp_max + 8);    // 8-byte aligned: everything before is a multiple of 8 B
+  unsigned char* swl = reinterpret_cast<unsigned char*>(sbar + 1);   // [16 units][kBwdBatch]
+
+  const int tiles = tiles_x * tiles_y;
+  const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+  const unsigned char* ulist = swl + (tid / kUL) * kBwdBatch;    // this lane's unit's list
+  unsigned char* wl0 = swl + warp * kUPW * kBwdBatch;            // list of the warp's first unit
+  uint32_t bar_phase = 0;
+  if (tid == 0) {
+    mbar_init(sbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // visible after the barrier that follows
+  }
+  int lx, ly;
+  unit_pixel(tid, lx, ly);
+  const int ix = tx * kTile + lx, iy = ty * kTile + ly;
+  const bool inside = ix < a.width && iy < a.height;
+  const float px = ix + 0.5f, py = iy + 0.5f;
+  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
+  const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
+  float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
+
+  float T_final, v_a, bg_dot = 0.f;
+  float v_c[D];
+  int last;
+  bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, smem, smem + 12 * (kBlendThreads + 1), sdec, swg,
+                             T_final, last, v_c, v_a);
+  if (inside && a.backgrounds) {
+    const float* bg = a.backgrounds + (size_t)k * D;
+#pragma unroll
+    for (int c = 0; c < D; ++c) bg_dot += bg[c] * v_c[c];
+  }
+  // this pixel's v_c -> sV (read by the Phase B lanes of its unit): 12 floats per pixel, zero padded
+  const int q = lane & 15, hu = lane >> 4;                        // pixel in unit, unit in warp
+  {
+    float* vp = sV + warp * kVWarp + hu * kVUnit + (q >> 3) * kVHalf + (q & 7) * kVPix;
+    float t12[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) t12[c] = c < D ? v_c[c % D] : 0.f;
+#pragma unroll
+    for (int c = 0; c < 12; c += 4)
+      if (c < D) *reinterpret_cast<float4*>(vp + c) = make_float4(t12[c], t12[c + 1], t12[c + 2], t12[c + 3]);
+  }
+  float T = T_final;
+  float S = 0.f;                           // sum_c v_c[c] * (colour accumulated behind the current Gaussian)
+  const float tf_term = T_final * (v_a - bg_dot);
+  int wmax = last;
+#pragma unroll
+  for (int o = kUL / 2; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  const int umax = wmax;                   // furthest entry any pixel of this lane's unit blended
+  wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 16));
+  if (lane == 0) warp_max[warp] = wmax;
+  fence_proxy_async();                     // the prologue's generic-proxy scratch writes precede the TMA writes to srec
+  __syncthreads();                         // prologue scratch is free, sV / swg / warp_max are complete
+  if (DEC && tid < 90 && swg[tid] != 0.f)
+    atomicAdd(a.v_w_partial + (size_t)(blockIdx.x % MOBGS_DEC_SLOTS) * 90 + tid, swg[tid]);
+  int tile_last = -1;
+#pragma unroll
+  for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
+  if (tile_last < beg) return;
+
+  float* Fm = sF + warp * (2 * kBlk * kFRow);                     // F  [kBlk][kFRow]: fac     of (entry, pixel of the warp)
+  float* VSm = Fm + kBlk * kFRow;                                 // VS [kBlk][kFRow]: v_sigma
+  const int pj = q & 7, ph = q >> 3;                              // Phase B: entry in block, pixel half
+  const float* vrow = sV + warp * kVWarp + hu * kVUnit + ph * kVHalf;
+  // tile-local x / y of the Phase B lane's pixels: columns 0..3 of the unit, rows 2 ph, 2 ph + 1
+  const float ubx = (float)(tx * kTile + ((tid / kUL) % kUX) * kUW) + 0.5f;
+  const float uby = (float)(ty * kTile + ((tid / kUL) / kUX) * kUH + 2 * ph) + 0.5f;
+  constexpr uint32_t kRecBytes = D > 6 ? 64 : (D > 2 ? 48 : 32);
+
+  // walk the list back to front in batches: batch b covers [hi - kBwdBatch + 1, hi]
+  for (int hi = tile_last; hi >= beg; hi -= kBwdBatch) {
+    const int lo = max(beg, hi - kBwdBatch + 1);
+    const int bn = hi - lo + 1;
+    __syncthreads();   // previous batch fully flushed
+    if (tid == 0) mbar_expect_tx(sbar, (uint32_t)bn * kRecBytes);
+    if (tid < bn) {
+      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      sid[tid] = g;
+      bulk_g2s(srec + tid * kRecFloats, recs + (size_t)g * 4, kRecBytes, sbar);
+    }
+    for (int i = tid; i < kBwdBatch * kAccRow; i += kBlendThreads) sacc[i] = 0.f;
+    mbar_wait(sbar, bar_phase);
+    bar_phase ^= 1;
+    if (tid < bn) {
+      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecFloats);
+      smask[tid] = unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
+    }
+    __syncthreads();
+    // entries above this unit's furthest pixel contribute nothing: they never enter its list
+    const int cnt = build_unit_lists<kBwdBatch>(smask, wl0, warp, lane, max(0, hi - umax), bn);
+    const int cnt_warp = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+    for (int base = 0; base < cnt_warp; base += kBlk) {
+      const int nb = min(kBlk, cnt_warp - base);
+      // ---- Phase A: lane = pixel.  A unit that is through idles on slot 0 with valid = false.
+#pragma unroll 2
+      for (int i = 0; i < nb; ++i) {
+        const bool act = base + i < cnt;
+        const int t = act ? ulist[base + i] : 0;
+        const float4* r = reinterpret_cast<const float4*>(srec + t * kRecFloats);
+        const float4 r0 = r[0], r1 = r[1];
+        float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
+        if (D > 2) r2 = r[2];
+        if (D > 6) r3 = r[3];
+        const float dx = r0.x - px, dy = r0.y - py;
+        const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
+        const float vis = ex2_approx(sigma * kNegLog2e);
+        const float alpha = fminf(kAlphaMax, r0.z * vis);
+        const bool valid = act && inside && hi - t <= last && sigma >= 0.f && alpha >= kAlphaMin;
+        // lanes whose pixel does not blend this Gaussian run the same arithmetic with alpha = 0, which
+        // leaves T and S unchanged and makes both stored terms exactly zero
+        const float al = valid ? alpha : 0.f;
+        const float ra = __fdividef(1.f, 1.f - al);
+        T *= ra;
+        const float fac = al * T;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < D; ++c) d += rec_color(r1, r2, r3, c) * v_c[c];
+        const float v_alpha = d * T + (tf_term - S) * ra;
+        S += d * fac;
+        const float ov = r0.z * (valid ? vis : 0.f);             // (sigma < 0 lanes may hold vis = inf)
+        const float v_sigma = ov <= kAlphaMax ? -ov * v_alpha : 0.f;
+        Fm[i * kFRow + lane] = fac;
+        VSm[i * kFRow + lane] = v_sigma;
+      }
+      __syncwarp();
+      // ---- Phase B: lane = (entry pj of the block, pixel half ph) of its unit
+      float acc[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+      const bool on = pj < nb && base + pj < cnt;
+      int tb = 0;
+      if (on) {
+        tb = ulist[base + pj];
+        const float2 mean = *reinterpret_cast<const float2*>(srec + tb * kRecFloats);
+        const float* fr = Fm + pj * kFRow + hu * 16 + ph * 8;
+        const float* sr = VSm + pj * kFRow + hu * 16 + ph * 8;
+        const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
+        const float4 s0 = *reinterpret_cast<const float4*>(sr), s1 = *reinterpret_cast<const float4*>(sr + 4);
+        const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float dxs[4], dys[2];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dxs[c] = mean.x - (ubx + (float)c);
+        dys[0] = mean.y - uby;
+        dys[1] = mean.y - (uby + 1.f);
+#pragma unroll
+        for (int pp = 0; pp < 8; ++pp) {
+          const float dx = dxs[pp & 3], dy = dys[pp >> 2];
+          const float vs = sv[pp], sx = vs * dx, sy = vs * dy;
+          acc[0] += sx;
+          acc[1] += sy;
+          acc[2] += vs;
+          acc[3] += sx * dx;
+          acc[4] += sx * dy;
+          acc[5] += sy * dy;
+          const float4* vp = reinterpret_cast<const float4*>(vrow + pp * kVPix);
+          const float4 v0 = vp[0];
+          acc[6] += fv[pp] * v0.x;
+          if (D > 1) acc[7] += fv[pp] * v0.y;
+          if (D > 2) acc[8] += fv[pp] * v0.z;
+          if (D > 3) acc[9] += fv[pp] * v0.w;
+          if (D > 4) {
+            const float4 v1 = vp[1];
+            acc[10] += fv[pp] * v1.x;
+            if (D > 5) acc[11] += fv[pp] * v1.y;
+            if (D > 6) acc[12] += fv[pp] * v1.z;
+            if (D > 7) acc[13] += fv[pp] * v1.w;
+          }
+          if (D > 8) {
+            const float4 v2 = vp[2];
+            acc[14] += fv[pp] * v2.x;
+            if (D > 9) acc[15] += fv[pp] * v2.y;
+          }
+        }
+      }
+      // join the two pixel halves: afterwards acc[i] of lane (pj, ph) is the unit sum of value 8 ph + i
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float send = ph ? acc[i] : acc[i + 8];
+        const float keep = ph ? acc[i + 8] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      if (on) {
+        float* dst = sacc + tb * kAccRow + ph * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (acc[i] != 0.f) atomicAdd(dst + i, acc[i]);
+      }
+      __syncwarp();   // Phase B reads of F / VS are done before the next block overwrites them
+    }
+    __syncthreads();
+    if (tid < bn) {
+      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecFloats);
+      const float4 r0 = r[0], r1 = r[1];
+      const float* sa = sacc + tid * kAccRow;
+      const float ax = sa[0], ay = sa[1], a0 = sa[2];
+      float4 s[4];
+      s[0] = make_float4(r0.w * ax + r1.x * ay, r1.x * ax + r1.y * ay, a0 != 0.f ? -a0 / r0.z : 0.f, 0.5f * sa[3]);
+      s[1] = make_float4(sa[4], 0.5f * sa[5], sa[6], sa[7]);
+      s[2] = make_float4(sa[8], sa[9], sa[10], sa[11]);
+      s[3] = make_float4(sa[12], sa[13], sa[14], sa[15]);
+      float* dst = v_recs + (size_t)sid[tid] * kRecFloats;
+      constexpr int kVec = (6 + D + 3) / 4;
+#pragma unroll
+      for (int v = 0; v < kVec; ++v)
+        if (s[v].x != 0.f || s[v].y != 0.f || s[v].z != 0.f || s[v].w != 0.f)
+          red_add_v4(dst + 4 * v, s[v].x, s[v].y, s[v].z, s[v].w);
+      if (a.v_means2d_sep && k == a.sep_list && (s[0].x != 0.f || s[0].y != 0.f)) {
+        atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid], s[0].x);
+        atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid] + 1, s[0].y);
+      }
+    }
+  }
+}
+
 }  // namespace mobgs
 
 using namespace mobgs;
@@ -597,9 +869,27 @@ template <int D>
 static void launch_fwd(const MobgsBlendFwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
   blend_fwd_kernel<D, false><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
 }
+// 1: transposing backward (blend_bwd_tr_kernel, needs 4x4 units); 0: butterfly backward (blend_bwd_kernel)
+#ifndef MOBGS_BWD_TRANSPOSE
+#define MOBGS_BWD_TRANSPOSE 1
+#endif
+template <int D, bool DEC>
+static void launch_bwd_kernel(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
+#if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16
+  static bool configured = false;   // per instantiation; the attribute is idempotent, a race only repeats the call
+  if (!configured) {
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrSmemBytes);
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    configured = true;
+  }
+  blend_bwd_tr_kernel<D, DEC><<<a.K * tiles_x * tiles_y, kBlendThreads, kTrSmemBytes, s>>>(a, tiles_x, tiles_y);
+#else
+  blend_bwd_kernel<D, DEC><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+#endif
+}
 template <int D>
 static void launch_bwd(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
-  blend_bwd_kernel<D, false><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
+  launch_bwd_kernel<D, false>(a, tiles_x, tiles_y, s);
 }
 
 #define MOBGS_DISPATCH_D(D, FN, ...)                                   \
@@ -643,7 +933,7 @@ extern "C" int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream) {
   if (a->dec_rays) {
     MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_colors && a->v_w_partial,
                   "fused decode prologue needs D=10, w1, w2, out_colors, v_w_partial");
-    blend_bwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+    launch_bwd_kernel<10, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
     return check_launch("blend_decode_bwd");
   }
   MOBGS_REQUIRE(a->v_out_colors, "v_out_colors must not be NULL");

@@ -1,0 +1,8 @@
+#!/bin/bash
+# (GPU box) one ncu --set full capture each of the fused blend backward / forward kernels of the headline step.
+mkdir -p gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:blend_bwd -s 2 -c 1 -f -o gpurun_out/blend_bwd \
+  python bench.py --no-cpu-baseline --steps 2 --warmup 1 > gpurun_out/ncu_bwd.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:blend_fwd -s 2 -c 1 -f -o gpurun_out/blend_fwd \
+  python bench.py --no-cpu-baseline --steps 2 --warmup 1 > gpurun_out/ncu_fwd.log 2>&1
+ls -la gpurun_out
