@@ -618,7 +618,14 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 //     one butterfly stage joins the two halves, the 16 sums go to the tile accumulator.
 // The flush turns moments into gradients (v_x = a Ax + b Ay, v_y = b Ax + c Ay, v_opac = -A0 / opac,
 // conic = (Axx / 2, Axy, Ayy / 2)) — linear, so summing moments over units first is equivalent.
-constexpr int kBwdBatch = 128;                 // list entries staged per batch (shared-memory budget)
+// 1: Phase B lanes turn their (unit, Gaussian) sums into gradients and send them straight to global
+// memory (2 x RED.128 per lane); 0: they are first combined across the tile's units in a shared-memory
+// accumulator (16 CAS-loop atomics per (unit, Gaussian) — those were 15 % of the instructions and 28 % of
+// the stall samples) and flushed once per (tile, Gaussian).
+#ifndef MOBGS_BWD_DIRECT_RED
+#define MOBGS_BWD_DIRECT_RED 1
+#endif
+constexpr int kBwdBatch = MOBGS_BWD_DIRECT_RED ? 256 : 128;   // list entries staged per batch (shared-memory budget)
 constexpr int kBlk = 8;                        // entries per Phase A / Phase B block
 constexpr int kFRow = 36;                      // row stride of the per-warp F / VS matrices (32 pixels + 4: the
                                                // 8 rows a quarter-warp reads in Phase B start 4 banks apart)
@@ -627,7 +634,8 @@ constexpr int kVHalf = 8 * kVPix + 4;          // second half of a unit's pixels
 constexpr int kVUnit = 2 * kVHalf + 8;         // second unit of the warp: +16 banks -> the four (unit, half)
 constexpr int kVWarp = 2 * kVUnit;             //   groups of a warp read four different 16-byte bank groups
 constexpr int kAccRow = 17;                    // accumulator row stride: row t starts at bank 17 t
-constexpr int kTrScratch = kBwdBatch * kRecFloats + kBwdBatch * kAccRow + 8 * 2 * kBlk * kFRow;   // floats
+constexpr int kAccFloats = MOBGS_BWD_DIRECT_RED ? 0 : kBwdBatch * kAccRow;
+constexpr int kTrScratch = kBwdBatch * kRecFloats + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
 static_assert(kTrScratch >= 27 * (kBlendThreads + 1), "prologue scratch must fit the aliased buffers");
 constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kBwdBatch + 8 * 4 + 16;
 
@@ -637,7 +645,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   extern __shared__ __align__(128) float smem[];
   float* srec = smem;                                            // [kBwdBatch][16]   (TMA destination)
   float* sacc = srec + kBwdBatch * kRecFloats;                   // [kBwdBatch][kAccRow]
-  float* sF = sacc + kBwdBatch * kAccRow;                        // [8 warps][F | VS][kBlk][kFRow]
+  float* sF = sacc + kAccFloats;                                 // [8 warps][F | VS][kBlk][kFRow]
   float* sV = smem + kTrScratch;                                 // [8 warps][kVWarp]
   float* sdec = sV + 8 * kVWarp;                                 // [96]
   float* swg = sdec + 96;                                        // [96]
@@ -726,7 +734,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
       sid[tid] = g;
       bulk_g2s(srec + tid * kRecFloats, recs + (size_t)g * 4, kRecBytes, sbar);
     }
-    for (int i = tid; i < kBwdBatch * kAccRow; i += kBlendThreads) sacc[i] = 0.f;
+    for (int i = tid; i < kAccFloats; i += kBlendThreads) sacc[i] = 0.f;
     mbar_wait(sbar, bar_phase);
     bar_phase ^= 1;
     if (tid < bn) {
@@ -828,6 +836,34 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         const float keep = ph ? acc[i + 8] : acc[i];
         acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
       }
+#if MOBGS_BWD_DIRECT_RED
+      if (on) {
+        float* dst = v_recs + (size_t)sid[tb] * kRecFloats + ph * 8;
+        if (ph == 0) {
+          // moments -> gradients: record layout x y opac ca | cb cc c0 c1
+          const float4* r = reinterpret_cast<const float4*>(srec + tb * kRecFloats);
+          const float4 r0 = r[0];
+          const float2 r1 = *reinterpret_cast<const float2*>(r + 1);
+          const float ax = acc[0], ay = acc[1];
+          acc[0] = r0.w * ax + r1.x * ay;
+          acc[1] = r1.x * ax + r1.y * ay;
+          acc[2] = acc[2] != 0.f ? -acc[2] * __fdividef(1.f, r0.z) : 0.f;
+          acc[3] *= 0.5f;
+          acc[5] *= 0.5f;
+          if (a.v_means2d_sep && k == a.sep_list && (acc[0] != 0.f || acc[1] != 0.f)) {
+            atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tb], acc[0]);
+            atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tb] + 1, acc[1]);
+          }
+        }
+        constexpr int kVec = (6 + D + 3) / 4;     // 16-byte chunks of the gradient record in use
+        if (2 * ph < kVec && (acc[0] != 0.f || acc[1] != 0.f || acc[2] != 0.f || acc[3] != 0.f))
+          red_add_v4(dst, acc[0], acc[1], acc[2], acc[3]);
+        if (2 * ph + 1 < kVec && (acc[4] != 0.f || acc[5] != 0.f || acc[6] != 0.f || acc[7] != 0.f))
+          red_add_v4(dst + 4, acc[4], acc[5], acc[6], acc[7]);
+      }
+      __syncwarp();   // Phase B reads of F / VS are done before the next block overwrites them
+    }
+#else
       if (on) {
         float* dst = sacc + tb * kAccRow + ph * 8;
 #pragma unroll
@@ -858,6 +894,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tid] + 1, s[0].y);
       }
     }
+#endif
   }
 }
 
