@@ -265,9 +265,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
 // loss w.r.t. the pixel's D blended channels (v_c) and alpha (v_a).  Plain path: read from
 // v_out_colors / v_out_alphas.  DEC: VJP of (expected depth, Sandwich decoder, sub-frame mean)
 // evaluated here, with the decoder weight gradients of the whole tile summed into swg[90].
-// sx [12][kBlendThreads + 1] and sg [15][kBlendThreads + 1] (ghpre 0..5 | gpre 6..8 | relu(h) 9..14)
+// sx [12][kProPad] and sg [15][kProPad] (ghpre 0..5 | gpre 6..8 | relu(h) 9..14), 16-byte aligned,
 // are scratch that may alias buffers which are idle until the list walk starts.  Called by all
 // threads of the CTA (contains barriers).
+constexpr int kProPad = kBlendThreads + 4;
 template <int D, bool DEC>
 __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k, int tid, bool inside, int ix, int iy,
                                                    float* sx, float* sg, float* sdec, float* swg,
@@ -297,7 +298,7 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
     // the record / accumulator buffers are idle during the prologue — and 180 threads then sum one
     // product each over half of the tile's pixels.  Live ranges are kept short on purpose: holding
     // the factors in registers spilled ~460 B per thread (4.9 GB of local-memory DRAM writes).
-    constexpr int kPad = kBlendThreads + 1;              // row stride: distinct rows hit distinct banks
+    constexpr int kPad = kProPad;                        // row stride: rows stay 16-byte aligned and start 4 banks apart
     const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
     const float* w1 = sdec;
     const float* w2 = sdec + (DEC ? 72 : 0);
@@ -376,8 +377,11 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
       const float* fa = o < 72 ? sg + (o / 12) * kPad : sg + (6 + (o - 72) / 6) * kPad;
       const float* fb = o < 72 ? sx + (o % 12) * kPad : sg + (9 + (o - 72) % 6) * kPad;
       float acc = 0.f;
-#pragma unroll 8
-      for (int p = p0; p < p0 + kBlendThreads / 2; ++p) acc += fa[p] * fb[p];
+#pragma unroll 4
+      for (int p = p0; p < p0 + kBlendThreads / 2; p += 4) {
+        const float4 x4 = *reinterpret_cast<const float4*>(fa + p), y4 = *reinterpret_cast<const float4*>(fb + p);
+        acc += x4.x * y4.x + x4.y * y4.y + x4.z * y4.z + x4.w * y4.w;
+      }
       if (acc != 0.f) atomicAdd(&swg[o], acc);
     }
   }
@@ -625,7 +629,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 #ifndef MOBGS_BWD_DIRECT_RED
 #define MOBGS_BWD_DIRECT_RED 1
 #endif
-constexpr int kBwdBatch = MOBGS_BWD_DIRECT_RED ? 256 : 128;   // list entries staged per batch (shared-memory budget)
+constexpr int kBwdBatch = MOBGS_BWD_DIRECT_RED ? 192 : 128;   // list entries staged per batch (shared-memory budget)
+constexpr int kRecRow = 20;                    // floats between staged records (16 used): the rows of 8 different
+                                               // entries start 4 banks apart for the per-entry reads of Phase B
+constexpr int kListRow = kBwdBatch + 8;        // bytes between unit lists: 8-byte loads of a warp's two units differ in bank
 constexpr int kBlk = 8;                        // entries per Phase A / Phase B block
 constexpr int kFRow = 36;                      // row stride of the per-warp F / VS matrices (32 pixels + 4: the
                                                // 8 rows a quarter-warp reads in Phase B start 4 banks apart)
@@ -635,16 +642,16 @@ constexpr int kVUnit = 2 * kVHalf + 8;         // second unit of the warp: +16 b
 constexpr int kVWarp = 2 * kVUnit;             //   groups of a warp read four different 16-byte bank groups
 constexpr int kAccRow = 17;                    // accumulator row stride: row t starts at bank 17 t
 constexpr int kAccFloats = MOBGS_BWD_DIRECT_RED ? 0 : kBwdBatch * kAccRow;
-constexpr int kTrScratch = kBwdBatch * kRecFloats + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
-static_assert(kTrScratch >= 27 * (kBlendThreads + 1), "prologue scratch must fit the aliased buffers");
-constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kBwdBatch + 8 * 4 + 16;
+constexpr int kTrScratch = kBwdBatch * kRecRow + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
+static_assert(kTrScratch >= 27 * kProPad, "prologue scratch must fit the aliased buffers");
+constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
 
 template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_tr_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   static_assert(kUL == 16, "transposing backward is written for 4x4-pixel units");
   extern __shared__ __align__(128) float smem[];
-  float* srec = smem;                                            // [kBwdBatch][16]   (TMA destination)
-  float* sacc = srec + kBwdBatch * kRecFloats;                   // [kBwdBatch][kAccRow]
+  float* srec = smem;                                            // [kBwdBatch][kRecRow]   (TMA destination)
+  float* sacc = srec + kBwdBatch * kRecRow;                      // [kBwdBatch][kAccRow]
   float* sF = sacc + kAccFloats;                                 // [8 warps][F | VS][kBlk][kFRow]
   float* sV = smem + kTrScratch;                                 // [8 warps][kVWarp]
   float* sdec = sV + 8 * kVWarp;                                 // [96]
@@ -653,14 +660,14 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   unsigned* smask = reinterpret_cast<unsigned*>(sid + kBwdBatch);   // [kBwdBatch]
   int* warp_max = reinterpret_cast<int*>(smask + kBwdBatch);     // [8]
   uint64_t* sbar = reinterpret_cast<uint64_t*>(warp_max + 8);    // 8-byte aligned: everything before is a multiple of 8 B
-  unsigned char* swl = reinterpret_cast<unsigned char*>(sbar + 1);   // [16 units][kBwdBatch]
+  unsigned char* swl = reinterpret_cast<unsigned char*>(sbar + 1);   // [16 units][kListRow], 8-byte aligned rows
 
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
   const int tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-  const unsigned char* ulist = swl + (tid / kUL) * kBwdBatch;    // this lane's unit's list
-  unsigned char* wl0 = swl + warp * kUPW * kBwdBatch;            // list of the warp's first unit
+  const unsigned char* ulist = swl + (tid / kUL) * kListRow;     // this lane's unit's list
+  unsigned char* wl0 = swl + warp * kUPW * kListRow;             // list of the warp's first unit
   uint32_t bar_phase = 0;
   if (tid == 0) {
     mbar_init(sbar, 1);
@@ -678,7 +685,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   float T_final, v_a, bg_dot = 0.f;
   float v_c[D];
   int last;
-  bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, smem, smem + 12 * (kBlendThreads + 1), sdec, swg,
+  bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, smem, smem + 12 * kProPad, sdec, swg,
                              T_final, last, v_c, v_a);
   if (inside && a.backgrounds) {
     const float* bg = a.backgrounds + (size_t)k * D;
@@ -732,27 +739,29 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     if (tid < bn) {
       const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
       sid[tid] = g;
-      bulk_g2s(srec + tid * kRecFloats, recs + (size_t)g * 4, kRecBytes, sbar);
+      bulk_g2s(srec + tid * kRecRow, recs + (size_t)g * 4, kRecBytes, sbar);
     }
     for (int i = tid; i < kAccFloats; i += kBlendThreads) sacc[i] = 0.f;
     mbar_wait(sbar, bar_phase);
     bar_phase ^= 1;
     if (tid < bn) {
-      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecFloats);
+      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecRow);
       smask[tid] = unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
     }
     __syncthreads();
     // entries above this unit's furthest pixel contribute nothing: they never enter its list
-    const int cnt = build_unit_lists<kBwdBatch>(smask, wl0, warp, lane, max(0, hi - umax), bn);
+    const int cnt = build_unit_lists<kListRow>(smask, wl0, warp, lane, max(0, hi - umax), bn);
     const int cnt_warp = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
     for (int base = 0; base < cnt_warp; base += kBlk) {
       const int nb = min(kBlk, cnt_warp - base);
+      const uint2 tl = *reinterpret_cast<const uint2*>(ulist + base);   // the block's 8 list bytes (stale past cnt)
       // ---- Phase A: lane = pixel.  A unit that is through idles on slot 0 with valid = false.
-#pragma unroll 2
-      for (int i = 0; i < nb; ++i) {
+#pragma unroll
+      for (int i = 0; i < kBlk; ++i) {
+        if (i >= nb) break;
         const bool act = base + i < cnt;
-        const int t = act ? ulist[base + i] : 0;
-        const float4* r = reinterpret_cast<const float4*>(srec + t * kRecFloats);
+        const int t = act ? (int)(((i < 4 ? tl.x : tl.y) >> (8 * (i & 3))) & 0xffu) : 0;
+        const float4* r = reinterpret_cast<const float4*>(srec + t * kRecRow);
         const float4 r0 = r[0], r1 = r[1];
         float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
         if (D > 2) r2 = r[2];
@@ -786,8 +795,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
       const bool on = pj < nb && base + pj < cnt;
       int tb = 0;
       if (on) {
-        tb = ulist[base + pj];
-        const float2 mean = *reinterpret_cast<const float2*>(srec + tb * kRecFloats);
+        tb = (int)(((pj < 4 ? tl.x : tl.y) >> (8 * (pj & 3))) & 0xffu);
+        const float2 mean = *reinterpret_cast<const float2*>(srec + tb * kRecRow);
         const float* fr = Fm + pj * kFRow + hu * 16 + ph * 8;
         const float* sr = VSm + pj * kFRow + hu * 16 + ph * 8;
         const float4 f0 = *reinterpret_cast<const float4*>(fr), f1 = *reinterpret_cast<const float4*>(fr + 4);
@@ -841,7 +850,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         float* dst = v_recs + (size_t)sid[tb] * kRecFloats + ph * 8;
         if (ph == 0) {
           // moments -> gradients: record layout x y opac ca | cb cc c0 c1
-          const float4* r = reinterpret_cast<const float4*>(srec + tb * kRecFloats);
+          const float4* r = reinterpret_cast<const float4*>(srec + tb * kRecRow);
           const float4 r0 = r[0];
           const float2 r1 = *reinterpret_cast<const float2*>(r + 1);
           const float ax = acc[0], ay = acc[1];
@@ -874,7 +883,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     }
     __syncthreads();
     if (tid < bn) {
-      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecFloats);
+      const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecRow);
       const float4 r0 = r[0], r1 = r[1];
       const float* sa = sacc + tid * kAccRow;
       const float ax = sa[0], ay = sa[1], a0 = sa[2];
