@@ -40,6 +40,16 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 constexpr float kNegLog2e = -1.4426950408889634f;
+// The staged conic is rescaled once per entry to (A, B, C) = -log2(e) (a/2, b, c/2), so that the exponent of
+// alpha = opac 2^p is p = dx (A dx + B dy) + C dy^2: five instructions per (pixel, Gaussian) pair instead of eight.
+constexpr float kConicDiag = 0.5f * kNegLog2e, kConicOff = kNegLog2e;
+__device__ __forceinline__ void rescale_conic(float* rec) {   // rec: x y opac ca | cb cc ...
+  rec[3] *= kConicDiag;
+  *reinterpret_cast<float2*>(rec + 4) = make_float2(rec[4] * kConicOff, rec[5] * kConicDiag);
+}
+__device__ __forceinline__ float pair_exponent(const float4& r0, const float4& r1, float dx, float dy) {
+  return dx * (r0.w * dx + r1.x * dy) + (r1.y * dy) * dy;
+}
 
 // Sub-warp units (blend_units.cuh): MOBGS_UNIT_LANES = 32 / 16 / 8 lanes per unit.
 #ifndef MOBGS_UNIT_LANES
@@ -146,7 +156,7 @@ template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   __shared__ __align__(128) float4 srec[kBlendThreads][4];
   __shared__ unsigned smask[kBlendThreads];
-  __shared__ unsigned char swl[kUnits][kBlendThreads];
+  __shared__ __align__(8) unsigned char swl[kUnits][kBlendThreads + 8];   // +8: 8-byte loads of a warp's units differ in bank
   __shared__ __align__(16) float sdec[DEC ? 96 : 4];
   __shared__ __align__(8) uint64_t sbar;
   const int tiles = tiles_x * tiles_y;
@@ -188,7 +198,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
     if (idx < end) bulk_g2s(&srec[tid][0], recs + (size_t)a.sorted_ids[idx] * 4, kRecBytes, &sbar);
     mbar_wait(&sbar, bar_phase);
     bar_phase ^= 1;
-    if (idx < end) smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
+    if (idx < end) {
+      smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
+      rescale_conic(reinterpret_cast<float*>(&srec[tid][0]));
+    }
 #else
     if (idx < end) {
       const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
@@ -197,17 +210,22 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
       smask[tid] = unit_mask(q0, q1, (float)(tx * kTile), (float)(ty * kTile));
+      rescale_conic(reinterpret_cast<float*>(&srec[tid][0]));
     }
 #endif
     __syncthreads();
-    const int cnt = build_unit_lists(smask, wl0, tid >> 5, lane, 0, bn);
-    for (int i = 0; i < cnt && !done; ++i) {
+    const int cnt = build_unit_lists<kBlendThreads + 8>(smask, wl0, tid >> 5, lane, 0, bn);
+    int last_t = -1;
+    // (a rolled loop: unrolling it over 8-byte list loads, as the backward does, was 12 % slower here —
+    // the per-lane continue / break paths multiply)
+    {
+      for (int i = 0; i < cnt && !done; ++i) {
       const int t = ulist[i];
       const float4 r0 = srec[t][0], r1 = srec[t][1];
       const float dx = r0.x - px, dy = r0.y - py;
-      const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-      const float alpha = fminf(kAlphaMax, r0.z * ex2_approx(sigma * kNegLog2e));
-      if (sigma < 0.f || alpha < kAlphaMin) continue;
+      const float pw = pair_exponent(r0, r1, dx, dy);            // = -sigma log2(e)
+      const float alpha = fminf(kAlphaMax, r0.z * ex2_approx(pw));
+      if (pw > 0.f || alpha < kAlphaMin) continue;
       const float next_T = T * (1.f - alpha);
       if (next_T <= kTStop) { done = true; break; }
       const float w = alpha * T;
@@ -227,9 +245,11 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
         if (D > 8) pix[8 % D] += r3.z * w;
         if (D > 9) pix[9 % D] += r3.w * w;
       }
-      last = b0 + t;
+      last_t = t;
       T = next_T;
+      }
     }
+    if (last_t >= 0) last = b0 + last_t;
   }
   if (inside) {
     const size_t p = ((size_t)k * a.height + iy) * a.width + ix;
@@ -747,6 +767,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     if (tid < bn) {
       const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecRow);
       smask[tid] = unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
+      rescale_conic(srec + tid * kRecRow);
     }
     __syncthreads();
     // entries above this unit's furthest pixel contribute nothing: they never enter its list
@@ -767,10 +788,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         if (D > 2) r2 = r[2];
         if (D > 6) r3 = r[3];
         const float dx = r0.x - px, dy = r0.y - py;
-        const float sigma = 0.5f * (r0.w * dx * dx + r1.y * dy * dy) + r1.x * dx * dy;
-        const float vis = ex2_approx(sigma * kNegLog2e);
+        const float pw = pair_exponent(r0, r1, dx, dy);          // = -sigma log2(e)
+        const float vis = ex2_approx(pw);
         const float alpha = fminf(kAlphaMax, r0.z * vis);
-        const bool valid = act && inside && hi - t <= last && sigma >= 0.f && alpha >= kAlphaMin;
+        const bool valid = act && inside && hi - t <= last && pw <= 0.f && alpha >= kAlphaMin;
         // lanes whose pixel does not blend this Gaussian run the same arithmetic with alpha = 0, which
         // leaves T and S unchanged and makes both stored terms exactly zero
         const float al = valid ? alpha : 0.f;
@@ -854,8 +875,9 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
           const float4 r0 = r[0];
           const float2 r1 = *reinterpret_cast<const float2*>(r + 1);
           const float ax = acc[0], ay = acc[1];
-          acc[0] = r0.w * ax + r1.x * ay;
-          acc[1] = r1.x * ax + r1.y * ay;
+          const float ca = r0.w * (1.f / kConicDiag), cb = r1.x * (1.f / kConicOff), cc = r1.y * (1.f / kConicDiag);
+          acc[0] = ca * ax + cb * ay;
+          acc[1] = cb * ax + cc * ay;
           acc[2] = acc[2] != 0.f ? -acc[2] * __fdividef(1.f, r0.z) : 0.f;
           acc[3] *= 0.5f;
           acc[5] *= 0.5f;
@@ -888,7 +910,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
       const float* sa = sacc + tid * kAccRow;
       const float ax = sa[0], ay = sa[1], a0 = sa[2];
       float4 s[4];
-      s[0] = make_float4(r0.w * ax + r1.x * ay, r1.x * ax + r1.y * ay, a0 != 0.f ? -a0 / r0.z : 0.f, 0.5f * sa[3]);
+      const float ca = r0.w * (1.f / kConicDiag), cb = r1.x * (1.f / kConicOff), cc = r1.y * (1.f / kConicDiag);
+      s[0] = make_float4(ca * ax + cb * ay, cb * ax + cc * ay, a0 != 0.f ? -a0 / r0.z : 0.f, 0.5f * sa[3]);
       s[1] = make_float4(sa[4], 0.5f * sa[5], sa[6], sa[7]);
       s[2] = make_float4(sa[8], sa[9], sa[10], sa[11]);
       s[3] = make_float4(sa[12], sa[13], sa[14], sa[15]);
