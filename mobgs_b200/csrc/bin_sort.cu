@@ -206,38 +206,45 @@ __device__ __forceinline__ void radix_pass(const uint64_t* src, uint64_t* dst, i
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* bufA = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* bufB = bufA + kSortSmemCap;
-  int (*warp_hist)[256] = reinterpret_cast<int (*)[256]>(bufB + kSortSmemCap);
-  __shared__ int digit_base[kSortWarps];
-  __shared__ unsigned long long red_or[kSortWarps], red_and[kSortWarps];
-
+// Small segments (n <= kRankSortMax, the common case): all-pairs rank sort out of 6 KB of static shared
+// memory — keys are unique (they embed the Gaussian index), so rank = #{keys smaller} is the final
+// position.  A kernel of its own so that its occupancy is not capped by the radix path's 72 KB buffers.
+__global__ void __launch_bounds__(kSortThreads) tile_rank_sort_kernel(MobgsTileSort a) {
+  __shared__ __align__(16) uint64_t buf[kRankSortMax + 1];
   const int seg = blockIdx.x;
   const int beg = a.tile_offsets[seg];
   int n = a.tile_offsets[seg + 1] - beg;
   if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
-  if (n <= 0) return;
-  uint64_t* gkeys = a.keys + beg;
+  if (n <= 0 || n > kRankSortMax) return;
+  const uint64_t* gkeys = a.keys + beg;
   if (n == 1) {
     if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(gkeys[0] & 0xffffffffu);
     return;
   }
-  if (n <= kRankSortMax) {
-    // small segment (the common case): all-pairs rank sort out of shared memory — keys are unique
-    // (they embed the Gaussian index), so rank = #{keys smaller} is the final position.
-    for (int i = threadIdx.x; i < n; i += kSortThreads) bufA[i] = gkeys[i];
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += kSortThreads) {
-      const uint64_t key = bufA[i];
-      int rank = 0;
+  for (int i = threadIdx.x; i < n; i += kSortThreads) buf[i] = gkeys[i];
+  if (threadIdx.x == 0) buf[n] = ~0ull;          // sentinel: never smaller than a key (pairs are read two at a time)
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kSortThreads) {
+    const uint64_t key = buf[i];
+    int rank = 0;
 #pragma unroll 4
-      for (int j = 0; j < n; ++j) rank += bufA[j] < key;
-      a.sorted_ids[beg + rank] = (int)(key & 0xffffffffu);
+    for (int j = 0; j < n; j += 2) {
+      const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(buf + j);   // one LDS.128 = two keys
+      rank += (kk.x < key) + (kk.y < key);
     }
-    return;
+    a.sorted_ids[beg + rank] = (int)(key & 0xffffffffu);
   }
+}
+
+// Large segments (n > kRankSortMax, rare): LSD radix sort, one CTA per segment at a time.  The grid is a
+// few CTAs per SM; each scans 256 segment sizes at once and sorts the large ones it finds.
+__device__ void radix_sort_segment(const MobgsTileSort& a, int seg, uint64_t* bufA, uint64_t* bufB,
+                                   int (*warp_hist)[256], int* digit_base, unsigned long long* red_or,
+                                   unsigned long long* red_and) {
+  const int beg = a.tile_offsets[seg];
+  int n = a.tile_offsets[seg + 1] - beg;
+  if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
+  uint64_t* gkeys = a.keys + beg;
   const bool in_smem = n <= kSortSmemCap;
   uint64_t* src = in_smem ? bufA : gkeys;
   uint64_t* dst = in_smem ? bufB : a.keys_tmp + beg;
@@ -267,6 +274,34 @@ __global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a
     uint64_t* t = src; src = dst; dst = t;
   }
   for (int i = threadIdx.x; i < n; i += kSortThreads) a.sorted_ids[beg + i] = (int)(src[i] & 0xffffffffu);
+}
+
+__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a, int nt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint64_t* bufA = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* bufB = bufA + kSortSmemCap;
+  int (*warp_hist)[256] = reinterpret_cast<int (*)[256]>(bufB + kSortSmemCap);
+  __shared__ int digit_base[kSortWarps];
+  __shared__ unsigned long long red_or[kSortWarps], red_and[kSortWarps];
+  __shared__ int big[kSortThreads];
+  __shared__ int nbig;
+  for (int c0 = blockIdx.x * kSortThreads; c0 < nt; c0 += gridDim.x * kSortThreads) {
+    if (threadIdx.x == 0) nbig = 0;
+    __syncthreads();
+    const int seg = c0 + threadIdx.x;
+    if (seg < nt) {
+      const int beg = a.tile_offsets[seg];
+      int n = a.tile_offsets[seg + 1] - beg;
+      if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
+      if (n > kRankSortMax) big[atomicAdd(&nbig, 1)] = seg;
+    }
+    __syncthreads();
+    const int nb = nbig;
+    for (int b = 0; b < nb; ++b) {
+      radix_sort_segment(a, big[b], bufA, bufB, warp_hist, digit_base, red_or, red_and);
+      __syncthreads();
+    }
+  }
 }
 
 }  // namespace mobgs
@@ -304,6 +339,14 @@ extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
   tile_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
   const size_t smem = 2 * sizeof(uint64_t) * kSortSmemCap + sizeof(int) * kSortWarps * 256;
   cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  tile_sort_kernel<<<nt, kSortThreads, smem, s>>>(*a);
+  tile_rank_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);
+  static int sort_ctas = 0;           // a few CTAs per SM (the radix buffers allow 3)
+  if (!sort_ctas) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sort_ctas = 3 * sms;
+  }
+  tile_sort_kernel<<<min(sort_ctas, (nt + kSortThreads - 1) / kSortThreads), kSortThreads, smem, s>>>(*a, nt);
   return check_launch("tile_emit_sort");
 }
