@@ -346,19 +346,22 @@ def run_ours(args):
     dom = max(("mobgs_blend_fwd", "mobgs_blend_bwd"), key=lambda n: kernel_ms.get(n, 0.0))
     dom_bytes = bytes_bwd if dom == "mobgs_blend_bwd" else bytes_fwd
     ach = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    try:    # dram__bytes_read+write of one launch from the committed ncu --set full capture
+    traffic = issue = lsu = None
+    try:    # dram bytes / pipe utilisation of one launch from the committed ncu --set full captures
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            prof = json.load(f)
+        traffic = prof.get(args.workload, {}).get(dom)
+        issue = prof.get("issue_slot_utilisation", {}).get(dom)
+        lsu = prof.get("lsu_pipe_utilisation", {}).get(dom)
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "peak_kind": peak_kind,
                 "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes": dom_bytes,
                 "intersections_consumed": ieff, "intersections_listed": itot, "pixels": P_loc,
-                "issue_slot_utilisation": 0.843,
-                "note": "the blend kernels are instruction-issue bound (ncu: 84 % issue slots, 6 % DRAM; "
-                        "profiles/r1_blend_bwd_ncu.txt), not HBM bound; the HBM fraction is reported because "
+                "issue_slot_utilisation": issue, "lsu_pipe_utilisation": lsu,
+                "note": "the blend kernels are bound by instruction issue and the shared-memory (LSU) pipe, not by HBM "
+                        "(ncu figures above from profiles/r1_blend_*_ncu.txt); the HBM fraction is reported because "
                         "BASELINE.json's north_star asks for it. algorithmic_bytes = 132*I_eff + 52*P; since the "
                         "decoder VJP is fused into this kernel it also reads img10/rays/gradients (~100 B/pixel) "
                         "that the byte model does not count"}
