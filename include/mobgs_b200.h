@@ -420,6 +420,34 @@ typedef struct {
 int mobgs_hexplane_features_fwd(const MobgsHexFeat* a, void* stream);
 int mobgs_hexplane_features_bwd(const MobgsHexFeat* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f4: multi-tensor Adam step (replaces the two `torch.optim.Adam(l, lr=0.0, eps=1e-15).step()` calls
+ * of train.py:796-800 over the parameter groups of scene/gaussian_model.py:598-641; amsgrad=False,
+ * weight_decay=0).  One launch updates up to MOBGS_ADAM_MAX_TENSORS fp32 tensors in place:
+ *   m = m + (g - m) one_minus_beta1;  v = v beta2 + one_minus_beta2 g g;
+ *   p -= step_size[t] * m / (sqrt(v) / bc2_sqrt[t] + eps)
+ * with step_size[t] = lr_t / (1 - beta1^step_t), bc2_sqrt[t] = sqrt(1 - beta2^step_t) computed by the
+ * caller.  chunk_begin[t] = sum_{u<t} ceil(numel[u] / mobgs_adam_chunk_elems()), chunk_begin[n_tensors]
+ * = total (the kernel's work list).  Tensors must be contiguous; 16-byte alignment enables the
+ * vector path. */
+#define MOBGS_ADAM_MAX_TENSORS 64
+typedef struct {
+  int32_t n_tensors;
+  float beta1, beta2, eps;
+  float one_minus_beta1, one_minus_beta2;   /* rounded from double by the caller, as torch passes them */
+  int32_t reserved_;
+  float* param[MOBGS_ADAM_MAX_TENSORS];
+  const float* grad[MOBGS_ADAM_MAX_TENSORS];
+  float* exp_avg[MOBGS_ADAM_MAX_TENSORS];
+  float* exp_avg_sq[MOBGS_ADAM_MAX_TENSORS];
+  int64_t numel[MOBGS_ADAM_MAX_TENSORS];
+  float step_size[MOBGS_ADAM_MAX_TENSORS];
+  float bc2_sqrt[MOBGS_ADAM_MAX_TENSORS];
+  int32_t chunk_begin[MOBGS_ADAM_MAX_TENSORS + 1];
+} MobgsAdam;
+int mobgs_adam_step(const MobgsAdam* a, void* stream);
+int mobgs_adam_chunk_elems(void);
+
 #ifdef __cplusplus
 }
 #endif

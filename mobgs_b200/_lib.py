@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -205,6 +205,20 @@ class HexFeat(C.Structure):
                 ("g_planes", C.c_void_p * 24), ("g_pts", C.c_void_p), ("g_times", C.c_void_p)]
 
 
+ADAM_MAX_TENSORS = 64
+
+
+class Adam(C.Structure):
+    _fields_ = [("n_tensors", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("one_minus_beta1", C.c_float), ("one_minus_beta2", C.c_float), ("reserved_", C.c_int32),
+                ("param", C.c_void_p * ADAM_MAX_TENSORS), ("grad", C.c_void_p * ADAM_MAX_TENSORS),
+                ("exp_avg", C.c_void_p * ADAM_MAX_TENSORS), ("exp_avg_sq", C.c_void_p * ADAM_MAX_TENSORS),
+                ("numel", C.c_int64 * ADAM_MAX_TENSORS), ("step_size", C.c_float * ADAM_MAX_TENSORS),
+                ("bc2_sqrt", C.c_float * ADAM_MAX_TENSORS), ("chunk_begin", C.c_int32 * (ADAM_MAX_TENSORS + 1))]
+
+
+EXTRA_STRUCTS = {"MobgsAdam": Adam}
+
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
 ENTRY_POINTS = {
@@ -226,6 +240,8 @@ ENTRY_POINTS = {
     "mobgs_flow_records_bwd": FlowRecBwd,
     "mobgs_hexplane_features_fwd": HexFeat,
     "mobgs_hexplane_features_bwd": HexFeat,
+    "mobgs_adam_step": Adam,
+    "mobgs_adam_chunk_elems": "int",
 }
 
 _lib = None
@@ -257,6 +273,9 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)   # AttributeError => symbol missing: fail loudly
             if struct is None:
                 fn.restype = C.c_char_p
+                fn.argtypes = []
+            elif struct == "int":
+                fn.restype = C.c_int
                 fn.argtypes = []
             else:
                 fn.restype = C.c_int

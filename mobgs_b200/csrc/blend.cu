@@ -39,6 +39,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float rcp_approx(float x) {   // one MUFU.RCP (|rel err| <= 2^-22); x in [1e-3, 1] at its call sites
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr float kNegLog2e = -1.4426950408889634f;
 // The staged conic is rescaled once per entry to (A, B, C) = -log2(e) (a/2, b, c/2), so that the exponent of
 // alpha = opac 2^p is p = dx (A dx + B dy) + C dy^2: five instructions per (pixel, Gaussian) pair instead of eight.
@@ -795,7 +800,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         // lanes whose pixel does not blend this Gaussian run the same arithmetic with alpha = 0, which
         // leaves T and S unchanged and makes both stored terms exactly zero
         const float al = valid ? alpha : 0.f;
-        const float ra = __fdividef(1.f, 1.f - al);
+        const float ra = rcp_approx(1.f - al);
         T *= ra;
         const float fac = al * T;
         float d = 0.f;
