@@ -448,6 +448,42 @@ typedef struct {
 int mobgs_adam_step(const MobgsAdam* a, void* stream);
 int mobgs_adam_chunk_elems(void);
 
+/* ------------------------------------------------------------------------------------------
+ * f2: photometric loss of the training step, forward + backward fused (train.py:621-628):
+ *   photo_loss = l1_loss(image, gt) + lambda_dssim (1 - ssim(image, gt))
+ * with utils/loss_utils.py:233-239 l1_loss (mask=None) and :351-382 ssim (11x11 Gaussian window, sigma
+ * 1.5, zero padding, per channel, mean over everything).  img / gt: [planes, H, W] fp32 contiguous
+ * (planes = batch x channels).  window: the 11 normalised 1-D taps (the 2-D window is their outer product).
+ *   fwd: sums[0] = sum |x - y|, sums[1] = sum ssim_map (double, zeroed inside the call); d_mu1 / d_x2 /
+ *        d_xy [planes,H,W] receive the per-pixel partials of the SSIM map (all NULL = forward only).
+ *   bwd: v_img = v_loss[0] * ( scale_l1 sign(x - y) + scale_ssim * dSSIMsum/dx ), v_loss a device scalar
+ *        (NULL = 1); the caller passes scale_l1 = 1/numel, scale_ssim = -lambda_dssim/numel. */
+typedef struct {
+  int32_t planes, H, W;
+  const float* img;
+  const float* gt;
+  float window[11];
+  double* sums;      /* [2] */
+  float* d_mu1;
+  float* d_x2;
+  float* d_xy;
+} MobgsPhotoLossFwd;
+int mobgs_photo_loss_fwd(const MobgsPhotoLossFwd* a, void* stream);
+
+typedef struct {
+  int32_t planes, H, W;
+  const float* img;
+  const float* gt;
+  float window[11];
+  const float* d_mu1;
+  const float* d_x2;
+  const float* d_xy;
+  const float* v_loss;   /* device scalar or NULL */
+  float scale_l1, scale_ssim;
+  float* v_img;          /* [planes,H,W] written */
+} MobgsPhotoLossBwd;
+int mobgs_photo_loss_bwd(const MobgsPhotoLossBwd* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -217,7 +217,19 @@ class Adam(C.Structure):
                 ("bc2_sqrt", C.c_float * ADAM_MAX_TENSORS), ("chunk_begin", C.c_int32 * (ADAM_MAX_TENSORS + 1))]
 
 
-EXTRA_STRUCTS = {"MobgsAdam": Adam}
+class PhotoLossFwd(C.Structure):
+    _fields_ = [("planes", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("img", C.c_void_p), ("gt", C.c_void_p),
+                ("window", C.c_float * 11), ("sums", C.c_void_p), ("d_mu1", C.c_void_p), ("d_x2", C.c_void_p),
+                ("d_xy", C.c_void_p)]
+
+
+class PhotoLossBwd(C.Structure):
+    _fields_ = [("planes", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("img", C.c_void_p), ("gt", C.c_void_p),
+                ("window", C.c_float * 11), ("d_mu1", C.c_void_p), ("d_x2", C.c_void_p), ("d_xy", C.c_void_p),
+                ("v_loss", C.c_void_p), ("scale_l1", C.c_float), ("scale_ssim", C.c_float), ("v_img", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -241,6 +253,8 @@ ENTRY_POINTS = {
     "mobgs_hexplane_features_fwd": HexFeat,
     "mobgs_hexplane_features_bwd": HexFeat,
     "mobgs_adam_step": Adam,
+    "mobgs_photo_loss_fwd": PhotoLossFwd,
+    "mobgs_photo_loss_bwd": PhotoLossBwd,
     "mobgs_adam_chunk_elems": "int",
 }
 

@@ -1,0 +1,105 @@
+"""Fused photometric loss with the reference's function names.
+
+    photo_loss = l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))          train.py:621-628
+
+`l1_loss` / `ssim` have the signatures of utils/loss_utils.py:233 / :351 for the arguments train.py
+uses (mask=None, window_size=11, size_average=True); `photo_loss` is the fused form of train.py:621-628
+— one forward and one backward kernel for both terms (INTEGRATION.md shows the two-line edit).
+Gradients flow to the first argument only (the ground-truth image never requires grad in the
+reference).  CUDA fp32 only; there is no fallback path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _window11() -> np.ndarray:
+    """utils/loss_utils.py:338-341 gaussian(11, 1.5): float32 taps, normalised in float32."""
+    g = torch.tensor([math.exp(-(x - 11 // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(11)], dtype=torch.float32)
+    return (g / g.sum()).numpy()
+
+
+_WINDOW = _window11()
+
+
+def _check(img, gt):
+    if not (img.is_cuda and gt.is_cuda and img.dtype == torch.float32 and gt.dtype == torch.float32):
+        raise RuntimeError("mobgs_b200.losses needs CUDA fp32 tensors (there is no CPU fallback)")
+    if img.shape != gt.shape or img.dim() < 2:
+        raise RuntimeError(f"shape mismatch {tuple(img.shape)} vs {tuple(gt.shape)}")
+
+
+class _PhotoLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, gt, lambda_dssim, want):
+        _check(img, gt)
+        img_c, gt_c = img.contiguous(), gt.contiguous()
+        H, W = img_c.shape[-2:]
+        planes = img_c.numel() // (H * W)
+        need_grad = img.requires_grad
+        sums = torch.empty(2, dtype=torch.float64, device=img.device)
+        a = _lib.PhotoLossFwd()
+        a.planes, a.H, a.W = planes, H, W
+        a.img, a.gt, a.sums = img_c.data_ptr(), gt_c.data_ptr(), sums.data_ptr()
+        for i in range(11):
+            a.window[i] = float(_WINDOW[i])
+        maps = None
+        if need_grad:
+            maps = torch.empty(3, planes, H, W, device=img.device)
+            a.d_mu1, a.d_x2, a.d_xy = maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr()
+        _lib.call("mobgs_photo_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        n = img_c.numel()
+        l1 = (sums[0] / n).float()
+        ss = (sums[1] / n).float()
+        ctx.save_for_backward(img_c, gt_c, maps)
+        ctx.lam, ctx.want, ctx.shape = float(lambda_dssim), want, img.shape
+        if want == "l1":
+            return l1
+        if want == "ssim":
+            return ss
+        return l1 + lambda_dssim * (1.0 - ss)
+
+    @staticmethod
+    def backward(ctx, g):
+        img_c, gt_c, maps = ctx.saved_tensors
+        H, W = img_c.shape[-2:]
+        planes = img_c.numel() // (H * W)
+        n = img_c.numel()
+        g = g.contiguous().float()
+        v = torch.empty_like(img_c)
+        a = _lib.PhotoLossBwd()
+        a.planes, a.H, a.W = planes, H, W
+        a.img, a.gt = img_c.data_ptr(), gt_c.data_ptr()
+        for i in range(11):
+            a.window[i] = float(_WINDOW[i])
+        a.d_mu1, a.d_x2, a.d_xy = maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr()
+        a.v_loss = g.data_ptr()
+        a.scale_l1 = {"l1": 1.0 / n, "ssim": 0.0}.get(ctx.want, 1.0 / n)
+        a.scale_ssim = {"l1": 0.0, "ssim": 1.0 / n}.get(ctx.want, -ctx.lam / n)
+        a.v_img = v.data_ptr()
+        _lib.call("mobgs_photo_loss_bwd", a, torch.cuda.current_stream().cuda_stream)
+        return v.view(ctx.shape), None, None, None
+
+
+def photo_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float) -> torch.Tensor:
+    """train.py:621-628: `l1_loss(image, gt) + lambda_dssim * (1.0 - ssim(image, gt))` in two launches."""
+    return _PhotoLoss.apply(image, gt, lambda_dssim, "photo")
+
+
+def l1_loss(network_output: torch.Tensor, gt: torch.Tensor, mask=None) -> torch.Tensor:
+    """utils/loss_utils.py:233-239 with mask=None (the photometric use, train.py:621)."""
+    if mask is not None:
+        raise RuntimeError("mobgs_b200.losses.l1_loss implements the mask=None form only")
+    return _PhotoLoss.apply(network_output, gt, 0.0, "l1")
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True) -> torch.Tensor:
+    """utils/loss_utils.py:351-382 with the defaults train.py:626 uses."""
+    if window_size != 11 or not size_average:
+        raise RuntimeError("mobgs_b200.losses.ssim implements window_size=11, size_average=True only")
+    return _PhotoLoss.apply(img1, img2, 0.0, "ssim")

@@ -1,0 +1,44 @@
+"""ORACLE — test infrastructure only (tests/, smoke(), bench cpu_baseline may import it; the product never does).
+
+CPU restatement of the photometric loss of the training step:
+
+    l1_loss(network_output, gt)            utils/loss_utils.py:233-239 (mask=None branch)
+    ssim(img1, img2)                       utils/loss_utils.py:338-382 (gaussian / create_window / _ssim)
+    photo_loss = Ll1 + lambda_dssim * (1 - ssim)      train.py:621-628
+
+PINNED: tests/golden/photo_loss.npz is produced by tests/golden/make_golden.py, which imports the
+reference's own utils/loss_utils.py (CPU, fp32) and stores inputs, loss values and autograd gradients;
+tests/test_oracle.py::test_photo_loss_oracle_matches_reference_golden holds this file to them.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def gaussian_window(window_size: int = 11, sigma: float = 1.5) -> torch.Tensor:
+    g = torch.tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * sigma ** 2)) for x in range(window_size)])
+    return g / g.sum()
+
+
+def l1_loss(x, y):
+    return (x - y).abs().mean()
+
+
+def ssim(img1, img2, window_size: int = 11):
+    C = img1.size(-3)
+    w1 = gaussian_window(window_size).to(img1.device, img1.dtype).unsqueeze(1)   # (loss_utils.py:355-357)
+    window = (w1 @ w1.t()).unsqueeze(0).unsqueeze(0).expand(C, 1, window_size, window_size).contiguous()
+    pad = window_size // 2
+    conv = lambda t: F.conv2d(t, window, padding=pad, groups=C)
+    mu1, mu2 = conv(img1), conv(img2)
+    mu1_sq, mu2_sq, mu12 = mu1 * mu1, mu2 * mu2, mu1 * mu2
+    s1 = conv(img1 * img1) - mu1_sq
+    s2 = conv(img2 * img2) - mu2_sq
+    s12 = conv(img1 * img2) - mu12
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    return (((2 * mu12 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))).mean()
+
+
+def photo_loss(image, gt, lambda_dssim: float):
+    return l1_loss(image, gt) + lambda_dssim * (1.0 - ssim(image, gt))

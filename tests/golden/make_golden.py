@@ -172,8 +172,36 @@ def make_hexplane_golden(out_dir):
     print("wrote hexplane", {k: v.shape for k, v in blob.items() if not k.startswith(("sd::", "pgrad::"))})
 
 
+def make_photo_loss_golden(out_dir):
+    """photo_loss.npz: the reference's own utils/loss_utils.py l1_loss + ssim (train.py:621-628) on CPU fp32:
+    a [2,3,45,70] batch (not a multiple of the 16-px tile, like 288 = 18 x 16 but 70 != k x 16) with
+    smooth + noisy content, plus a tiny [1,3,7,9] case smaller than the 11x11 window."""
+    import utils.loss_utils as L          # the reference module, unmodified
+    g = torch.Generator().manual_seed(11)
+    blob = {}
+    for tag, shape in (("a", (2, 3, 45, 70)), ("b", (1, 3, 7, 9))):
+        B, C, H, W = shape
+        yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+        base = torch.stack([0.5 + 0.4 * torch.sin(6 * xx + c) * torch.cos(4 * yy) for c in range(C)])[None].expand(B, -1, -1, -1)
+        gt = (base + 0.05 * torch.randn(shape, generator=g)).clamp(0, 1).contiguous()
+        img = (gt + 0.1 * torch.randn(shape, generator=g)).clamp(0, 1).contiguous().requires_grad_(True)
+        lam = 0.2
+        l1 = L.l1_loss(img, gt)
+        ss = L.ssim(img, gt)
+        loss = l1 + lam * (1.0 - ss)
+        loss.backward()
+        blob.update({f"{tag}_img": _np(img), f"{tag}_gt": _np(gt), f"{tag}_l1": _np(l1), f"{tag}_ssim": _np(ss),
+                     f"{tag}_loss": _np(loss), f"{tag}_grad": _np(img.grad), f"{tag}_lambda": np.float32(lam)})
+    np.savez_compressed(os.path.join(out_dir, "photo_loss.npz"), **blob)
+    print("wrote photo_loss", {k: getattr(v, "shape", None) for k, v in blob.items()})
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
+    if "--only-loss" in sys.argv:
+        make_photo_loss_golden(out)
+        sys.exit(0)
     make_render_goldens(out)
     make_hexplane_golden(out)
+    make_photo_loss_golden(out)
