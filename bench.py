@@ -160,26 +160,11 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-_LOCAL_DIRS = {}
-
-
 def build_rays(viewmats, intr, W, H):
-    """Camera.cam_ray for K cameras on the device (scene/cameras.py:132-146): [K,6,H,W].  The
-    per-pixel camera-space directions depend only on the intrinsics and are cached."""
-    import torch
-    dev = viewmats.device
-    key = (W, H, intr.fx, intr.fy, intr.cx, intr.cy, dev)
-    if key not in _LOCAL_DIRS:
-        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev) + 0.5,
-                                torch.arange(W, dtype=torch.float32, device=dev) + 0.5, indexing="ij")
-        d = torch.stack([(xs - intr.cx) / intr.fx, (ys - intr.cy) / intr.fy, torch.ones_like(xs)], dim=0)
-        _LOCAL_DIRS[key] = (d / d.norm(dim=0, keepdim=True)).reshape(3, H * W)
-    c2w = torch.inverse(viewmats)
-    K = viewmats.shape[0]
-    rays = torch.empty(K, 6, H * W, device=dev)
-    rays[:, :3] = c2w[:, :3, 3, None]
-    torch.matmul(c2w[:, :3, :3], _LOCAL_DIRS[key], out=rays[:, 3:])
-    return rays.reshape(K, 6, H, W)
+    """Camera.cam_ray for the K sub-frame cameras on the device (scene/cameras.py:132-146): [K,6,H,W],
+    one mobgs_camera_rays_fwd launch instead of K meshgrid + matmul chains."""
+    from mobgs_b200.cameras import camera_rays_from_w2c
+    return camera_rays_from_w2c(viewmats, intr.fx, intr.fy, intr.cx, intr.cy, W, H)
 
 
 def run_ours(args):

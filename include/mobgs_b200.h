@@ -484,6 +484,26 @@ typedef struct {
 } MobgsPhotoLossBwd;
 int mobgs_photo_loss_bwd(const MobgsPhotoLossBwd* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f3: Camera.cam_ray of K cameras (scene/cameras.py:132-146, :244-284): per pixel p = (x, y)
+ *   l = normalise(((x + 0.5 - ppx) / sfx, (y + 0.5 - ppy) / sfy, 1)),  d = normalise(rot[k] l)
+ *   rays[k] = [centre[k] broadcast (3 planes) | d (3 planes)]            rays [K,6,H,W]
+ * rot [K,3,3] = camera-to-world rotation (Camera.R), centre [K,3] = camera centre, (ppx, ppy, sfx, sfy) =
+ * principal point and scale factors of the camera metadata (dycheck_geometry/camera.py).
+ *   bwd: v_rays [K,6,H,W] -> v_rot [K,3,3], v_centre [K,3] (zeroed inside the call). */
+typedef struct {
+  int32_t K, H, W;
+  float ppx, ppy, sfx, sfy;
+  const float* rot;
+  const float* centre;
+  float* rays;            /* fwd out */
+  const float* v_rays;    /* bwd in  */
+  float* v_rot;           /* bwd out */
+  float* v_centre;        /* bwd out */
+} MobgsCameraRays;
+int mobgs_camera_rays_fwd(const MobgsCameraRays* a, void* stream);
+int mobgs_camera_rays_bwd(const MobgsCameraRays* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

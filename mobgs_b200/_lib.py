@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -229,7 +229,13 @@ class PhotoLossBwd(C.Structure):
                 ("v_loss", C.c_void_p), ("scale_l1", C.c_float), ("scale_ssim", C.c_float), ("v_img", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+class CameraRays(C.Structure):
+    _fields_ = [("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ppx", C.c_float), ("ppy", C.c_float),
+                ("sfx", C.c_float), ("sfy", C.c_float), ("rot", C.c_void_p), ("centre", C.c_void_p),
+                ("rays", C.c_void_p), ("v_rays", C.c_void_p), ("v_rot", C.c_void_p), ("v_centre", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -255,6 +261,8 @@ ENTRY_POINTS = {
     "mobgs_adam_step": Adam,
     "mobgs_photo_loss_fwd": PhotoLossFwd,
     "mobgs_photo_loss_bwd": PhotoLossBwd,
+    "mobgs_camera_rays_fwd": CameraRays,
+    "mobgs_camera_rays_bwd": CameraRays,
     "mobgs_adam_chunk_elems": "int",
 }
 

@@ -253,3 +253,23 @@ def get_flow_static_ref(source_camera, target_camera, splat_camera, stat_pc, dyn
 # ----------------------------------------------------------------------------
 def blur_mean(images):
     return torch.mean(torch.stack(list(images), dim=0), dim=0) + 1e-10
+
+
+def camera_rays_ref(rot, centre, ppx, ppy, sfx, sfy, width, height):
+    """Camera.cam_ray for K cameras: scene/cameras.py:140-146 with get_pixels_torch :244-253,
+    pixels_to_local_viewdirs_torch :255-266 and pixels_to_viewdirs_torch :268-284.
+    rot [K,3,3] = Camera.R (camera-to-world), centre [K,3] -> [K,6,H,W].
+    Pinned by tests/golden/camera_rays.npz (the reference's own methods, tests/golden/make_golden.py)."""
+    xx, yy = torch.meshgrid(torch.arange(width, dtype=torch.float32), torch.arange(height, dtype=torch.float32), indexing="xy")
+    pixels = torch.stack([xx, yy], dim=-1) + 0.5
+    y = (pixels[..., 1] - ppy) / sfy
+    x = (pixels[..., 0] - ppx) / sfx
+    local = torch.stack([x, y, torch.ones_like(x)], dim=-1)
+    local = (local / torch.norm(local, dim=-1, keepdim=True)).to(rot.dtype)
+    out = []
+    for k in range(rot.shape[0]):
+        v = torch.matmul(rot[k], local.reshape(-1, 3)[..., None])[..., 0]
+        v = (v / torch.norm(v, dim=-1, keepdim=True)).view(height, width, 3)
+        origin, _ = torch.broadcast_tensors(centre[k], v)
+        out.append(torch.cat((origin, v), dim=-1).permute(2, 0, 1))
+    return torch.stack(out)

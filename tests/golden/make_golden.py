@@ -196,12 +196,49 @@ def make_photo_loss_golden(out_dir):
     print("wrote photo_loss", {k: getattr(v, "shape", None) for k, v in blob.items()})
 
 
+def make_camera_rays_golden(out_dir):
+    """camera_rays.npz: cam_ray of K = 3 cameras through the reference's own scene/cameras.py methods
+    (get_pixels_torch :244-253, pixels_to_local_viewdirs_torch :255-266, pixels_to_viewdirs_torch :268-284,
+    executed unmodified on a stub `self`) and the four lines of Camera.__init__ :140-146 that assemble the
+    tensor, plus the gradients of a weighted sum w.r.t. R and the camera centre."""
+    from types import SimpleNamespace as NS
+    from scene.cameras import Camera          # the reference class, unmodified
+    W, H, K = 37, 21, 3
+    g = torch.Generator().manual_seed(3)
+    meta = NS(principal_point_x=W / 2 + 0.7, principal_point_y=H / 2 - 0.4, scale_factor_x=31.0, scale_factor_y=29.5)
+    rots, cens, rays, g_rot, g_cen = [], [], [], [], []
+    wgt = torch.randn(K, 6, H, W, generator=g)
+    for k in range(K):
+        Q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+        Q = (Q * (1.0 + 0.05 * k)).requires_grad_(True)          # not exactly orthonormal: the re-normalisation matters
+        c = torch.randn(3, generator=g).requires_grad_(True)
+        stub = NS(metadata=meta, R=Q, data_device="cpu")
+        stub.pixels_to_local_viewdirs_torch = lambda px, stub=stub: Camera.pixels_to_local_viewdirs_torch(stub, px)
+        pixels = Camera.get_pixels_torch(stub, W, H, use_center=True)
+        viewdirs = Camera.pixels_to_viewdirs_torch(stub, pixels)
+        cam_origin, _ = torch.broadcast_tensors(c, viewdirs)                  # cameras.py:142
+        cam_ray = torch.cat((cam_origin, viewdirs), dim=-1)                   # :143
+        cam_ray = cam_ray.permute(2, 0, 1).unsqueeze(0)                       # :144
+        (cam_ray[0] * wgt[k]).sum().backward()
+        rots.append(_np(Q)); cens.append(_np(c)); rays.append(_np(cam_ray[0]))
+        g_rot.append(_np(Q.grad)); g_cen.append(_np(c.grad))
+    blob = {"rot": np.stack(rots), "centre": np.stack(cens), "rays": np.stack(rays), "weight": _np(wgt),
+            "g_rot": np.stack(g_rot), "g_centre": np.stack(g_cen),
+            "geom": np.array([meta.principal_point_x, meta.principal_point_y, meta.scale_factor_x, meta.scale_factor_y, W, H], np.float64)}
+    np.savez_compressed(os.path.join(out_dir, "camera_rays.npz"), **blob)
+    print("wrote camera_rays", {k: v.shape for k, v in blob.items()})
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     if "--only-loss" in sys.argv:
         make_photo_loss_golden(out)
         sys.exit(0)
+    if "--only-rays" in sys.argv:
+        make_camera_rays_golden(out)
+        sys.exit(0)
     make_render_goldens(out)
     make_hexplane_golden(out)
     make_photo_loss_golden(out)
+    make_camera_rays_golden(out)
