@@ -266,9 +266,9 @@ def run_ours(args):
                                           and p is not stat._omega and p is not stat._features_t
                                           and p is not stat._trbf_center and p is not dyn._trbf_center
                                           and p is not dyn._xyz and all(p is not q for q in stat.rgbdecoder.parameters())]
-                stats["fg"] = FlatGradients(stats["fg_params"])
+                stats["fg"] = FlatGradients(stats["fg_params"], inplace_shared=not shard_sub)
             stats["fg"].reduce()
-            stats["allreduce_bytes"] = stats["fg"].flat.numel() * 4
+            stats["allreduce_bytes"] = stats["fg"].last_collective_elems * 4
         view.grad = None
         stats["out"] = out
         if not resident:

@@ -32,7 +32,9 @@ __device__ __forceinline__ TileRect tile_rect(float mx, float my, int radius, in
 }
 
 // Smallest sigma = 0.5(a dx^2 + c dy^2) + b dx dy over the rectangle of pixel centres of a tile.
-__device__ __forceinline__ float min_sigma_rect(float mx, float my, float a, float b, float c,
+// nb_c = -b / c and nb_a = -b / a are computed once per Gaussian (approximate reciprocals: their error is
+// far inside the +0.01 margin on tau).
+__device__ __forceinline__ float min_sigma_rect(float mx, float my, float a, float b, float c, float nb_c, float nb_a,
                                                 float xlo, float xhi, float ylo, float yhi) {
   const float dxl = xlo - mx, dxh = xhi - mx, dyl = ylo - my, dyh = yhi - my;
   if (dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f) return 0.f;
@@ -41,13 +43,13 @@ __device__ __forceinline__ float min_sigma_rect(float mx, float my, float a, flo
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const float dx = e ? dxh : dxl;
-    const float dy = fminf(dyh, fmaxf(dyl, -b * dx / c));
+    const float dy = fminf(dyh, fmaxf(dyl, nb_c * dx));
     best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
   }
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const float dy = e ? dyh : dyl;
-    const float dx = fminf(dxh, fmaxf(dxl, -b * dy / a));
+    const float dx = fminf(dxh, fmaxf(dxl, nb_a * dy));
     best = fminf(best, 0.5f * (a * dx * dx + c * dy * dy) + b * dx * dy);
   }
   return best;
@@ -67,8 +69,10 @@ template <typename F>
 __device__ __forceinline__ void for_each_tile(const GaussGeom& g, int radius, int width, int height,
                                               int tiles_x, int tiles_y, int tight, F f) {
   const TileRect r = tile_rect(g.mx, g.my, radius, tiles_x, tiles_y);
-  float tau = 0.f;
+  float tau = 0.f, nb_c = 0.f, nb_a = 0.f;
   if (tight) {
+    nb_c = -g.cb * __fdividef(1.f, g.cc);
+    nb_a = -g.cb * __fdividef(1.f, g.ca);
     // a pixel contributes iff opac * exp(-sigma) >= 1/255  <=>  sigma <= log(255 opac)
     tau = __logf(255.f * g.opac) + 0.01f;   // +0.01: safety margin for fp rounding
     if (!(tau >= 0.f)) return;
@@ -79,7 +83,7 @@ __device__ __forceinline__ void for_each_tile(const GaussGeom& g, int radius, in
         const float xlo = tx * kTile + 0.5f, ylo = ty * kTile + 0.5f;
         const float xhi = fminf((float)(tx * kTile + kTile), (float)width) - 0.5f;
         const float yhi = fminf((float)(ty * kTile + kTile), (float)height) - 0.5f;
-        if (min_sigma_rect(g.mx, g.my, g.ca, g.cb, g.cc, xlo, xhi, ylo, yhi) > tau) continue;
+        if (min_sigma_rect(g.mx, g.my, g.ca, g.cb, g.cc, nb_c, nb_a, xlo, xhi, ylo, yhi) > tau) continue;
       }
       f(ty * tiles_x + tx);
     }

@@ -40,7 +40,12 @@ def shard_subframes(n_views: int, K: int, rank: int, world: int) -> List[Tuple[i
 class FlatGradients:
     """Flat fp32 buffer over the gradients of a fixed parameter list; `.reduce()` = one collective."""
 
-    def __init__(self, params: Sequence[torch.Tensor]):
+    def __init__(self, params: Sequence[torch.Tensor], inplace_shared: bool = False):
+        """inplace_shared: reduce gradients that share one storage in place (see shared_storages).  Only
+        valid when every rank builds its gradients through the same autograd graph (view sharding), so
+        that all ranks find the same shared buffers; with sub-frame sharding idle ranks have no gradients
+        and every rank must take the packed path."""
+        self.inplace_shared = inplace_shared
         self.params = list(params)
         self.sizes = [p.numel() for p in self.params]
         self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
@@ -65,13 +70,66 @@ class FlatGradients:
                 p.grad.copy_(g)
             off += n
 
+    def shared_storages(self):
+        """Gradients that already live in one flat buffer (fused.synth_project's backward returns views
+        into a single allocation, which autograd adopts as `.grad`): [(alias over the whole storage,
+        parameter indices)] for every storage shared by more than one gradient — such a buffer is reduced
+        in place, without pack / unpack.  Deterministic across ranks (order of first appearance)."""
+        groups = {}
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None or g.dtype != torch.float32 or not g.is_contiguous():
+                continue
+            groups.setdefault(g.untyped_storage().data_ptr(), []).append(i)
+        out = []
+        for idx in groups.values():
+            if len(idx) < 2:
+                continue
+            g0 = self.params[idx[0]].grad
+            st = g0.untyped_storage()
+            alias = torch.empty(0, dtype=torch.float32, device=g0.device).set_(st, 0, (st.nbytes() // 4,))
+            out.append((alias, idx))
+        return out
+
     def reduce(self, group=None, average: bool = False) -> torch.Tensor:
-        self.pack()
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.flat, group=group)
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        shared = self.shared_storages() if self.inplace_shared else []
+        covered = {i for _, idx in shared for i in idx}
+        self.last_collective_elems = 0
+        for alias, _ in shared:                      # in place: these gradients need no copy at all
+            if multi:
+                dist.all_reduce(alias, group=group)
+                if average:
+                    alias.div_(dist.get_world_size(group))
+            self.last_collective_elems += alias.numel()
+        if len(covered) == len(self.params):
+            return self.flat
+        # everything else goes through the packed buffer (segments of covered parameters stay zero)
+        off = 0
+        for i, (p, n) in enumerate(zip(self.params, self.sizes)):
+            if i not in covered:
+                if p.grad is not None:
+                    self.flat[off:off + n].copy_(p.grad.reshape(-1))
+                else:
+                    self.flat[off:off + n].zero_()
+            off += n
+        rest = [i for i in range(len(self.params)) if i not in covered]
+        lo = sum(self.sizes[:rest[0]])
+        hi = sum(self.sizes[:rest[-1] + 1])
+        if multi:
+            dist.all_reduce(self.flat[lo:hi], group=group)
             if average:
-                self.flat.div_(dist.get_world_size(group))
-        self.unpack()
+                self.flat[lo:hi].div_(dist.get_world_size(group))
+        self.last_collective_elems += hi - lo
+        off = 0
+        for i, (p, n) in enumerate(zip(self.params, self.sizes)):
+            if i not in covered:
+                g = self.flat[off:off + n].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+            off += n
         return self.flat
 
 

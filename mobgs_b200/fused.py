@@ -73,9 +73,18 @@ class _SynthProject(torch.autograd.Function):
         K = viewmats.shape[0]
         dev = viewmats.device
         g_rec = _f32c(g_rec)
-        v_st = [torch.empty_like(t) for t in st]
-        v_dy = [torch.zeros_like(dy[0])] + [torch.empty_like(t) for t in dy[1:]]
-        v_dy[7].zero_()     # trbf_center: dt is detached in the reference (render():102) -> no gradient
+        # All Gaussian-parameter gradients are views into ONE zeroed flat buffer (segments padded to 16 B):
+        # autograd adopts the views as `.grad`, so a data-parallel caller all-reduces the buffer in place
+        # (dist.FlatGradients) instead of packing / unpacking 12 tensors.  control_xyz needs the zeros
+        # (accumulated in place); trbf_center gets no gradient: dt is detached in the reference (render():102).
+        outs = list(st) + list(dy[:7])
+        starts, tot = [], 0
+        for t in outs:
+            starts.append(tot)
+            tot += (t.numel() + 3) // 4 * 4
+        flat = torch.zeros(tot, device=dev)
+        views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(starts, outs)]
+        v_st, v_dy = views[:5], views[5:] + [None]
         v_off = torch.empty_like(off) if off is not None else None
         v_view = torch.zeros(K, 4, 4, device=dev) if ctx.needs_input_grad[0] else None
         cams = _cams(viewmats, Ks, width, height)

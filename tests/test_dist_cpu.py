@@ -139,3 +139,56 @@ def test_subframe_sharding_matches_single_process():
         for a, p in zip(res[r][1], params):
             want = p.grad if p.grad is not None else torch.zeros_like(p)
             torch.testing.assert_close(torch.from_numpy(a), want, atol=1e-6, rtol=1e-5)
+
+
+def _inplace_worker(rank, world, port, q):
+    """Gradients that are views into one flat buffer (what fused.synth_project's backward returns) are
+    all-reduced in place; a gradient with its own storage goes through the packed path in the same call."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mobgs_b200.dist import FlatGradients
+    g = torch.Generator().manual_seed(100 + rank)
+    shapes = [(7, 3), (5, 4), (11,)]
+    params = [torch.zeros(s, requires_grad=True) for s in shapes] + [torch.zeros(6, 12, requires_grad=True)]
+    flat = torch.zeros(sum((torch.Size(s).numel() + 3) // 4 * 4 for s in shapes))
+    off = 0
+    for p, s in zip(params, shapes):
+        n = torch.Size(s).numel()
+        flat[off:off + n] = torch.randn(n, generator=g)
+        p.grad = flat[off:off + n].view(s)
+        off += (n + 3) // 4 * 4
+    params[3].grad = torch.randn(6, 12, generator=g)
+    ptrs = [p.grad.data_ptr() for p in params[:3]]
+    fg = FlatGradients(params, inplace_shared=True)
+    fg.reduce()
+    assert [p.grad.data_ptr() for p in params[:3]] == ptrs          # reduced where they were
+    assert fg.last_collective_elems == flat.numel() + 72
+    q.put((rank, [p.grad.detach().numpy().copy() for p in params]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_inplace_reduction_of_shared_gradient_storage():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_inplace_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = []
+    for i, s in enumerate([(7, 3), (5, 4), (11,), (6, 12)]):
+        tot = torch.zeros(s)
+        for rank in (0, 1):
+            g = torch.Generator().manual_seed(100 + rank)
+            vals = [torch.randn(torch.Size(t).numel(), generator=g).view(t) for t in [(7, 3), (5, 4), (11,)]]
+            vals.append(torch.randn(6, 12, generator=g))
+            tot += vals[i]
+        want.append(tot)
+    for r in (0, 1):
+        for a, b in zip(results[r], want):
+            torch.testing.assert_close(torch.from_numpy(a), b, atol=1e-6, rtol=1e-6)
