@@ -68,22 +68,39 @@ __global__ void __launch_bounds__(kProjThreads) project_fwd_kernel(MobgsProjectF
   }
 }
 
-// 12 warp reductions per (warp, sub-frame); lanes that did not contribute pass zeros.  The warp sums
-// go to a shared-memory accumulator and leave the CTA as one atomicAdd per value at the very end:
-// thousands of CTAs hammering the same 12*K global addresses would serialise in L2.
+// View-matrix gradient of one (warp, sub-frame): the 12 per-lane terms (zeros from lanes that did not
+// contribute) are summed over the warp with a transposing butterfly — each stage halves the values a
+// lane holds while doubling the lanes summed: 16 shuffles for the 12 (padded to 16) values instead of
+// 60 — after which 12 different lanes each hold one complete sum and add it to the CTA's shared-memory
+// accumulator in parallel (one lane doing 12 CAS-loop atomics in a row was 30 % of this kernel's stall
+// samples).  The accumulator leaves the CTA as one atomicAdd per value at the very end: thousands of
+// CTAs hammering the same 12*K global addresses would serialise in L2.
 __device__ __forceinline__ void reduce_viewmat_grad(float (*v_view)[12], int k, const ProjGrad& g, bool active) {
   if (!__any_sync(0xffffffffu, active)) return;
-  float vals[12];
+  float v[16];
 #pragma unroll
-  for (int i = 0; i < 9; ++i) vals[i] = active ? g.r[i] : 0.f;
+  for (int i = 0; i < 9; ++i) v[i] = active ? g.r[i] : 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) vals[9 + i] = active ? g.t[i] : 0.f;
+  for (int i = 0; i < 3; ++i) v[9 + i] = active ? g.t[i] : 0.f;
 #pragma unroll
-  for (int i = 0; i < 12; ++i) vals[i] = warp_sum(vals[i]);
-  if ((threadIdx.x & 31) == 0) {
+  for (int i = 12; i < 16; ++i) v[i] = 0.f;
+  const int lane = threadIdx.x & 31;
+  int vidx = 0;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) atomicAdd(&v_view[k][i], vals[i]);
+  for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < n) {
+        const float send = up ? v[i] : v[i + n];
+        const float keep = up ? v[i + n] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    vidx += up ? n : 0;
   }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  if ((lane & 1) == 0 && vidx < 12 && v[0] != 0.f) atomicAdd(&v_view[k][vidx], v[0]);
 }
 
 __device__ __forceinline__ void flush_viewmat_grad(float (*v_view)[12], float* v_viewmats, int K) {
@@ -231,6 +248,9 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSy
   }
 }
 
+#ifndef MOBGS_CTRL_RED
+#define MOBGS_CTRL_RED 1
+#endif
 __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSynthBwd a) {
   __shared__ CamSmem sm;
   load_cams(sm, a.cams, a.t_spline, a.t_poly);
@@ -319,7 +339,12 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
           const float w = tp.w[t] * 1e-2f;
           if (w != 0.f) {
             float* c = v_ctrl + 3 * tp.idx[t];
+#if MOBGS_CTRL_RED
+            // fire-and-forget reductions: no load in the dependent chain (the row is zeroed by the caller)
+            atomicAdd(c, w * gr.p[0]); atomicAdd(c + 1, w * gr.p[1]); atomicAdd(c + 2, w * gr.p[2]);
+#else
             c[0] += w * gr.p[0]; c[1] += w * gr.p[1]; c[2] += w * gr.p[2];
+#endif
           }
         }
       }
