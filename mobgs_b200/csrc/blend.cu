@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 }
 
 
+#if MOBGS_UNIT_LANES == 16
 // ---------------------------------------------------------------------------------------------
 // Backward, transposing variant (kUL == 16).  The butterfly above spends ~45 % of the kernel's
 // instructions moving per-(pixel, Gaussian) terms between lanes.  Here the reduction over pixels
@@ -986,6 +987,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
 #endif
   }
 }
+
+#endif  // MOBGS_UNIT_LANES == 16
 
 }  // namespace mobgs
 
