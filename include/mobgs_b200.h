@@ -504,6 +504,36 @@ typedef struct {
 int mobgs_camera_rays_fwd(const MobgsCameraRays* a, void* stream);
 int mobgs_camera_rays_bwd(const MobgsCameraRays* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f1 (second half): flow-warp loss of train.py:656-676, forward + backward fused.
+ *   term1 = l1_loss(grid_sample(ori (expanded over K), norm(exp2mid)), latent, mask = latent_alpha)
+ *   term2 = l1_loss(grid_sample(latent, norm(mid2exp)), ori (expanded), mask = d_alpha (expanded))
+ * norm(c) = 2 c / (size - 1) - 1; grid_sample bilinear, padding_mode='border', align_corners=False (the
+ * call's default); masked l1_loss as utils/loss_utils.py:233-237.  Layouts (fp32, contiguous):
+ * ori [B,3,H,W], latent [B,K,3,H,W], exp2mid / mid2exp [B,K,H,W,2] (x, y in pixels), latent_alpha
+ * [B,K,1,H,W], d_alpha [B,1,H,W].
+ *   fwd: sums[0..3] = (num1, den1, num2, den2) in double (zeroed inside); loss = num1/(den1+1e-8) + num2/(den2+1e-8)
+ *   bwd: needs the sums of the forward; v_loss = device scalar (NULL = 1); writes v_exp2mid, v_mid2exp,
+ *        v_latent_alpha, v_d_alpha and accumulates v_latent (zeroed inside). */
+typedef struct {
+  int32_t B, K, H, W;
+  const float* ori;
+  const float* latent;
+  const float* exp2mid;
+  const float* mid2exp;
+  const float* latent_alpha;
+  const float* d_alpha;
+  double* sums;              /* [4] fwd out / bwd in */
+  const float* v_loss;
+  float* v_latent;
+  float* v_exp2mid;
+  float* v_mid2exp;
+  float* v_latent_alpha;
+  float* v_d_alpha;
+} MobgsFlowWarp;
+int mobgs_flow_warp_loss_fwd(const MobgsFlowWarp* a, void* stream);
+int mobgs_flow_warp_loss_bwd(const MobgsFlowWarp* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

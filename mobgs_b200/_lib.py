@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -235,7 +235,15 @@ class CameraRays(C.Structure):
                 ("rays", C.c_void_p), ("v_rays", C.c_void_p), ("v_rot", C.c_void_p), ("v_centre", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+class FlowWarp(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("ori", C.c_void_p),
+                ("latent", C.c_void_p), ("exp2mid", C.c_void_p), ("mid2exp", C.c_void_p), ("latent_alpha", C.c_void_p),
+                ("d_alpha", C.c_void_p), ("sums", C.c_void_p), ("v_loss", C.c_void_p), ("v_latent", C.c_void_p),
+                ("v_exp2mid", C.c_void_p), ("v_mid2exp", C.c_void_p), ("v_latent_alpha", C.c_void_p),
+                ("v_d_alpha", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -261,6 +269,8 @@ ENTRY_POINTS = {
     "mobgs_adam_step": Adam,
     "mobgs_photo_loss_fwd": PhotoLossFwd,
     "mobgs_photo_loss_bwd": PhotoLossBwd,
+    "mobgs_flow_warp_loss_fwd": FlowWarp,
+    "mobgs_flow_warp_loss_bwd": FlowWarp,
     "mobgs_camera_rays_fwd": CameraRays,
     "mobgs_camera_rays_bwd": CameraRays,
     "mobgs_adam_chunk_elems": "int",

@@ -103,3 +103,53 @@ def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_ave
     if window_size != 11 or not size_average:
         raise RuntimeError("mobgs_b200.losses.ssim implements window_size=11, size_average=True only")
     return _PhotoLoss.apply(img1, img2, 0.0, "ssim")
+
+
+class _FlowWarpLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ori, latent, exp2mid, mid2exp, latent_alpha, d_alpha):
+        ts = [t.contiguous() for t in (ori, latent, exp2mid, mid2exp, latent_alpha, d_alpha)]
+        for t in ts:
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise RuntimeError("flow_warp_loss needs CUDA fp32 tensors (there is no CPU fallback)")
+        ori_c, lat_c, e2m_c, m2e_c, la_c, da_c = ts
+        B, K, C, H, W = lat_c.shape
+        if C != 3 or ori_c.shape != (B, 3, H, W) or e2m_c.shape != (B, K, H, W, 2) or m2e_c.shape != (B, K, H, W, 2) \
+                or la_c.numel() != B * K * H * W or da_c.numel() != B * H * W:
+            raise RuntimeError("flow_warp_loss: shape mismatch")
+        sums = torch.empty(4, dtype=torch.float64, device=ori.device)
+        a = _lib.FlowWarp()
+        a.B, a.K, a.H, a.W = B, K, H, W
+        a.ori, a.latent, a.exp2mid, a.mid2exp = ori_c.data_ptr(), lat_c.data_ptr(), e2m_c.data_ptr(), m2e_c.data_ptr()
+        a.latent_alpha, a.d_alpha, a.sums = la_c.data_ptr(), da_c.data_ptr(), sums.data_ptr()
+        _lib.call("mobgs_flow_warp_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(ori_c, lat_c, e2m_c, m2e_c, la_c, da_c, sums)
+        ctx.shapes = (latent.shape, exp2mid.shape, mid2exp.shape, latent_alpha.shape, d_alpha.shape)
+        return (sums[0] / (sums[1] + 1e-8) + sums[2] / (sums[3] + 1e-8)).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        ori_c, lat_c, e2m_c, m2e_c, la_c, da_c, sums = ctx.saved_tensors
+        B, K, _, H, W = lat_c.shape
+        g = g.contiguous().float()
+        v_lat, v_e2m, v_m2e = torch.empty_like(lat_c), torch.empty_like(e2m_c), torch.empty_like(m2e_c)
+        v_la, v_da = torch.empty_like(la_c), torch.empty_like(da_c)
+        a = _lib.FlowWarp()
+        a.B, a.K, a.H, a.W = B, K, H, W
+        a.ori, a.latent, a.exp2mid, a.mid2exp = ori_c.data_ptr(), lat_c.data_ptr(), e2m_c.data_ptr(), m2e_c.data_ptr()
+        a.latent_alpha, a.d_alpha, a.sums = la_c.data_ptr(), da_c.data_ptr(), sums.data_ptr()
+        a.v_loss = g.data_ptr()
+        a.v_latent, a.v_exp2mid, a.v_mid2exp = v_lat.data_ptr(), v_e2m.data_ptr(), v_m2e.data_ptr()
+        a.v_latent_alpha, a.v_d_alpha = v_la.data_ptr(), v_da.data_ptr()
+        _lib.call("mobgs_flow_warp_loss_bwd", a, torch.cuda.current_stream().cuda_stream)
+        s = ctx.shapes
+        return None, v_lat.view(s[0]), v_e2m.view(s[1]), v_m2e.view(s[2]), v_la.view(s[3]), v_da.view(s[4])
+
+
+def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha) -> torch.Tensor:
+    """The flow-warp loss of train.py:656-676 without its `lambda_flow_loss` factor, as one forward + one
+    backward kernel.  ori_image [B,3,H,W] (`ori_image_tensor`), latent_img [B,K,3,H,W]
+    (`latent_img_final_tensor`), exp2mid_coord / mid2exp_coord [B,K,H,W,2] in pixels (NOT normalised — the
+    reference's in-place normalisation of train.py:659-662 / :667-670 happens inside), latent_alpha [B,K,1,H,W],
+    d_alpha [B,1,H,W].  Gradients flow to everything but ori_image."""
+    return _FlowWarpLoss.apply(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha)

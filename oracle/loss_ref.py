@@ -42,3 +42,28 @@ def ssim(img1, img2, window_size: int = 11):
 
 def photo_loss(image, gt, lambda_dssim: float):
     return l1_loss(image, gt) + lambda_dssim * (1.0 - ssim(image, gt))
+
+
+def l1_loss_masked(network_output, gt, mask):
+    """utils/loss_utils.py:233-237 (mask branch)."""
+    channel = gt.shape[1]
+    mask = mask.expand(-1, channel, -1, -1)
+    return torch.abs((network_output - gt) * mask).sum() / (mask.sum() + 1e-8)
+
+
+def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha):
+    """train.py:656-676 without the lambda_flow_loss factor.  ori_image [B,3,H,W], latent_img [B,K,3,H,W],
+    exp2mid_coord / mid2exp_coord [B,K,H,W,2] in pixels, latent_alpha [B,K,1,H,W], d_alpha [B,1,H,W].
+    (The reference normalises the coordinate tensors in place; out of place here — same autograd graph.)
+    Pinned by tests/golden/flow_warp_loss.npz (those train.py lines executed with the reference's own l1_loss)."""
+    B, K, _, H, W = latent_img.shape
+
+    def norm(c):
+        c = torch.stack([c[..., 0] / (W - 1), c[..., 1] / (H - 1)], dim=-1)
+        return (2.0 * c - 1.0).flatten(0, 1)
+
+    ori_exp = ori_image.unsqueeze(1).expand(-1, K, -1, -1, -1).flatten(0, 1)
+    warped_exp2mid = F.grid_sample(ori_exp, norm(exp2mid_coord), mode='bilinear', padding_mode='border').reshape(-1, K, 3, H, W)
+    warped_mid2exp = F.grid_sample(latent_img.flatten(0, 1), norm(mid2exp_coord), mode='bilinear', padding_mode='border').reshape(-1, K, 3, H, W)
+    return (l1_loss_masked(warped_exp2mid.flatten(0, 1), latent_img.flatten(0, 1), latent_alpha.flatten(0, 1))
+            + l1_loss_masked(warped_mid2exp.flatten(0, 1), ori_exp, d_alpha.unsqueeze(1).expand(-1, K, -1, -1, -1).flatten(0, 1)))

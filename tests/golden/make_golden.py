@@ -229,11 +229,64 @@ def make_camera_rays_golden(out_dir):
     print("wrote camera_rays", {k: v.shape for k, v in blob.items()})
 
 
+def make_flow_warp_golden(out_dir):
+    """flow_warp_loss.npz: train.py:656-676 executed line by line (the statements are inline in the training
+    loop, so they are reproduced here verbatim, in-place normalisation included) with the reference's own
+    utils.loss_utils.l1_loss and torch's F.grid_sample, CPU fp32.  B = 2 views, K = 3 exposures, 23 x 31 px;
+    coordinates = pixel grid + smooth offsets, some pushed outside the image (border clipping)."""
+    import torch.nn.functional as F
+    from utils.loss_utils import l1_loss          # the reference function, unmodified
+    g = torch.Generator().manual_seed(21)
+    B, K, H, W = 2, 3, 23, 31
+    exposure_length = K
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    base = torch.stack([xs, ys], -1)[None, None].expand(B, K, -1, -1, -1)
+
+    def coords():
+        c = base + 3.0 * torch.randn(B, K, 1, 1, 2, generator=g) + 1.5 * torch.randn(B, K, H, W, 2, generator=g)
+        c[:, :, :2, :, 1] -= 6.0          # rows sampled above the image
+        c[:, :, :, -2:, 0] += 9.0         # columns sampled right of it
+        return c.contiguous().requires_grad_(True)
+
+    e2m_leaf, m2e_leaf = coords(), coords()
+    ori_image_tensor = torch.rand(B, 3, H, W, generator=g)
+    latent_leaf = torch.rand(B, K, 3, H, W, generator=g).requires_grad_(True)
+    la_leaf = torch.rand(B, K, 1, H, W, generator=g).requires_grad_(True)
+    da_leaf = torch.rand(B, 1, H, W, generator=g).requires_grad_(True)
+    exp2mid_coord_final_tensor, mid2exp_coord_final_tensor = e2m_leaf.clone(), m2e_leaf.clone()
+    latent_img_final_tensor, latent_alpha_final_tensor, d_alpha_tensor = latent_leaf, la_leaf, da_leaf
+    # ---- train.py:658-675 ----
+    norm_exp2mid_coord_final_tensor = exp2mid_coord_final_tensor
+    norm_exp2mid_coord_final_tensor[..., 0] = norm_exp2mid_coord_final_tensor[..., 0] / (W - 1)
+    norm_exp2mid_coord_final_tensor[..., 1] = norm_exp2mid_coord_final_tensor[..., 1] / (H - 1)
+    norm_exp2mid_coord_final_tensor = 2.0 * norm_exp2mid_coord_final_tensor - 1.0
+    norm_exp2mid_coord_final_tensor = norm_exp2mid_coord_final_tensor.flatten(0, 1)
+    warped_exp2mid_img_tensor = F.grid_sample(ori_image_tensor.unsqueeze(1).expand(-1, exposure_length, -1, -1, -1).flatten(0,1), norm_exp2mid_coord_final_tensor, mode='bilinear', padding_mode='border').reshape(-1, exposure_length, 3, H, W)
+    norm_mid2exp_coord_final_tensor = mid2exp_coord_final_tensor
+    norm_mid2exp_coord_final_tensor[..., 0] = norm_mid2exp_coord_final_tensor[..., 0] / (W - 1)
+    norm_mid2exp_coord_final_tensor[..., 1] = norm_mid2exp_coord_final_tensor[..., 1] / (H - 1)
+    norm_mid2exp_coord_final_tensor = 2.0 * norm_mid2exp_coord_final_tensor - 1.0
+    norm_mid2exp_coord_final_tensor = norm_mid2exp_coord_final_tensor.flatten(0, 1)
+    warped_mid2exp_img_tensor = F.grid_sample(latent_img_final_tensor.flatten(0,1), norm_mid2exp_coord_final_tensor, mode='bilinear', padding_mode='border').reshape(-1, exposure_length, 3, H, W)
+    flow_loss = (l1_loss(warped_exp2mid_img_tensor.flatten(0,1), latent_img_final_tensor.flatten(0,1), mask=latent_alpha_final_tensor.flatten(0,1)) + l1_loss(warped_mid2exp_img_tensor.flatten(0,1), ori_image_tensor.unsqueeze(1).expand(-1, exposure_length, -1, -1, -1).flatten(0,1), mask=d_alpha_tensor.unsqueeze(1).expand(-1, exposure_length, -1, -1, -1).flatten(0,1)))
+    # --------------------------
+    flow_loss.backward()
+    blob = {"ori": _np(ori_image_tensor), "latent": _np(latent_leaf), "exp2mid": _np(e2m_leaf), "mid2exp": _np(m2e_leaf),
+            "latent_alpha": _np(la_leaf), "d_alpha": _np(da_leaf), "loss": _np(flow_loss),
+            "g_latent": _np(latent_leaf.grad), "g_exp2mid": _np(e2m_leaf.grad), "g_mid2exp": _np(m2e_leaf.grad),
+            "g_latent_alpha": _np(la_leaf.grad), "g_d_alpha": _np(da_leaf.grad)}
+    np.savez_compressed(os.path.join(out_dir, "flow_warp_loss.npz"), **blob)
+    print("wrote flow_warp_loss", float(flow_loss))
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
     if "--only-loss" in sys.argv:
         make_photo_loss_golden(out)
+        sys.exit(0)
+    if "--only-flow-warp" in sys.argv:
+        make_flow_warp_golden(out)
         sys.exit(0)
     if "--only-rays" in sys.argv:
         make_camera_rays_golden(out)
@@ -242,3 +295,4 @@ if __name__ == "__main__":
     make_hexplane_golden(out)
     make_photo_loss_golden(out)
     make_camera_rays_golden(out)
+    make_flow_warp_golden(out)
