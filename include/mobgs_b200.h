@@ -534,6 +534,24 @@ typedef struct {
 int mobgs_flow_warp_loss_fwd(const MobgsFlowWarp* a, void* stream);
 int mobgs_flow_warp_loss_bwd(const MobgsFlowWarp* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f2 (remainder): regularisers of train.py:651-655 in one pass.
+ *   sums[0] = sum |depth - gt_depth|           (l1_loss numerator, utils/loss_utils.py:233-239; mean = / n_depth)
+ *   sums[1] = entropy_loss(alpha)              (:264-276, eps 1e-6)
+ *   sums[2] = sparsity_loss(alpha) = sum alpha^2  (:285-295)
+ * g_depth [n_depth] = sign(depth - gt_depth), g_alpha [n_alpha] = d(entropy + sparsity)/d alpha — unscaled
+ * gradient maps (both optional); sums are double, zeroed inside the call. */
+typedef struct {
+  int64_t n_depth, n_alpha;
+  const float* depth;
+  const float* gt_depth;
+  const float* alpha;
+  double* sums;        /* [3] */
+  float* g_depth;
+  float* g_alpha;
+} MobgsRegLoss;
+int mobgs_reg_loss_fwd(const MobgsRegLoss* a, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -243,7 +243,12 @@ class FlowWarp(C.Structure):
                 ("v_d_alpha", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+class RegLoss(C.Structure):
+    _fields_ = [("n_depth", C.c_int64), ("n_alpha", C.c_int64), ("depth", C.c_void_p), ("gt_depth", C.c_void_p),
+                ("alpha", C.c_void_p), ("sums", C.c_void_p), ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p)]
+
+
+EXTRA_STRUCTS = {"MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -269,6 +274,7 @@ ENTRY_POINTS = {
     "mobgs_adam_step": Adam,
     "mobgs_photo_loss_fwd": PhotoLossFwd,
     "mobgs_photo_loss_bwd": PhotoLossBwd,
+    "mobgs_reg_loss_fwd": RegLoss,
     "mobgs_flow_warp_loss_fwd": FlowWarp,
     "mobgs_flow_warp_loss_bwd": FlowWarp,
     "mobgs_camera_rays_fwd": CameraRays,

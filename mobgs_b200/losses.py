@@ -153,3 +153,43 @@ def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_a
     reference's in-place normalisation of train.py:659-662 / :667-670 happens inside), latent_alpha [B,K,1,H,W],
     d_alpha [B,1,H,W].  Gradients flow to everything but ori_image."""
     return _FlowWarpLoss.apply(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha)
+
+
+class _RegLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, gt_depth, d_alpha, w_depth, w_mask):
+        d_c, g_c, a_c = depth.contiguous(), gt_depth.contiguous(), d_alpha.contiguous()
+        for t in (d_c, g_c, a_c):
+            if not (t.is_cuda and t.dtype == torch.float32):
+                raise RuntimeError("reg_loss needs CUDA fp32 tensors (there is no CPU fallback)")
+        if d_c.shape != g_c.shape:
+            raise RuntimeError("reg_loss: depth / gt_depth shape mismatch")
+        need = depth.requires_grad or d_alpha.requires_grad
+        sums = torch.empty(3, dtype=torch.float64, device=depth.device)
+        gd = torch.empty_like(d_c) if need else None
+        ga = torch.empty_like(a_c) if need else None
+        a = _lib.RegLoss()
+        a.n_depth, a.n_alpha = d_c.numel(), a_c.numel()
+        a.depth, a.gt_depth, a.alpha, a.sums = d_c.data_ptr(), g_c.data_ptr(), a_c.data_ptr(), sums.data_ptr()
+        if need:
+            a.g_depth, a.g_alpha = gd.data_ptr(), ga.data_ptr()
+        _lib.call("mobgs_reg_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        ctx.save_for_backward(gd, ga)
+        ctx.scales = (w_depth / max(d_c.numel(), 1), w_mask)
+        ctx.shapes = (depth.shape, d_alpha.shape)
+        ctx.mark_non_differentiable(sums)
+        total = (w_depth * sums[0] / max(d_c.numel(), 1) + w_mask * (sums[1] + sums[2])).float()
+        return total, sums
+
+    @staticmethod
+    def backward(ctx, g, _g_sums):
+        gd, ga = ctx.saved_tensors
+        sd, sa = ctx.scales
+        return (g * sd) * gd.view(ctx.shapes[0]), None, (g * sa) * ga.view(ctx.shapes[1]), None, None
+
+
+def reg_loss(depth, gt_depth, d_alpha, w_depth: float = 0.2, w_mask: float = 1e-7):
+    """train.py:651-655: `0.2 * l1_loss(depth, gt_depth) + 1e-7 * entropy_loss(d_alpha) + 1e-7 * sparsity_loss(d_alpha)`
+    in one launch.  Returns (reg, sums) with sums = [sum |depth - gt|, entropy, sparsity] (float64, for logging:
+    depth_loss = sums[0] / depth.numel())."""
+    return _RegLoss.apply(depth, gt_depth, d_alpha, float(w_depth), float(w_mask))

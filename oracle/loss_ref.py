@@ -67,3 +67,19 @@ def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_a
     warped_mid2exp = F.grid_sample(latent_img.flatten(0, 1), norm(mid2exp_coord), mode='bilinear', padding_mode='border').reshape(-1, K, 3, H, W)
     return (l1_loss_masked(warped_exp2mid.flatten(0, 1), latent_img.flatten(0, 1), latent_alpha.flatten(0, 1))
             + l1_loss_masked(warped_mid2exp.flatten(0, 1), ori_exp, d_alpha.unsqueeze(1).expand(-1, K, -1, -1, -1).flatten(0, 1)))
+
+
+def entropy_loss(alpha):
+    """utils/loss_utils.py:264-276."""
+    epsilon = 1e-6
+    return -torch.sum(alpha * torch.log(alpha + epsilon) + (1 - alpha) * torch.log(1 - alpha + epsilon))
+
+
+def sparsity_loss(alpha):
+    """utils/loss_utils.py:285-295."""
+    return torch.sum(alpha ** 2)
+
+
+def reg_loss(depth, gt_depth, d_alpha, w_depth=0.2, w_mask=1e-7):
+    """train.py:651-655.  Pinned by tests/golden/reg_loss.npz (the reference's own three functions)."""
+    return w_depth * l1_loss(depth, gt_depth) + w_mask * entropy_loss(d_alpha) + w_mask * sparsity_loss(d_alpha)

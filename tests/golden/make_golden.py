@@ -279,6 +279,28 @@ def make_flow_warp_golden(out_dir):
     print("wrote flow_warp_loss", float(flow_loss))
 
 
+def make_reg_loss_golden(out_dir):
+    """reg_loss.npz: train.py:651-655 with the reference's own l1_loss / entropy_loss / sparsity_loss (CPU fp32)."""
+    from utils.loss_utils import entropy_loss, l1_loss, sparsity_loss
+    g = torch.Generator().manual_seed(31)
+    B, H, W = 2, 19, 27
+    depth_tensor = (1.0 + 4.0 * torch.rand(B, 1, H, W, generator=g)).requires_grad_(True)
+    gt_depth_tensor = 1.0 + 4.0 * torch.rand(B, 1, H, W, generator=g)
+    d_alpha_tensor = torch.rand(B, 1, H, W, generator=g)
+    d_alpha_tensor[0, 0, 0, :4] = torch.tensor([0.0, 1.0, 1e-7, 1 - 1e-7])      # the epsilon matters at the ends
+    d_alpha_tensor.requires_grad_(True)
+    depth_loss = l1_loss(depth_tensor, gt_depth_tensor)
+    reg = 0.2 * depth_loss
+    mask_loss = 1e-7 * entropy_loss(d_alpha_tensor) + 1e-7 * sparsity_loss(d_alpha_tensor)
+    reg = reg + mask_loss
+    reg.backward()
+    blob = {"depth": _np(depth_tensor), "gt_depth": _np(gt_depth_tensor), "d_alpha": _np(d_alpha_tensor), "reg": _np(reg),
+            "depth_loss": _np(depth_loss), "entropy": _np(entropy_loss(d_alpha_tensor)), "sparsity": _np(sparsity_loss(d_alpha_tensor)),
+            "g_depth": _np(depth_tensor.grad), "g_d_alpha": _np(d_alpha_tensor.grad)}
+    np.savez_compressed(os.path.join(out_dir, "reg_loss.npz"), **blob)
+    print("wrote reg_loss", float(reg))
+
+
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out, exist_ok=True)
@@ -288,6 +310,9 @@ if __name__ == "__main__":
     if "--only-flow-warp" in sys.argv:
         make_flow_warp_golden(out)
         sys.exit(0)
+    if "--only-reg" in sys.argv:
+        make_reg_loss_golden(out)
+        sys.exit(0)
     if "--only-rays" in sys.argv:
         make_camera_rays_golden(out)
         sys.exit(0)
@@ -296,3 +321,4 @@ if __name__ == "__main__":
     make_photo_loss_golden(out)
     make_camera_rays_golden(out)
     make_flow_warp_golden(out)
+    make_reg_loss_golden(out)

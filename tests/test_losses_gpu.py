@@ -71,3 +71,32 @@ def test_photo_loss_forward_only_and_noncontiguous():
     assert abs(float(out) - float(L.photo_loss(xi, yi, 0.2))) <= 1e-5
     with pytest.raises(RuntimeError):
         losses.photo_loss(xi, yi, 0.2)                                  # CPU tensors: no fallback
+
+
+def test_reg_loss_matches_reference_golden_and_oracle():
+    """train.py:651-655 (depth L1 + entropy + sparsity of d_alpha) in one launch."""
+    from mobgs_b200 import losses
+    from oracle import loss_ref as L
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reg_loss.npz"))
+    d = torch.from_numpy(z["depth"]).cuda().requires_grad_(True)
+    a = torch.from_numpy(z["d_alpha"]).cuda().requires_grad_(True)
+    reg, sums = losses.reg_loss(d, torch.from_numpy(z["gt_depth"]).cuda(), a)
+    assert abs(float(reg) - float(z["reg"])) <= 1e-5 * abs(float(z["reg"]))
+    assert abs(float(sums[0]) / d.numel() - float(z["depth_loss"])) <= 1e-5 * float(z["depth_loss"])
+    assert abs(float(sums[1]) - float(z["entropy"])) <= 1e-5 * abs(float(z["entropy"]))
+    assert abs(float(sums[2]) - float(z["sparsity"])) <= 1e-5 * float(z["sparsity"])
+    (reg * 3.0).backward()
+    _grad_close(d.grad.cpu().numpy() / 3.0, z["g_depth"])
+    _grad_close(a.grad.cpu().numpy() / 3.0, z["g_d_alpha"])
+    # a larger seeded case against the oracle
+    g = torch.Generator().manual_seed(9)
+    dd, gt, al = 1 + 3 * torch.rand(2, 1, 288, 512, generator=g), 1 + 3 * torch.rand(2, 1, 288, 512, generator=g), torch.rand(2, 1, 288, 512, generator=g)
+    do, ao = dd.clone().requires_grad_(True), al.clone().requires_grad_(True)
+    ref = L.reg_loss(do, gt, ao)
+    ref.backward()
+    dc, ac = dd.cuda().requires_grad_(True), al.cuda().requires_grad_(True)
+    out, _ = losses.reg_loss(dc, gt.cuda(), ac)
+    out.backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    _grad_close(dc.grad.cpu().numpy(), do.grad.numpy())
+    _grad_close(ac.grad.cpu().numpy(), ao.grad.numpy())
