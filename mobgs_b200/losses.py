@@ -92,10 +92,14 @@ def photo_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float) -> to
 
 
 def l1_loss(network_output: torch.Tensor, gt: torch.Tensor, mask=None) -> torch.Tensor:
-    """utils/loss_utils.py:233-239 with mask=None (the photometric use, train.py:621)."""
+    """utils/loss_utils.py:233-239 with mask=None (the photometric / depth use, train.py:621, :651): one
+    streaming launch (mobgs_reg_loss_fwd with an empty alpha term) that also leaves sign(x - y) for the
+    backward, which is then a scalar multiply."""
     if mask is not None:
         raise RuntimeError("mobgs_b200.losses.l1_loss implements the mask=None form only")
-    return _PhotoLoss.apply(network_output, gt, 0.0, "l1")
+    _check(network_output, gt)
+    empty = network_output.new_empty(0)
+    return _RegLoss.apply(network_output, gt, empty, 1.0, 0.0)[0]
 
 
 def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True) -> torch.Tensor:
