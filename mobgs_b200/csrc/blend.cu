@@ -1,16 +1,23 @@
 // K6'/K7': front-to-back alpha compositing, forward and VJP.
 //
-// One CTA = one 16x16 tile of one sub-frame, one thread = one pixel.  The tile's depth-sorted
-// list is consumed in batches of 256 entries: every thread fetches one packed 64-byte record
-// (4 x LDG.128, L2-resident: the record array is 64 B x N) into shared memory, then all
-// 256 pixels walk the batch with broadcast LDS.128 reads — geometry *and* colours come from
-// shared memory (gsplat re-reads colours from global memory per (pixel, Gaussian) pair and
-// pads D=10 to 16 channels; here the channel count is a template parameter).
+// One CTA = one 16x16 tile of one sub-frame, one thread = one pixel.  The tile's depth-sorted list is
+// consumed in batches: every thread stages one packed 64-byte record with a TMA bulk copy (cp.async.bulk
+// -> mbarrier) into shared memory — geometry *and* colours (gsplat re-reads colours from global memory
+// per (pixel, Gaussian) pair and pads D=10 to 16 channels; here the channel count is a template
+// parameter) — and computes which of the tile's sixteen 4x4-pixel *units* the Gaussian can reach with
+// alpha >= 1/255 (blend_units.cuh, exact).  Each warp compacts the batch into one list per unit, so its two
+// half-warps walk different Gaussians at the same time and skip everything that cannot touch them.
 //
-// Backward: per (pixel, Gaussian) gradients are warp-reduced with shuffles, combined across the
-// 8 warps of the CTA in a shared-memory accumulator, and leave the SM as four 16-byte vector
-// reductions (REDG.128) per (tile, Gaussian) — gsplat issues 16 scalar atomics per (warp,
-// Gaussian).
+// Forward (blend_fwd_kernel): per-lane loop over the unit's list, LDS.128 broadcast of the record, ex2.approx;
+// optional fused epilogue: expected depth + Sandwich decoder while the pixel is in registers.
+//
+// Backward (blend_bwd_tr_kernel): back to front with the scalar suffix S instead of gsplat's per-channel
+// buffer.  The sum over pixels is done by changing ownership: Phase A (lane = pixel) parks fac = alpha T and
+// v_sigma of 8 list entries in a per-warp matrix, Phase B (lane = entry x half of the unit's pixels) turns a
+// row of it into the 16 gradient sums of that (unit, Gaussian) and sends them to global memory as 2 x
+// RED.128 per lane — gsplat issues 16 scalar atomics per (warp, Gaussian) after 5-step shuffle reductions.
+// blend_bwd_kernel (transposing-butterfly reductions + shared accumulator) is the earlier variant, kept for
+// the ablation build (-DMOBGS_BWD_TRANSPOSE=0) and for unit sizes other than 16 lanes.
 #include "common.cuh"
 #include "blend_units.cuh"
 #include "decode_math.cuh"
