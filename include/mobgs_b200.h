@@ -552,6 +552,12 @@ typedef struct {
 } MobgsRegLoss;
 int mobgs_reg_loss_fwd(const MobgsRegLoss* a, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * K9 / f4: simple_knn._C.distCUDA2(points [N,3]) -> [N]: mean squared distance to the 3 nearest
+ * neighbours, the point itself excluded (scene/gaussian_model.py:420, :514).  Tiled brute force, O(N^2):
+ * for the initialisation point clouds. */
+int mobgs_knn3_mean_dist2(const float* points, float* out, int32_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -305,6 +305,8 @@ def load() -> C.CDLL:
                     "Run `python -c 'import __graft_entry__ as g; g.build()'`. There is no fallback path."
                 ) from e
         lib = C.CDLL(LIB_PATH)
+        lib.mobgs_knn3_mean_dist2.restype = C.c_int
+        lib.mobgs_knn3_mean_dist2.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         lib.mobgs_subframe_mean.restype = C.c_int
         lib.mobgs_subframe_mean.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
         for name, struct in ENTRY_POINTS.items():
@@ -336,6 +338,15 @@ TIMING = None
 
 
 DEC_SLOTS = 1024
+
+
+def knn3_mean_dist2(points_ptr, out_ptr, n, stream) -> None:
+    global LAUNCH_COUNT
+    lib = load()
+    LAUNCH_COUNT += 1
+    rc = lib.mobgs_knn3_mean_dist2(C.c_void_p(points_ptr), C.c_void_p(out_ptr), C.c_int32(n), C.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError(f"mobgs_knn3_mean_dist2 failed (code {rc}): {lib.mobgs_last_error().decode()}")
 
 
 def subframe_mean(rgb_ptr, mean_ptr, K, n, stream) -> None:

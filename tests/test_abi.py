@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert len(names) >= 13
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported by {path}"
-        assert n in _lib.ENTRY_POINTS or n == "mobgs_subframe_mean", f"{n} has no ctypes binding in mobgs_b200/_lib.py"
+        assert n in _lib.ENTRY_POINTS or n in ("mobgs_subframe_mean", "mobgs_knn3_mean_dist2"), f"{n} has no ctypes binding in mobgs_b200/_lib.py"
     assert b"sm_100a" in _lib.load().mobgs_version()
 
 
