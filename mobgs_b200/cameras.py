@@ -25,7 +25,7 @@ class _CameraRays(torch.autograd.Function):
         a.K, a.H, a.W = K, H, W
         a.ppx, a.ppy, a.sfx, a.sfy = ppx, ppy, sfx, sfy
         a.rot, a.centre, a.rays = rot_c.data_ptr(), cen_c.data_ptr(), rays.data_ptr()
-        _lib.call("mobgs_camera_rays_fwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_camera_rays_fwd", a, _lib.current_stream())
         ctx.save_for_backward(rot_c, cen_c)
         ctx.geom = (ppx, ppy, sfx, sfy, W, H)
         return rays
@@ -42,7 +42,7 @@ class _CameraRays(torch.autograd.Function):
         a.ppx, a.ppy, a.sfx, a.sfy = ppx, ppy, sfx, sfy
         a.rot, a.centre = rot_c.data_ptr(), cen_c.data_ptr()
         a.v_rays, a.v_rot, a.v_centre = g.data_ptr(), v_rot.data_ptr(), v_cen.data_ptr()
-        _lib.call("mobgs_camera_rays_bwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_camera_rays_bwd", a, _lib.current_stream())
         return v_rot, v_cen, None, None, None, None, None, None
 
 

@@ -13,5 +13,5 @@ def distCUDA2(points: torch.Tensor) -> torch.Tensor:
     if pts.dim() != 2 or pts.shape[1] != 3:
         raise RuntimeError(f"distCUDA2 expects [N,3] points, got {tuple(pts.shape)}")
     out = torch.empty(pts.shape[0], device=pts.device)
-    _lib.knn3_mean_dist2(pts.data_ptr(), out.data_ptr(), pts.shape[0], torch.cuda.current_stream().cuda_stream)
+    _lib.knn3_mean_dist2(pts.data_ptr(), out.data_ptr(), pts.shape[0], _lib.current_stream())
     return out

@@ -52,7 +52,7 @@ class _PhotoLoss(torch.autograd.Function):
         if need_grad:
             maps = torch.empty(3, planes, H, W, device=img.device)
             a.d_mu1, a.d_x2, a.d_xy = maps[0].data_ptr(), maps[1].data_ptr(), maps[2].data_ptr()
-        _lib.call("mobgs_photo_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_photo_loss_fwd", a, _lib.current_stream())
         n = img_c.numel()
         l1 = (sums[0] / n).float()
         ss = (sums[1] / n).float()
@@ -82,7 +82,7 @@ class _PhotoLoss(torch.autograd.Function):
         a.scale_l1 = {"l1": 1.0 / n, "ssim": 0.0}.get(ctx.want, 1.0 / n)
         a.scale_ssim = {"l1": 0.0, "ssim": 1.0 / n}.get(ctx.want, -ctx.lam / n)
         a.v_img = v.data_ptr()
-        _lib.call("mobgs_photo_loss_bwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_photo_loss_bwd", a, _lib.current_stream())
         return v.view(ctx.shape), None, None, None
 
 
@@ -126,7 +126,7 @@ class _FlowWarpLoss(torch.autograd.Function):
         a.B, a.K, a.H, a.W = B, K, H, W
         a.ori, a.latent, a.exp2mid, a.mid2exp = ori_c.data_ptr(), lat_c.data_ptr(), e2m_c.data_ptr(), m2e_c.data_ptr()
         a.latent_alpha, a.d_alpha, a.sums = la_c.data_ptr(), da_c.data_ptr(), sums.data_ptr()
-        _lib.call("mobgs_flow_warp_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_flow_warp_loss_fwd", a, _lib.current_stream())
         ctx.save_for_backward(ori_c, lat_c, e2m_c, m2e_c, la_c, da_c, sums)
         ctx.shapes = (latent.shape, exp2mid.shape, mid2exp.shape, latent_alpha.shape, d_alpha.shape)
         return (sums[0] / (sums[1] + 1e-8) + sums[2] / (sums[3] + 1e-8)).float()
@@ -145,7 +145,7 @@ class _FlowWarpLoss(torch.autograd.Function):
         a.v_loss = g.data_ptr()
         a.v_latent, a.v_exp2mid, a.v_mid2exp = v_lat.data_ptr(), v_e2m.data_ptr(), v_m2e.data_ptr()
         a.v_latent_alpha, a.v_d_alpha = v_la.data_ptr(), v_da.data_ptr()
-        _lib.call("mobgs_flow_warp_loss_bwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_flow_warp_loss_bwd", a, _lib.current_stream())
         s = ctx.shapes
         return None, v_lat.view(s[0]), v_e2m.view(s[1]), v_m2e.view(s[2]), v_la.view(s[3]), v_da.view(s[4])
 
@@ -177,7 +177,7 @@ class _RegLoss(torch.autograd.Function):
         a.depth, a.gt_depth, a.alpha, a.sums = d_c.data_ptr(), g_c.data_ptr(), a_c.data_ptr(), sums.data_ptr()
         if need:
             a.g_depth, a.g_alpha = gd.data_ptr(), ga.data_ptr()
-        _lib.call("mobgs_reg_loss_fwd", a, torch.cuda.current_stream().cuda_stream)
+        _lib.call("mobgs_reg_loss_fwd", a, _lib.current_stream())
         ctx.save_for_backward(gd, ga)
         ctx.scales = (w_depth / max(d_c.numel(), 1), w_mask)
         ctx.shapes = (depth.shape, d_alpha.shape)

@@ -18,7 +18,7 @@ EPS2D, NEAR, FAR, RADIUS_CLIP = 0.3, 0.01, 1e10, 0.0   # gsplat.rendering.raster
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return L.current_stream()
 
 
 def _p(t: Optional[torch.Tensor]):

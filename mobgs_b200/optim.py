@@ -52,7 +52,7 @@ def _launch(items):
     if not items:
         return
     chunk = _lib.load().mobgs_adam_chunk_elems()
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _lib.current_stream()
     # one launch per (beta1, beta2, eps) combination (the reference has exactly one)
     by_hyper = {}
     for it in items:
