@@ -514,7 +514,10 @@ int mobgs_camera_rays_bwd(const MobgsCameraRays* a, void* stream);
  * [B,K,1,H,W], d_alpha [B,1,H,W].
  *   fwd: sums[0..3] = (num1, den1, num2, den2) in double (zeroed inside); loss = num1/(den1+1e-8) + num2/(den2+1e-8)
  *   bwd: needs the sums of the forward; v_loss = device scalar (NULL = 1); writes v_exp2mid, v_mid2exp,
- *        v_latent_alpha, v_d_alpha and accumulates v_latent (zeroed inside). */
+ *        v_latent_alpha, v_d_alpha and accumulates v_latent (zeroed inside).  v_ori (optional, NULL =
+ *        skip; zeroed inside) receives d loss / d ori: in the reference ori_image_tensor is the live
+ *        centre render (train.py:469, :607), so the loss reaches it through the exp2mid grid_sample
+ *        (bilinear scatter) and as the L1 target of the mid2exp term. */
 typedef struct {
   int32_t B, K, H, W;
   const float* ori;
@@ -530,6 +533,7 @@ typedef struct {
   float* v_mid2exp;
   float* v_latent_alpha;
   float* v_d_alpha;
+  float* v_ori;              /* [B,3,H,W] or NULL */
 } MobgsFlowWarp;
 int mobgs_flow_warp_loss_fwd(const MobgsFlowWarp* a, void* stream);
 int mobgs_flow_warp_loss_bwd(const MobgsFlowWarp* a, void* stream);

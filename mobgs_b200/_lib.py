@@ -241,7 +241,7 @@ class FlowWarp(C.Structure):
                 ("latent", C.c_void_p), ("exp2mid", C.c_void_p), ("mid2exp", C.c_void_p), ("latent_alpha", C.c_void_p),
                 ("d_alpha", C.c_void_p), ("sums", C.c_void_p), ("v_loss", C.c_void_p), ("v_latent", C.c_void_p),
                 ("v_exp2mid", C.c_void_p), ("v_mid2exp", C.c_void_p), ("v_latent_alpha", C.c_void_p),
-                ("v_d_alpha", C.c_void_p)]
+                ("v_d_alpha", C.c_void_p), ("v_ori", C.c_void_p)]
 
 
 class RegLoss(C.Structure):

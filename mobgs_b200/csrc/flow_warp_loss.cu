@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(kFwThreads) flow_warp_bwd_kernel(const __grid_
 #pragma unroll
   for (int c = 0; c < 3; ++c) o[c] = ori[(size_t)c * P + p];
   float v_m2 = 0.f;
+  float v_o[3] = {0.f, 0.f, 0.f};          // d loss / d ori[b, :, p] as the L1 target of the mid2exp term
+  float* v_ori = a.v_ori ? a.v_ori + (size_t)b * 3 * P : nullptr;
   for (int k = 0; k < a.K; ++k) {
     const size_t bk = (size_t)b * a.K + k;
     const float* lat = a.latent + bk * 3 * P;
@@ -134,7 +136,18 @@ __global__ void __launch_bounds__(kFwThreads) flow_warp_bwd_kernel(const __grid_
       const float s1 = sgn(r1 * m1);
       const float gw1 = g * s1 * m1 * i1;                 // d loss / d warped1[c]
       v1x += gw1 * dx; v1y += gw1 * dy;
-      if (gw1 != 0.f) atomicAdd(v_lat + (size_t)c * P + p, -gw1);
+      if (gw1 != 0.f) {
+        atomicAdd(v_lat + (size_t)c * P + p, -gw1);
+        if (v_ori) {                                       // the sampled source: bilinear scatter
+          float* vp = v_ori + (size_t)c * P;
+          const bool xin = b1.x0 + 1 < a.W, yin = b1.y0 + 1 < a.H;
+          const float ux = 1.f - b1.wx, uy = 1.f - b1.wy;
+          atomicAdd(vp + (size_t)b1.y0 * a.W + b1.x0, gw1 * ux * uy);
+          if (xin) atomicAdd(vp + (size_t)b1.y0 * a.W + b1.x0 + 1, gw1 * b1.wx * uy);
+          if (yin) atomicAdd(vp + (size_t)(b1.y0 + 1) * a.W + b1.x0, gw1 * ux * b1.wy);
+          if (xin && yin) atomicAdd(vp + (size_t)(b1.y0 + 1) * a.W + b1.x0 + 1, gw1 * b1.wx * b1.wy);
+        }
+      }
       v_m1 += g * s1 * r1 * i1;
       // mid2exp: source = latent image (scatter), target = ori image, mask = dynamic alpha
       const float w2 = bilin_sample(lat + (size_t)c * P, b2, a.W, a.H, dx, dy);
@@ -143,6 +156,7 @@ __global__ void __launch_bounds__(kFwThreads) flow_warp_bwd_kernel(const __grid_
       const float gw2 = g * s2 * m2 * i2;                 // d loss / d warped2[c]
       v2x += gw2 * dx; v2y += gw2 * dy;
       v_m2 += g * s2 * r2 * i2;
+      v_o[c] -= gw2;
       if (gw2 != 0.f) {
         float* vp = v_lat + (size_t)c * P;
         const bool xin = b2.x0 + 1 < a.W, yin = b2.y0 + 1 < a.H;
@@ -159,6 +173,11 @@ __global__ void __launch_bounds__(kFwThreads) flow_warp_bwd_kernel(const __grid_
     v_m2 -= g * q2;
   }
   a.v_d_alpha[(size_t)b * P + p] = v_m2;
+  if (v_ori) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      if (v_o[c] != 0.f) atomicAdd(v_ori + (size_t)c * P + p, v_o[c]);
+  }
 }
 
 }  // namespace mobgs
@@ -187,6 +206,7 @@ extern "C" int mobgs_flow_warp_loss_bwd(const MobgsFlowWarp* a, void* stream) {
   MOBGS_REQUIRE(a->v_latent && a->v_exp2mid && a->v_mid2exp && a->v_latent_alpha && a->v_d_alpha, "NULL gradient pointer");
   cudaStream_t s = (cudaStream_t)stream;
   cudaMemsetAsync(a->v_latent, 0, sizeof(float) * (size_t)a->B * a->K * 3 * a->H * a->W, s);
+  if (a->v_ori) cudaMemsetAsync(a->v_ori, 0, sizeof(float) * (size_t)a->B * 3 * a->H * a->W, s);
   const dim3 grid((a->H * a->W + kFwThreads - 1) / kFwThreads, a->B);
   flow_warp_bwd_kernel<<<grid, kFwThreads, 0, s>>>(*a);
   return check_launch("flow_warp_loss_bwd");

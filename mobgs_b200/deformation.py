@@ -106,11 +106,9 @@ def _hexfeat_struct(pts, times, aabb, planes):
     a = L.HexFeat()
     a.N = pts.shape[0]
     a.pts, a.times = _p(pts), _p(times)
-    akey = (aabb.data_ptr(), aabb._version)
-    if _PACK_CACHE.get("aabb_key") != akey:
-        _PACK_CACHE["aabb_key"], _PACK_CACHE["aabb"] = akey, aabb.detach().float().cpu().reshape(-1).tolist()
+    ab = _aabb_host(aabb)
     for i in range(6):
-        a.aabb[i] = _PACK_CACHE["aabb"][i]
+        a.aabb[i] = ab[i]
     a.levels = len(planes)
     cl = [g.detach()[0].permute(1, 2, 0).contiguous().float() for level in planes for g in level]
     for i, t in enumerate(cl):
@@ -184,11 +182,24 @@ def fused_forward_raw(pts, scales, rots, times, aabb, planes: Sequence[Sequence[
 _PACK_CACHE = {}
 
 
+def _aabb_host(aabb):
+    """the six AABB floats on the host: one 24-byte read-back per AABB change, not per call"""
+    hit = _PACK_CACHE.get("aabb")
+    if hit is not None and hit[0] is aabb and hit[1] == aabb._version:
+        return hit[2]
+    vals = aabb.detach().float().cpu().reshape(-1).tolist()
+    _PACK_CACHE["aabb"] = (aabb, aabb._version, vals)
+    return vals
+
+
 def _packed_operands(planes, w0, b0, heads):
     flat = [p for level in planes for p in level] + [w0, b0] + [t for h in heads for t in h]
-    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in flat)
+    # identity is checked on the tensor OBJECTS the cache keeps alive (an address can be recycled by the
+    # allocator; an object that is still referenced cannot), plus the autograd version counter, which
+    # FusedAdam bumps after its raw-pointer update (optim._launch)
+    key = [(t, t._version) for t in flat]
     hit = _PACK_CACHE.get("last")
-    if hit is not None and hit[0] == key:
+    if hit is not None and len(hit[0]) == len(key) and all(a is b and va == vb for (a, va), (b, vb) in zip(hit[0], key)):
         return hit[1], hit[2]
     cl = []
     for grids in planes:
@@ -212,10 +223,7 @@ def _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads)
     a = L.HexMlpFwd()
     a.N = N
     a.pts, a.scales, a.rots, a.times = _p(pts), _p(scales), _p(rots), _p(times)
-    akey = (aabb.data_ptr(), aabb._version)
-    if _PACK_CACHE.get("aabb_key") != akey:            # one 24-byte read-back per AABB change, not per call
-        _PACK_CACHE["aabb_key"], _PACK_CACHE["aabb"] = akey, aabb.detach().float().cpu().reshape(-1).tolist()
-    ab = _PACK_CACHE["aabb"]
+    ab = _aabb_host(aabb)
     for i in range(6):
         a.aabb[i] = ab[i]
     a.levels, a.net_width, a.plane_features = levels, NET_WIDTH, PLANE_FEATURES

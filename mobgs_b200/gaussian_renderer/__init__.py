@@ -32,14 +32,13 @@ _BG_CACHE = {}
 
 def _bg10(bg_color, dev):
     """bg[:3] tiled over the 9 feature channels + 0 for the depth channel (render():90-91), cached per
-    background tensor (identity + version) — it is the same tensor on every call of a training run."""
-    key = (bg_color.data_ptr(), bg_color._version, str(dev))
-    hit = _BG_CACHE.get("bg")
-    if hit is not None and hit[0] == key:
-        return hit[1]
+    background tensor (object identity + version) — it is the same tensor on every call of a training run."""
+    hit = _BG_CACHE.get("bg")     # the cache holds the tensor itself, so its identity cannot be recycled
+    if hit is not None and hit[0] is bg_color and hit[1] == bg_color._version and hit[2] == dev:
+        return hit[3]
     b3 = bg_color[:3].detach().to(device=dev, dtype=torch.float32)
     out = torch.cat([b3, b3, b3, b3.new_zeros(1)])[None]
-    _BG_CACHE["bg"] = (key, out)
+    _BG_CACHE["bg"] = (bg_color, bg_color._version, dev, out)
     return out
 
 

@@ -129,6 +129,7 @@ class _FlowWarpLoss(torch.autograd.Function):
         _lib.call("mobgs_flow_warp_loss_fwd", a, _lib.current_stream())
         ctx.save_for_backward(ori_c, lat_c, e2m_c, m2e_c, la_c, da_c, sums)
         ctx.shapes = (latent.shape, exp2mid.shape, mid2exp.shape, latent_alpha.shape, d_alpha.shape)
+        ctx.ori_shape = ori.shape
         return (sums[0] / (sums[1] + 1e-8) + sums[2] / (sums[3] + 1e-8)).float()
 
     @staticmethod
@@ -138,6 +139,7 @@ class _FlowWarpLoss(torch.autograd.Function):
         g = g.contiguous().float()
         v_lat, v_e2m, v_m2e = torch.empty_like(lat_c), torch.empty_like(e2m_c), torch.empty_like(m2e_c)
         v_la, v_da = torch.empty_like(la_c), torch.empty_like(da_c)
+        v_ori = torch.empty_like(ori_c) if ctx.needs_input_grad[0] else None
         a = _lib.FlowWarp()
         a.B, a.K, a.H, a.W = B, K, H, W
         a.ori, a.latent, a.exp2mid, a.mid2exp = ori_c.data_ptr(), lat_c.data_ptr(), e2m_c.data_ptr(), m2e_c.data_ptr()
@@ -145,9 +147,11 @@ class _FlowWarpLoss(torch.autograd.Function):
         a.v_loss = g.data_ptr()
         a.v_latent, a.v_exp2mid, a.v_mid2exp = v_lat.data_ptr(), v_e2m.data_ptr(), v_m2e.data_ptr()
         a.v_latent_alpha, a.v_d_alpha = v_la.data_ptr(), v_da.data_ptr()
+        if v_ori is not None:
+            a.v_ori = v_ori.data_ptr()
         _lib.call("mobgs_flow_warp_loss_bwd", a, _lib.current_stream())
         s = ctx.shapes
-        return None, v_lat.view(s[0]), v_e2m.view(s[1]), v_m2e.view(s[2]), v_la.view(s[3]), v_da.view(s[4])
+        return (v_ori.view(ctx.ori_shape) if v_ori is not None else None), v_lat.view(s[0]), v_e2m.view(s[1]), v_m2e.view(s[2]), v_la.view(s[3]), v_da.view(s[4])
 
 
 def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha) -> torch.Tensor:
@@ -155,7 +159,8 @@ def flow_warp_loss(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_a
     backward kernel.  ori_image [B,3,H,W] (`ori_image_tensor`), latent_img [B,K,3,H,W]
     (`latent_img_final_tensor`), exp2mid_coord / mid2exp_coord [B,K,H,W,2] in pixels (NOT normalised — the
     reference's in-place normalisation of train.py:659-662 / :667-670 happens inside), latent_alpha [B,K,1,H,W],
-    d_alpha [B,1,H,W].  Gradients flow to everything but ori_image."""
+    d_alpha [B,1,H,W].  Gradients flow to every argument, `ori_image` included: in the reference it is the live
+    centre render (train.py:469, :607), reached through the exp2mid grid_sample and as the mid2exp L1 target."""
     return _FlowWarpLoss.apply(ori_image, latent_img, exp2mid_coord, mid2exp_coord, latent_alpha, d_alpha)
 
 

@@ -181,12 +181,18 @@ def rasterize_to_pixels(
     tile_size: int = TILE_SIZE,
     pixel_chunk: int = 8192,
     return_stats: bool = False,
+    window: Optional[Tuple[int, int, int, int]] = None,
 ):
     """isect_tiles + stable (tile, depth) sort + rasterize_to_pixels_fwd_kernel, dense.
 
     For every pixel the candidate sequence is: Gaussians whose tile AABB covers the
     pixel's 16x16 tile, in ascending depth (ties: ascending index — the stable LSB
-    radix sort keeps emission order)."""
+    radix sort keeps emission order).
+
+    window = (x0, y0, w, h), tile aligned: only the pixels of that window are evaluated (output
+    [h,w,D]) and only the Gaussians whose tile AABB touches the window's tiles enter the dense
+    pixel x Gaussian arithmetic — per pixel exactly the candidate sequence of the full-frame
+    render, so a crop of a 1 M-Gaussian / 1080p frame costs what a small frame costs."""
     N = means2d.shape[0]
     D = colors.shape[-1]
     dev, dt = means2d.device, means2d.dtype
@@ -201,8 +207,19 @@ def rasterize_to_pixels(
     col = colors[order]
     op = opacities[order]
     x0, y0, x1, y1 = tile_bounds(m2.detach(), radii[order], tile_w, tile_h, tile_size)
+    if window is None:
+        wx0, wy0, ww, wh = 0, 0, width, height
+    else:
+        wx0, wy0, ww, wh = (int(v) for v in window)
+        assert wx0 % tile_size == 0 and wy0 % tile_size == 0 and wx0 >= 0 and wy0 >= 0
+        assert wx0 + ww <= width and wy0 + wh <= height
+        t0x, t0y = wx0 // tile_size, wy0 // tile_size
+        t1x, t1y = (wx0 + ww - 1) // tile_size + 1, (wy0 + wh - 1) // tile_size + 1
+        keep = (x0 < t1x) & (x1 > t0x) & (y0 < t1y) & (y1 > t0y)
+        m2, cn, col, op = m2[keep], cn[keep], col[keep], op[keep]
+        x0, y0, x1, y1 = x0[keep], y0[keep], x1[keep], y1[keep]
 
-    P = width * height
+    P = ww * wh
     out_c = []
     out_a = []
     n_pairs = 0
@@ -210,8 +227,8 @@ def rasterize_to_pixels(
     for s in range(0, P, pixel_chunk):
         e = min(P, s + pixel_chunk)
         pid = torch.arange(s, e, device=dev)
-        pyi = pid // width
-        pxi = pid % width
+        pyi = pid // ww + wy0
+        pxi = pid % ww + wx0
         px = pxi.to(dt) + 0.5
         py = pyi.to(dt) + 0.5
         tx = (pxi // tile_size)[:, None]
@@ -242,8 +259,8 @@ def rasterize_to_pixels(
         if return_stats:
             n_pairs += int(in_tile.sum())
             n_blend += int((a > 0).sum())
-    rc = torch.cat(out_c, 0).reshape(height, width, D)
-    ra = torch.cat(out_a, 0).reshape(height, width, 1)
+    rc = torch.cat(out_c, 0).reshape(wh, ww, D)
+    ra = torch.cat(out_a, 0).reshape(wh, ww, 1)
     if return_stats:
         return rc, ra, {"pixel_pairs": n_pairs, "blended_pairs": n_blend}
     return rc, ra
@@ -268,11 +285,13 @@ def rasterization(
     tile_size: int = TILE_SIZE,
     backgrounds: Optional[torch.Tensor] = None,   # [C,D]
     render_mode: str = "RGB",
+    window: Optional[Tuple[int, int, int, int]] = None,
     **unused,
 ):
     """Restates gsplat.rendering.rasterization for the kwargs the reference passes.
 
-    Returns (render_colors [C,H,W,D(+1)], render_alphas [C,H,W,1], meta)."""
+    Returns (render_colors [C,H,W,D(+1)], render_alphas [C,H,W,1], meta).  `window` (oracle-only
+    extension, see rasterize_to_pixels): project everything, rasterise one tile-aligned crop."""
     assert sh_degree is None and not packed
     assert render_mode in ("RGB", "RGB+ED", "RGB+D", "D", "ED")
     C = viewmats.shape[0]
@@ -293,7 +312,7 @@ def rasterization(
     for c in range(C):
         rc, ra = rasterize_to_pixels(
             means2d[c], conics[c], colors[c], opacities, radii[c], depths[c], width, height,
-            backgrounds[c] if backgrounds is not None else None, tile_size)
+            backgrounds[c] if backgrounds is not None else None, tile_size, window=window)
         rcs.append(rc)
         ras.append(ra)
     render_colors = torch.stack(rcs, 0)

@@ -17,6 +17,8 @@ in mobgs_b200/scene.py).  Runs on whatever device the parameters live on.
 """
 from __future__ import annotations
 
+import functools
+
 import torch
 
 from . import gsplat_ref as G
@@ -93,11 +95,12 @@ def static_attributes(stat_pc):
             stat_pc.get_opacity, stat_pc.get_features_static)
 
 
-def _raster(means, quats, scales, opac, colors, bg, viewmat, K, cam, mode):
+def _raster(means, quats, scales, opac, colors, bg, viewmat, K, cam, mode, window=None):
     return G.rasterization(
         means=means, quats=quats, scales=scales, opacities=opac.squeeze(-1), colors=colors,
         backgrounds=bg, viewmats=viewmat[None], Ks=K[None],
-        width=int(cam.image_width), height=int(cam.image_height), packed=False, render_mode=mode)
+        width=int(cam.image_width), height=int(cam.image_height), packed=False, render_mode=mode,
+        window=window)
 
 
 def _project(means, quats, scales, viewmat, K, cam):
@@ -118,7 +121,11 @@ def render_ref(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color, scaling_modifi
                override_color=None, stage="fine", cam_type=None, is_static=False, over_t=None,
                over_vde=None, get_static=False, get_dynamic=False, stat_stat=True, ref_wc=None,
                iter_fact=1, flow=None, coherent=None, target_ts=None, target_w2cs=None,
-               get_heatmap=False, w2c=None, delta_exposure=None, get_flow=False, cluster=None):
+               get_heatmap=False, w2c=None, delta_exposure=None, get_flow=False, cluster=None,
+               window=None):
+    """`window` = (x0, y0, w, h), tile aligned (oracle-only extension): every image in the result is
+    the crop of the full-frame render to that window (all Gaussians are projected, only the window is
+    rasterised) — how the full-size parity tests and bench.py's CPU arm sample a 1 M-Gaussian frame."""
     cam = viewpoint_camera
     viewmat = cam.world_view_transform.transpose(0, 1) if w2c is None else w2c
     K = cam.K
@@ -134,18 +141,23 @@ def render_ref(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color, scaling_modifi
     s_means, s_quats, s_scales, s_opac, s_cols = static_attributes(stat_pc)
     w1, w2 = _decoder_weights(dyn_pc)
 
+    rays = cam.cam_ray
+    if window is not None:
+        rays = rays[..., window[1]:window[1] + window[3], window[0]:window[0] + window[2]]
+    rast = functools.partial(_raster, window=window)
+
     def decode(img10):
-        return sandwich(img10[..., :-1].permute(0, 3, 1, 2), cam.cam_ray, w1, w2).squeeze(0)
+        return sandwich(img10[..., :-1].permute(0, 3, 1, 2), rays, w1, w2).squeeze(0)
 
     out = {k: None for k in ("s_render", "s_depth", "d_render", "d_depth", "d_alpha", "d_means3d",
                              "s_alpha", "blending_factor", "world_coordinates", "splat_center",
                              "ori_flow", "ori_coord_map", "labels", "centroids")}
     if get_dynamic:
-        d_img, _, _ = _raster(d_means, d_quats, d_scales, d_opac, d_cols, bg9[None], viewmat, K, cam, "RGB+ED")
+        d_img, _, _ = rast(d_means, d_quats, d_scales, d_opac, d_cols, bg9[None], viewmat, K, cam, "RGB+ED")
         out["d_depth"] = d_img[..., -1]
         out["d_render"] = decode(d_img)
         ones = torch.ones(d_cols.shape[0], 1, dtype=like.dtype, device=like.device)
-        d_alpha, _, _ = _raster(d_means, d_quats, d_scales, d_opac, ones, bg9[0:1][None], viewmat, K, cam, "RGB")
+        d_alpha, _, _ = rast(d_means, d_quats, d_scales, d_opac, ones, bg9[0:1][None], viewmat, K, cam, "RGB")
         out["d_alpha"] = d_alpha[..., 0]
         out["d_means3d"] = d_means
 
@@ -161,7 +173,7 @@ def render_ref(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color, scaling_modifi
         ori_m2d = _project(torch.cat([s_means, o_means], 0), torch.cat([s_quats, o_quats], 0),
                            scales, viewmat, K, cam)
 
-    img, _, info = _raster(means, quats, scales, opac, cols, bg9[None], viewmat, K, cam, "RGB+ED")
+    img, _, info = rast(means, quats, scales, opac, cols, bg9[None], viewmat, K, cam, "RGB+ED")
     depth = img[..., -1]
     radii = info["radii"].squeeze(0)
     if info["means2d"].requires_grad:
@@ -169,19 +181,22 @@ def render_ref(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color, scaling_modifi
     rendered = decode(img)
 
     if get_static:
-        s_img, _, _ = _raster(s_means, s_quats, s_scales, s_opac, s_cols, bg9[None], viewmat, K, cam, "RGB+ED")
+        s_img, _, _ = rast(s_means, s_quats, s_scales, s_opac, s_cols, bg9[None], viewmat, K, cam, "RGB+ED")
         # reference quirk kept (renderer :250): s_depth is the last *column* of the decoded RGB
         out["s_depth"] = rendered[..., -1]
         out["s_render"] = decode(s_img)
         ones = torch.ones(s_cols.shape[0], 1, dtype=like.dtype, device=like.device)
-        s_alpha, _, _ = _raster(s_means, s_quats, s_scales, s_opac, ones, bg9[0:1][None], viewmat, K, cam, "RGB")
+        s_alpha, _, _ = rast(s_means, s_quats, s_scales, s_opac, ones, bg9[0:1][None], viewmat, K, cam, "RGB")
         out["s_alpha"] = s_alpha[..., 0]
 
     if want_flow:
         flow_2d = (ori_m2d - info["means2d"].clone().detach()).squeeze(0)
-        rendered_flow, _, _ = _raster(means, quats, scales, opac, flow_2d, None, viewmat, K, cam, "RGB")
+        rendered_flow, _, _ = rast(means, quats, scales, opac, flow_2d, None, viewmat, K, cam, "RGB")
         out["ori_flow"] = rendered_flow
-        out["ori_coord_map"] = _pixel_grid(cam, rendered_flow) + rendered_flow
+        grid = _pixel_grid(cam, rendered_flow)
+        if window is not None:
+            grid = grid[window[1]:window[1] + window[3], window[0]:window[0] + window[2]]
+        out["ori_coord_map"] = grid + rendered_flow
 
     out.update({
         "render": rendered, "viewspace_points": info["means2d"], "visibility_filter": radii > 0,

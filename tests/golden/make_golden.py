@@ -249,7 +249,7 @@ def make_flow_warp_golden(out_dir):
         return c.contiguous().requires_grad_(True)
 
     e2m_leaf, m2e_leaf = coords(), coords()
-    ori_image_tensor = torch.rand(B, 3, H, W, generator=g)
+    ori_image_tensor = torch.rand(B, 3, H, W, generator=g).requires_grad_(True)   # live in train.py (:469, :607)
     latent_leaf = torch.rand(B, K, 3, H, W, generator=g).requires_grad_(True)
     la_leaf = torch.rand(B, K, 1, H, W, generator=g).requires_grad_(True)
     da_leaf = torch.rand(B, 1, H, W, generator=g).requires_grad_(True)
@@ -274,7 +274,7 @@ def make_flow_warp_golden(out_dir):
     blob = {"ori": _np(ori_image_tensor), "latent": _np(latent_leaf), "exp2mid": _np(e2m_leaf), "mid2exp": _np(m2e_leaf),
             "latent_alpha": _np(la_leaf), "d_alpha": _np(da_leaf), "loss": _np(flow_loss),
             "g_latent": _np(latent_leaf.grad), "g_exp2mid": _np(e2m_leaf.grad), "g_mid2exp": _np(m2e_leaf.grad),
-            "g_latent_alpha": _np(la_leaf.grad), "g_d_alpha": _np(da_leaf.grad)}
+            "g_latent_alpha": _np(la_leaf.grad), "g_d_alpha": _np(da_leaf.grad), "g_ori": _np(ori_image_tensor.grad)}
     np.savez_compressed(os.path.join(out_dir, "flow_warp_loss.npz"), **blob)
     print("wrote flow_warp_loss", float(flow_loss))
 

@@ -1,6 +1,6 @@
 """f1 (second half) parity: mobgs_b200.losses.flow_warp_loss (mobgs_flow_warp_loss_fwd / _bwd) against the
 golden written from train.py:656-676 with the reference's own l1_loss, and against oracle.loss_ref on seeded
-inputs.  Tolerance (fp32, written here): 1e-5 relative on the loss, 1e-4 of the max magnitude on gradients
+inputs — gradients of every input, `ori_image_tensor` included (live in the reference, train.py:469, :607).  Tolerance (fp32, written here): 1e-5 relative on the loss, 1e-4 of the max magnitude on gradients
 (north_star: 1e-4 abs / 1e-3 rel); at most 1e-3 of the coordinate-gradient elements may differ more — a
 sample position that lands within rounding of a pixel boundary picks the other bilinear cell."""
 import os
@@ -11,7 +11,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "flow_warp_loss.npz")
-KEYS = ("latent", "exp2mid", "mid2exp", "latent_alpha", "d_alpha")
+KEYS = ("ori", "latent", "exp2mid", "mid2exp", "latent_alpha", "d_alpha")
 
 
 def _check_grads(got, ref):
@@ -24,7 +24,7 @@ def _check_grads(got, ref):
 
 def _run_ours(t, up=1.0):
     from mobgs_b200.losses import flow_warp_loss
-    c = {k: v.clone().cuda().requires_grad_(k != "ori") for k, v in t.items()}
+    c = {k: v.clone().cuda().requires_grad_(True) for k, v in t.items()}
     loss = flow_warp_loss(c["ori"], c["latent"], c["exp2mid"], c["mid2exp"], c["latent_alpha"], c["d_alpha"])
     (loss * up).backward()
     return float(loss), {k: c[k].grad.cpu().numpy() for k in KEYS}
@@ -32,7 +32,7 @@ def _run_ours(t, up=1.0):
 
 def test_flow_warp_loss_matches_reference_golden():
     z = np.load(GOLD)
-    t = {k: torch.from_numpy(z[k]) for k in ("ori",) + KEYS}
+    t = {k: torch.from_numpy(z[k]) for k in KEYS}
     loss, grads = _run_ours(t)
     assert abs(loss - float(z["loss"])) <= 1e-5 * abs(float(z["loss"]))
     _check_grads(grads, {k: z["g_" + k] for k in KEYS})
@@ -49,7 +49,7 @@ def test_flow_warp_loss_matches_oracle(B, K, H, W):
          "mid2exp": (base + 2.0 * torch.randn(B, K, H, W, 2, generator=g)).contiguous(),
          "latent_alpha": torch.rand(B, K, 1, H, W, generator=g), "d_alpha": torch.rand(B, 1, H, W, generator=g)}
     t["d_alpha"][:, :, :1] = 0.0                       # masked-out pixels
-    o = {k: v.clone().requires_grad_(k != "ori") for k, v in t.items()}
+    o = {k: v.clone().requires_grad_(True) for k, v in t.items()}
     ref = L.flow_warp_loss(o["ori"], o["latent"], o["exp2mid"], o["mid2exp"], o["latent_alpha"], o["d_alpha"])
     (ref * 0.7).backward()
     loss, grads = _run_ours(t, up=0.7)

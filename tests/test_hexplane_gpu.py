@@ -105,3 +105,35 @@ def test_native_feature_gather_and_vjp_match_grid_sample():
     flat0 = [p for level in grids for p in level]
     for i, (g, p0) in enumerate(zip(g_planes, flat0)):
         _cmp(g, p0.grad, f"g_plane{i}", atol=1e-5 * max(1.0, float(p0.grad.abs().max())))
+
+
+def test_fused_adam_step_invalidates_the_packed_operand_cache():
+    """FusedAdam writes parameters through raw pointers; the packed TF32 weights /
+    channels-last planes of the fused forward are cached on (tensor, version), so the step must bump the
+    version.  forward -> FusedAdam.step -> forward has to see the new weights (compared with the oracle
+    on the updated module)."""
+    from mobgs_b200.deformation import HexPlaneMLP
+    from mobgs_b200.optim import FusedAdam
+    from oracle.hexplane_ref import deform_forward_ref
+    torch.manual_seed(11)
+    net = HexPlaneMLP(_hexplane_args(16)).cuda()
+    net.set_aabb([1.3, 1.1, 1.2], [-1.2, -1.0, -1.4])
+    n = 300
+    ins = [torch.rand(n, 3, device="cuda") * 2 - 1, torch.randn(n, 3, device="cuda") * 0.3 - 3,
+           torch.randn(n, 4, device="cuda"), torch.rand(n, 1, device="cuda")]
+    params = [p for p in net.parameters() if p.requires_grad]
+    opt = FusedAdam(params, lr=5e-2, eps=1e-15)
+    v0 = [p._version for p in params]
+    p0, s0, r0 = net(*ins)
+    (p0.sum() + s0.sum() + r0.sum()).backward()
+    opt.step()
+    assert all(p._version > v for p, v in zip(params, v0) if p.grad is not None)
+    with torch.no_grad():
+        got = net(*ins)
+        ref_net = HexPlaneMLP(_hexplane_args(16))
+        ref_net.load_state_dict({k: v.cpu() for k, v in net.state_dict().items()})
+        ref_net.set_aabb([1.3, 1.1, 1.2], [-1.2, -1.0, -1.4])
+        want = deform_forward_ref(ref_net, *[t.cpu() for t in ins])
+    assert (got[0] - p0.detach()).abs().max() > 1e-3          # the step moved the output ...
+    for g, w, name in zip(got, want, ("pts", "scales", "rots")):
+        _cmp(g, w, name)                                      # ... to what the updated weights give
