@@ -1,0 +1,133 @@
+"""Parity at BASELINE's full size (1 M Gaussians, 1920x1080), forward AND backward, against the oracle.
+
+The dense oracle cannot render a 1 M-Gaussian 1080p frame, but it can render any tile-aligned WINDOW of it
+exactly (oracle.gsplat_ref.rasterize_to_pixels(window=): all Gaussians are projected, only those whose tile
+AABB touches the window enter the dense per-pixel arithmetic — per pixel the candidate sequence of the
+full-frame render).  The CUDA path renders the full frame (K-batched fused chain, the bench.py step); the loss
+is a random-weighted sum of the blurred prediction, the expected depths and the alphas INSIDE the windows, so
+its gradient reaches exactly the Gaussians the windows see.  Compared: window crops of image / depth / alpha
+and every parameter gradient (per-Gaussian tensors, decoder weights, view matrices).
+
+Tolerance (north_star): 1e-4 abs / 1e-3 rel, the absolute part scaled by the tensor's max for gradients.
+Elements outside it are allowed ONLY where a discrete decision of the rasteriser sits on its threshold
+(alpha = 1/255, alpha = 0.999, T = 1e-4, ceil of the 3-sigma radius — oracle.bench_ref.threshold_events /
+radius_on_threshold; margins: alpha within 1e-4 relative of its threshold — the projected conic / mean of the two
+implementations differ by ~1e-6 relative, which sigma <= 5.5 turns into ~1e-5 on alpha — and T within 5e-4):
+every outlier pixel must be such a pixel, every outlier Gaussian a candidate at one, and there may be at most
+1e-3 of the pixels / 3e-3 of the touched Gaussians.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+NS, ND, W, H, K = 700_000, 300_000, 1920, 1080, 3
+WINDOWS = [(928, 512, 64, 64), (0, 0, 64, 64), (1856, 1024, 64, 56), (320, 784, 96, 32)]
+
+
+def _outliers(got, want, atol, rtol):
+    got, want = got.detach().cpu().double(), want.detach().cpu().double()
+    return (got - want).abs() > atol + rtol * want.abs()
+
+
+@pytest.mark.timeout(900)
+def test_full_size_windows_forward_and_backward_match_oracle():
+    from mobgs_b200.cameras import camera_rays_from_w2c
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    from mobgs_b200.subframes import render_subframes
+    from oracle import bench_ref as B
+    from oracle import mobgs_ref as M
+
+    so, do, intr = synthetic_scene(NS, ND, W, H, seed=1234)
+    sc, dc, _ = synthetic_scene(NS, ND, W, H, seed=1234, device="cuda")
+    bg = torch.tensor([0.05, 0.1, 0.15])
+    deltas = (torch.linspace(-1, 1, K) * 0.4).tolist()
+    g = torch.Generator().manual_seed(9)
+    wts = [(torch.rand(3, h, w, generator=g) * 2 - 1, torch.rand(K, h, w, generator=g) * 0.2 - 0.1,
+            torch.rand(K, h, w, generator=g) * 0.2 - 0.1) for (_, _, w, h) in WINDOWS]
+
+    # ---------------- oracle: project once per sub-frame, rasterise the windows ----------------
+    view_o = torch.stack([subframe_w2c(k, K) for k in range(K)]).requires_grad_(True)
+    cams = [make_camera(intr, view_o[k]) for k in range(K)]
+    geo = B.project_subframes(so, do, cams, deltas)
+    loss_o = 0.0
+    crops = []
+    for win, (w_rgb, w_dep, w_alp) in zip(WINDOWS, wts):
+        rgb, dep, alp = B.render_window(geo, cams, do, bg, win)
+        pred = M.blur_mean(list(rgb))
+        loss_o = loss_o + (pred * w_rgb).sum() + (dep * w_dep).sum() + (alp * w_alp).sum()
+        crops.append((pred.detach(), dep.detach(), alp.detach()))
+    loss_o.backward()
+
+    # where two correct fp32 implementations may legitimately differ
+    flips, affected = [], torch.zeros(NS + ND, dtype=torch.bool)
+    for win in WINDOWS:
+        fw = torch.zeros(win[3], win[2], dtype=torch.bool)
+        for k in range(K):
+            f, a = B.threshold_events(geo[k], W, H, win, rel_alpha=1e-4, rel_T=5e-4)
+            fw |= f
+            affected |= a
+        flips.append(fw)
+    with torch.no_grad():
+        for k in range(K):
+            means = torch.cat([M.static_attributes(so)[0], M.dynamic_attributes(do, torch.tensor(0.5 + deltas[k] / 23), True)[0]])
+            quats = torch.cat([M.static_attributes(so)[1], M.dynamic_attributes(do, torch.tensor(0.5 + deltas[k] / 23), True)[1]])
+            scales = torch.cat([so.get_scaling, do.get_scaling])
+            affected |= B.radius_on_threshold(means, quats, scales, view_o[k].detach(), cams[k].K, W, H)
+
+    # ---------------- CUDA: the full frame through the fused K-batched chain ----------------
+    view_c = view_o.detach().cuda().requires_grad_(True)
+    t_poly = torch.tensor([0.5 + d / 23 for d in deltas]).cuda()
+    rays = camera_rays_from_w2c(view_c, intr.fx, intr.fy, intr.cx, intr.cy, W, H)
+    out = render_subframes(sc, dc, view_c, cams[0].K.cuda(), t_poly.clamp(0, 1), t_poly, rays, bg.cuda(), W, H)
+    Wr, Wd, Wa = torch.zeros(3, H, W), torch.zeros(K, H, W), torch.zeros(K, H, W)
+    for (x0, y0, w, h), (w_rgb, w_dep, w_alp) in zip(WINDOWS, wts):
+        Wr[:, y0:y0 + h, x0:x0 + w], Wd[:, y0:y0 + h, x0:x0 + w], Wa[:, y0:y0 + h, x0:x0 + w] = w_rgb, w_dep, w_alp
+    loss_c = (out["render"] * Wr.cuda()).sum() + (out["depth"] * Wd.cuda()).sum() + (out["alpha"] * Wa.cuda()).sum()
+    loss_c.backward()
+    torch.cuda.synchronize()
+
+    # ---------------- forward: window crops ----------------
+    n_px = n_bad_px = 0
+    for (x0, y0, w, h), (pred, dep, alp), fw in zip(WINDOWS, crops, flips):
+        got_rgb = out["render"].detach()[:, y0:y0 + h, x0:x0 + w]
+        got_dep = out["depth"].detach()[:, y0:y0 + h, x0:x0 + w]
+        got_alp = out["alpha"].detach()[:, y0:y0 + h, x0:x0 + w]
+        bad = _outliers(got_rgb, pred, 1e-4, 1e-3).any(0) | _outliers(got_dep, dep, 1e-4, 1e-3).any(0) \
+            | _outliers(got_alp, alp, 1e-4, 1e-3).any(0)
+        assert not (bad & ~fw).any(), ("image outlier away from every threshold", (x0, y0), int((bad & ~fw).sum()))
+        n_px += bad.numel()
+        n_bad_px += int(bad.sum())
+    assert n_bad_px <= 1e-3 * n_px, (n_bad_px, n_px)
+
+    # ---------------- backward: per-Gaussian gradients ----------------
+    pairs = [("_xyz", so, sc, 0), ("_rotation", so, sc, 0), ("_scaling", so, sc, 0), ("_opacity", so, sc, 0),
+             ("_features_dc", so, sc, 0), ("control_xyz", do, dc, NS), ("_rotation", do, dc, NS), ("_omega", do, dc, NS),
+             ("_scaling", do, dc, NS), ("_opacity", do, dc, NS), ("_features_dc", do, dc, NS), ("_features_t", do, dc, NS)]
+    checked = 0
+    for name, po, pc, off in pairs:
+        go, gc = getattr(po, name).grad, getattr(pc, name).grad
+        assert go is not None and gc is not None, name
+        n = go.shape[0]
+        scale = float(go.abs().max())
+        assert scale > 0, name
+        bad = _outliers(gc, go, 1e-4 * scale, 1e-3).reshape(n, -1).any(1)
+        live = (go.reshape(n, -1) != 0).any(1)
+        stray = bad & ~affected[off:off + n]
+        assert not stray.any(), (name, "gradient outlier at a Gaussian that touches no threshold", int(stray.sum()),
+                                 float((gc.cpu() - go).abs().reshape(n, -1)[stray].max()), scale)
+        assert int(bad.sum()) <= max(2, 3e-3 * int(live.sum())), (name, int(bad.sum()), int(live.sum()))
+        # the Gaussians the windows do not see get exactly nothing
+        assert not ((gc.cpu().reshape(n, -1) != 0).any(1) & ~live & ~affected[off:off + n]).any(), name
+        checked += int(live.sum())
+    assert checked > 20_000       # the windows really exercised the per-Gaussian backward
+
+    # ---------------- backward: shared tensors ----------------
+    for po, pc in zip(do.rgbdecoder.parameters(), dc.rgbdecoder.parameters()):
+        scale = float(po.grad.abs().max())
+        assert not _outliers(pc.grad, po.grad, 2e-3 * scale, 2e-3).any(), "decoder weights"
+    scale = float(view_o.grad[:, :3].abs().max())
+    assert not _outliers(view_c.grad[:, :3], view_o.grad[:, :3], 2e-3 * scale, 2e-3).any(), \
+        ("view matrices", view_c.grad[:, :3].cpu(), view_o.grad[:, :3])
