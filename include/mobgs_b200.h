@@ -185,6 +185,11 @@ typedef struct {
   int32_t rec_k[MOBGS_MAX_K];
   int32_t g_begin[MOBGS_MAX_K];
   int32_t g_end[MOBGS_MAX_K];
+  /* Blend kernels only: list k walks the tile lists that binning produced for its list
+   * tile_list[k] (identity = k).  Lists with the same geometry and index range but different
+   * colour payloads (the mid-time flow renders of get_flow, gaussian_renderer/__init__.py:456)
+   * are binned and sorted ONCE and share the result.  The binning entry points ignore it. */
+  int32_t tile_list[MOBGS_MAX_K];
 } MobgsLists;
 
 /* ------------------------------------------------------------------------------------------
@@ -251,6 +256,13 @@ typedef struct {
   const float* dec_w1; const float* dec_w2;
   float* out_rgb;
   float* out_depth;
+  /* Optional fused flow channels (flow_ref >= 0; fused-epilogue launches only): two more channels are
+   * composited in the same walk, with per-Gaussian colour records[flow_ref][g].xy - records[rec_k][g].xy
+   * (the screen-space displacement between two projections of the same Gaussian — get_flow's
+   * exp2mid rasterisation, gaussian_renderer/__init__.py:426-441, which shares geometry and order with
+   * the latent image render :473) and no background.  out_flow [K,H,W,2]. */
+  int32_t flow_ref;
+  float* out_flow;
 } MobgsBlendFwd;
 int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
 
@@ -284,6 +296,10 @@ typedef struct {
   int32_t mean_K;             /* the mean is over the first mean_K lists (0 = all K) */
   float* v_rays;
   float* v_w_partial;
+  /* VJP of the fused flow channels: g_flow [K,H,W,2]; the colour gradient is added to
+   * v_records[flow_ref][g].xy and subtracted from v_records[rec_k][g].xy. */
+  int32_t flow_ref;
+  const float* g_flow;
 } MobgsBlendBwd;
 
 #define MOBGS_DEC_SLOTS 1024
@@ -394,6 +410,16 @@ typedef struct {
   float* v_records;              /* [K+1,N,16] */
 } MobgsFlowRecBwd;
 int mobgs_flow_records_bwd(const MobgsFlowRecBwd* a, void* stream);
+
+/* Mid-time flow records: the K mid2exp rasterisations of get_flow (gaussian_renderer/__init__.py:444-457,
+ * one per exposure offset in train.py:563-579) share the mid-time geometry and differ only in their two
+ * colour channels.  fwd packs all 2K channels, ten per record set, over the mid geometry:
+ * flow_records [M,N,16], M = ceil(2K/10); channel j = 2k + a (a: 0 = x, 1 = y) = means2d_exp_k[a] -
+ * means2d_mid[a] sits in set j/10, colour slot j%10 (unused slots 0).  The M sets are rendered as M lists
+ * that share ONE tile binning (MobgsLists.tile_list).  bwd (MobgsFlowRecBwd with v_flow_records [M,N,16])
+ * writes v_records [K+1,N,16]. */
+int mobgs_midflow_records_fwd(const MobgsFlowRecFwd* a, void* stream);
+int mobgs_midflow_records_bwd(const MobgsFlowRecBwd* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * HexPlane feature gather and its VJP as stand-alone kernels (the first stage of a11, used by the

@@ -116,14 +116,19 @@ class Pack(C.Structure):
 
 
 class Lists(C.Structure):
-    _fields_ = [("rec_k", C.c_int32 * MAX_K), ("g_begin", C.c_int32 * MAX_K), ("g_end", C.c_int32 * MAX_K)]
+    _fields_ = [("rec_k", C.c_int32 * MAX_K), ("g_begin", C.c_int32 * MAX_K), ("g_end", C.c_int32 * MAX_K),
+                ("tile_list", C.c_int32 * MAX_K)]
 
 
-def make_lists(specs):
-    """specs: [(record_set, g_begin, g_end)] per list"""
+def make_lists(specs, tile_list=None):
+    """specs: [(record_set, g_begin, g_end)] per list; tile_list[k] = index of the binned tile lists list k
+    walks (default identity)."""
+    if len(specs) > MAX_K:
+        raise RuntimeError(f"at most {MAX_K} lists per launch, got {len(specs)}")
     l = Lists()
     for i, (rk, g0, g1) in enumerate(specs):
         l.rec_k[i], l.g_begin[i], l.g_end[i] = int(rk), int(g0), int(g1)
+        l.tile_list[i] = i if tile_list is None else int(tile_list[i])
     return l
 
 
@@ -150,7 +155,8 @@ class BlendFwd(C.Structure):
                 ("sorted_ids", C.c_void_p), ("backgrounds", C.c_void_p), ("out_colors", C.c_void_p),
                 ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p),
                 ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
-                ("dec_w2", C.c_void_p), ("out_rgb", C.c_void_p), ("out_depth", C.c_void_p)]
+                ("dec_w2", C.c_void_p), ("out_rgb", C.c_void_p), ("out_depth", C.c_void_p),
+                ("flow_ref", C.c_int32), ("out_flow", C.c_void_p)]
 
 
 class BlendBwd(C.Structure):
@@ -163,7 +169,8 @@ class BlendBwd(C.Structure):
                 ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
                 ("dec_w2", C.c_void_p), ("out_colors", C.c_void_p), ("g_rgb", C.c_void_p),
                 ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p), ("g_mean", C.c_void_p),
-                ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p)]
+                ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p),
+                ("flow_ref", C.c_int32), ("g_flow", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):
@@ -270,6 +277,8 @@ ENTRY_POINTS = {
     "mobgs_hexplane_mlp_fwd": HexMlpFwd,
     "mobgs_flow_records_fwd": FlowRecFwd,
     "mobgs_flow_records_bwd": FlowRecBwd,
+    "mobgs_midflow_records_fwd": FlowRecFwd,
+    "mobgs_midflow_records_bwd": FlowRecBwd,
     "mobgs_hexplane_features_fwd": HexFeat,
     "mobgs_hexplane_features_bwd": HexFeat,
     "mobgs_adam_step": Adam,

@@ -127,6 +127,11 @@ __device__ __forceinline__ int build_unit_lists(const unsigned* smask, unsigned 
   return mine;
 }
 
+// first / one-past-last entry of the tile lists walked by CTA (list k, tile): lists may share a binning
+__device__ __forceinline__ int tile_segment(const MobgsLists& l, int k, int tiles, int tile) {
+  return l.tile_list[k] * tiles + tile;
+}
+
 __device__ __forceinline__ int lane_id() {
   int l;
   asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
@@ -170,9 +175,11 @@ __device__ __forceinline__ void unit_pixel(int tid, int& lx, int& ly) {
   ly = (u / kUX) * kUH + (q / kUW);
 }
 
-template <int D, bool DEC>
-__global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
+template <int D, bool DEC, bool FLOW = false>
+__global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 : MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
+  static_assert(!FLOW || (DEC && !MOBGS_FWD_PREDICATED), "fused flow channels ride the decode launch of the divergent body");
   __shared__ __align__(128) float4 srec[kBlendThreads][4];
+  __shared__ __align__(8) float2 sflow[FLOW ? kBlendThreads : 1];   // per staged entry: records[flow_ref][g].xy - own xy
   __shared__ unsigned smask[kBlendThreads];
   __shared__ __align__(8) unsigned char swl[kUnits][kBlendThreads + 8];   // +8: 8-byte loads of a warp's units differ in bank
   __shared__ __align__(16) float sdec[DEC ? 96 : 4];
@@ -196,10 +203,13 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
   const int cap = (int)min(a.list_capacity, (int64_t)0x7fffffff);
-  const int beg = min(a.tile_offsets[blockIdx.x], cap), end = min(a.tile_offsets[blockIdx.x + 1], cap);
+  const int seg = tile_segment(a.lists, k, tiles, tile);
+  const int beg = min(a.tile_offsets[seg], cap), end = min(a.tile_offsets[seg + 1], cap);
   const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
+  const float4* recs_ref = FLOW ? reinterpret_cast<const float4*>(a.records) + (size_t)a.flow_ref * a.N * 4 : nullptr;
 
   float T = 1.f;
+  float fl0 = 0.f, fl1 = 0.f;
   float pix[D];
 #pragma unroll
   for (int c = 0; c < D; ++c) pix[c] = 0.f;
@@ -213,21 +223,32 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
 #if MOBGS_TMA_STAGE
     constexpr uint32_t kRecBytes = D > 6 ? 64 : (D > 2 ? 48 : 32);
     if (tid == 0) mbar_expect_tx(&sbar, (uint32_t)bn * kRecBytes);
-    if (idx < end) bulk_g2s(&srec[tid][0], recs + (size_t)a.sorted_ids[idx] * 4, kRecBytes, &sbar);
+    float2 mref = make_float2(0.f, 0.f);
+    if (idx < end) {
+      const int g = a.sorted_ids[idx];
+      bulk_g2s(&srec[tid][0], recs + (size_t)g * 4, kRecBytes, &sbar);
+      if (FLOW) mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
+    }
     mbar_wait(&sbar, bar_phase);
     bar_phase ^= 1;
     if (idx < end) {
       smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
+      if (FLOW) sflow[tid] = make_float2(mref.x - srec[tid][0].x, mref.y - srec[tid][0].y);
       rescale_conic(reinterpret_cast<float*>(&srec[tid][0]));
     }
 #else
     if (idx < end) {
-      const float4* r = recs + (size_t)a.sorted_ids[idx] * 4;
+      const int g = a.sorted_ids[idx];
+      const float4* r = recs + (size_t)g * 4;
       const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
       srec[tid][0] = q0; srec[tid][1] = q1;
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
       smask[tid] = unit_mask(q0, q1, (float)(tx * kTile), (float)(ty * kTile));
+      if (FLOW) {
+        const float2 mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
+        sflow[tid] = make_float2(mref.x - q0.x, mref.y - q0.y);
+      }
       rescale_conic(reinterpret_cast<float*>(&srec[tid][0]));
     }
 #endif
@@ -308,6 +329,11 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
         if (D > 8) pix[8 % D] += r3.z * w;
         if (D > 9) pix[9 % D] += r3.w * w;
       }
+      if (FLOW) {
+        const float2 f = sflow[t];
+        fl0 += f.x * w;
+        fl1 += f.y * w;
+      }
       last_t = t;
       T = next_T;
       }
@@ -341,6 +367,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_FWD_MIN_CTAS) blend_fwd_k
 #pragma unroll
       for (int c = 0; c < 3; ++c) a.out_rgb[((size_t)k * 3 + c) * P + pp] = out[c];
       if (a.out_depth) a.out_depth[(size_t)k * P + pp] = v[9] / fmaxf(1.f - T, kEdFloor);
+      if (FLOW) *reinterpret_cast<float2*>(a.out_flow + ((size_t)k * P + pp) * 2) = make_float2(fl0, fl1);
     }
   }
 }
@@ -498,7 +525,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   const int ix = tx * kTile + lx, iy = ty * kTile + ly;
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
-  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
+  const int beg = min(a.tile_offsets[tile_segment(a.lists, k, tiles, tile)], (int)min(a.list_capacity, (int64_t)0x7fffffff));
   const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
   float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
 
@@ -731,9 +758,16 @@ constexpr int kTrScratch = kBwdBatch * kRecRow + kAccFloats + 8 * 2 * kBlk * kFR
 static_assert(kTrScratch >= 27 * kProPad, "prologue scratch must fit the aliased buffers");
 constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
 
-template <int D, bool DEC>
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// FLOW: two more colour channels per entry, (records[flow_ref][g].xy - own xy), parked in floats 16..17 of the
+// staged row (rows are 20 floats, the TMA copy fills 16); their pixel gradients g_flow sit in slots 10..11 of sV.
+template <int D, bool DEC, bool FLOW = false>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_tr_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   static_assert(kUL == 16, "transposing backward is written for 4x4-pixel units");
+  static_assert(!FLOW || (D == 10 && MOBGS_BWD_DIRECT_RED), "fused flow channels need the D = 10 layout and direct reductions");
   extern __shared__ __align__(128) float smem[];
   float* srec = smem;                                            // [kBwdBatch][kRecRow]   (TMA destination)
   float* sacc = srec + kBwdBatch * kRecRow;                      // [kBwdBatch][kAccRow]
@@ -763,15 +797,28 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   const int ix = tx * kTile + lx, iy = ty * kTile + ly;
   const bool inside = ix < a.width && iy < a.height;
   const float px = ix + 0.5f, py = iy + 0.5f;
-  const int beg = min(a.tile_offsets[blockIdx.x], (int)min(a.list_capacity, (int64_t)0x7fffffff));
+  const int beg = min(a.tile_offsets[tile_segment(a.lists, k, tiles, tile)], (int)min(a.list_capacity, (int64_t)0x7fffffff));
   const float4* recs = reinterpret_cast<const float4*>(a.records) + (size_t)a.lists.rec_k[k] * a.N * 4;
   float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
+  const float4* recs_ref = FLOW ? reinterpret_cast<const float4*>(a.records) + (size_t)a.flow_ref * a.N * 4 : nullptr;
+  float* v_recs_ref = FLOW ? a.v_records + (size_t)a.flow_ref * a.N * kRecFloats : nullptr;
 
   float T_final, v_a, bg_dot = 0.f;
   float v_c[D];
   int last;
   bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, smem, smem + 12 * kProPad, sdec, swg,
                              T_final, last, v_c, v_a);
+  float v_fl0 = 0.f, v_fl1 = 0.f;
+  if (FLOW && inside) {
+    const float2 gf = __ldg(reinterpret_cast<const float2*>(a.g_flow + (((size_t)k * a.height + iy) * a.width + ix) * 2));
+    v_fl0 = gf.x; v_fl1 = gf.y;
+  }
+  // a tile none of whose pixels receives a gradient contributes exactly nothing (every term of the VJP is linear
+  // in v_c / v_a): it leaves after the prologue.  This is what makes a second backward pass through the same
+  // render cheap when the second loss touches few of its images (train.py:629 then :680).
+  bool px_zero = v_a == 0.f && v_fl0 == 0.f && v_fl1 == 0.f;
+#pragma unroll
+  for (int c = 0; c < D; ++c) px_zero = px_zero && v_c[c] == 0.f;
   if (inside && a.backgrounds) {
     const float* bg = a.backgrounds + (size_t)k * D;
 #pragma unroll
@@ -784,6 +831,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     float t12[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) t12[c] = c < D ? v_c[c % D] : 0.f;
+    if (FLOW) { t12[10] = v_fl0; t12[11] = v_fl1; }
 #pragma unroll
     for (int c = 0; c < 12; c += 4)
       if (c < D) *reinterpret_cast<float4*>(vp + c) = make_float4(t12[c], t12[c + 1], t12[c + 2], t12[c + 3]);
@@ -798,9 +846,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, 16));
   if (lane == 0) warp_max[warp] = wmax;
   fence_proxy_async();                     // the prologue's generic-proxy scratch writes precede the TMA writes to srec
-  __syncthreads();                         // prologue scratch is free, sV / swg / warp_max are complete
+  const int tile_zero = __syncthreads_and(px_zero);   // prologue scratch is free, sV / swg / warp_max are complete
   if (DEC && tid < 90 && swg[tid] != 0.f)
     atomicAdd(a.v_w_partial + (size_t)(blockIdx.x % MOBGS_DEC_SLOTS) * 90 + tid, swg[tid]);
+  if (tile_zero) return;
   int tile_last = -1;
 #pragma unroll
   for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
@@ -821,10 +870,12 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     const int bn = hi - lo + 1;
     __syncthreads();   // previous batch fully flushed
     if (tid == 0) mbar_expect_tx(sbar, (uint32_t)bn * kRecBytes);
+    float2 mref = make_float2(0.f, 0.f);
     if (tid < bn) {
       const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
       sid[tid] = g;
       bulk_g2s(srec + tid * kRecRow, recs + (size_t)g * 4, kRecBytes, sbar);
+      if (FLOW) mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
     }
     for (int i = tid; i < kAccFloats; i += kBlendThreads) sacc[i] = 0.f;
     mbar_wait(sbar, bar_phase);
@@ -832,6 +883,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     if (tid < bn) {
       const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecRow);
       smask[tid] = unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
+      if (FLOW) *reinterpret_cast<float2*>(srec + tid * kRecRow + 16) = make_float2(mref.x - r[0].x, mref.y - r[0].y);
       rescale_conic(srec + tid * kRecRow);
     }
     __syncthreads();
@@ -866,6 +918,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         float d = 0.f;
 #pragma unroll
         for (int c = 0; c < D; ++c) d += rec_color(r1, r2, r3, c) * v_c[c];
+        if (FLOW) {
+          const float2 f = *reinterpret_cast<const float2*>(srec + t * kRecRow + 16);
+          d += f.x * v_fl0 + f.y * v_fl1;
+        }
         const float v_alpha = d * T + (tf_term - S) * ra;
         S += d * fac;
         const float ov = r0.z * (valid ? vis : 0.f);             // (sigma < 0 lanes may hold vis = inf)
@@ -876,6 +932,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
       __syncwarp();
       // ---- Phase B: lane = (entry pj of the block, pixel half ph) of its unit
       float acc[16];
+      float accf0 = 0.f, accf1 = 0.f;         // FLOW: the two flow-colour gradient sums
 #pragma unroll
       for (int c = 0; c < 16; ++c) acc[c] = 0.f;
       const bool on = pj < nb && base + pj < cnt;
@@ -921,6 +978,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
             const float4 v2 = vp[2];
             acc[14] += fv[pp] * v2.x;
             if (D > 9) acc[15] += fv[pp] * v2.y;
+            if (FLOW) { accf0 += fv[pp] * v2.z; accf1 += fv[pp] * v2.w; }
           }
         }
       }
@@ -930,6 +988,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         const float send = ph ? acc[i] : acc[i + 8];
         const float keep = ph ? acc[i + 8] : acc[i];
         acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      if (FLOW) {
+        accf0 += __shfl_xor_sync(0xffffffffu, accf0, 8);
+        accf1 += __shfl_xor_sync(0xffffffffu, accf1, 8);
       }
 #if MOBGS_BWD_DIRECT_RED
       if (on) {
@@ -949,6 +1011,12 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
           if (a.v_means2d_sep && k == a.sep_list && (acc[0] != 0.f || acc[1] != 0.f)) {
             atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tb], acc[0]);
             atomicAdd(a.v_means2d_sep + 2 * (size_t)sid[tb] + 1, acc[1]);
+          }
+          if (FLOW) {
+            // flow colour = ref.xy - own.xy: its gradient goes to the reference record's mean and, negated, to this one's
+            acc[0] -= accf0;
+            acc[1] -= accf1;
+            if (accf0 != 0.f || accf1 != 0.f) red_add_v2(v_recs_ref + (size_t)sid[tb] * kRecFloats, accf0, accf1);
           }
         }
         constexpr int kVec = (6 + D + 3) / 4;     // 16-byte chunks of the gradient record in use
@@ -1009,17 +1077,18 @@ static void launch_fwd(const MobgsBlendFwd& a, int tiles_x, int tiles_y, cudaStr
 #ifndef MOBGS_BWD_TRANSPOSE
 #define MOBGS_BWD_TRANSPOSE 1
 #endif
-template <int D, bool DEC>
+template <int D, bool DEC, bool FLOW = false>
 static void launch_bwd_kernel(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
 #if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16
   static bool configured = false;   // per instantiation; the attribute is idempotent, a race only repeats the call
   if (!configured) {
-    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrSmemBytes);
-    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrSmemBytes);
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
-  blend_bwd_tr_kernel<D, DEC><<<a.K * tiles_x * tiles_y, kBlendThreads, kTrSmemBytes, s>>>(a, tiles_x, tiles_y);
+  blend_bwd_tr_kernel<D, DEC, FLOW><<<a.K * tiles_x * tiles_y, kBlendThreads, kTrSmemBytes, s>>>(a, tiles_x, tiles_y);
 #else
+  static_assert(!FLOW, "fused flow channels need the transposing backward");
   blend_bwd_kernel<D, DEC><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
 #endif
 }
@@ -1051,9 +1120,19 @@ extern "C" int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream) {
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
   if (a->dec_rays) {
     MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_rgb, "fused decode epilogue needs D=10, w1, w2, out_rgb");
+    if (a->out_flow) {
+#if !MOBGS_FWD_PREDICATED
+      MOBGS_REQUIRE(a->flow_ref >= 0, "flow_ref must name a record set");
+      blend_fwd_kernel<10, true, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+      return check_launch("blend_decode_flow_fwd");
+#else
+      MOBGS_REQUIRE(false, "fused flow channels are not built into the predicated ablation build");
+#endif
+    }
     blend_fwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
     return check_launch("blend_decode_fwd");
   }
+  MOBGS_REQUIRE(!a->out_flow, "fused flow channels need the fused decode epilogue (dec_rays)");
   MOBGS_DISPATCH_D(a->D, launch_fwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
   return check_launch("blend_fwd");
 }
@@ -1069,9 +1148,19 @@ extern "C" int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream) {
   if (a->dec_rays) {
     MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_colors && a->v_w_partial,
                   "fused decode prologue needs D=10, w1, w2, out_colors, v_w_partial");
+    if (a->g_flow) {
+#if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16 && MOBGS_BWD_DIRECT_RED
+      MOBGS_REQUIRE(a->flow_ref >= 0, "flow_ref must name a record set");
+      launch_bwd_kernel<10, true, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+      return check_launch("blend_decode_flow_bwd");
+#else
+      MOBGS_REQUIRE(false, "fused flow channels need the transposing backward build");
+#endif
+    }
     launch_bwd_kernel<10, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
     return check_launch("blend_decode_bwd");
   }
+  MOBGS_REQUIRE(!a->g_flow, "fused flow channels need the fused decode prologue (dec_rays)");
   MOBGS_REQUIRE(a->v_out_colors, "v_out_colors must not be NULL");
   MOBGS_DISPATCH_D(a->D, launch_bwd, *a, tiles_x, tiles_y, (cudaStream_t)stream);
   return check_launch("blend_bwd");

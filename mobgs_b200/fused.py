@@ -109,7 +109,7 @@ def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_sp
 
 class _BlendRecords(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, specs, tight, vsp_list):
+    def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, specs, tight, vsp_list, tile_list=None):
         records = _f32c(records)
         Kr, N = radii.shape
         dev = records.device
@@ -125,7 +125,8 @@ class _BlendRecords(torch.autograd.Function):
             L.call("mobgs_blend_fwd", a, _stream())
             return out_c, out_a, last
 
-        lists, (out_c, out_a, last) = build_tile_lists(records, radii, depths, width, height, tight, specs, consume=blend)
+        lists, (out_c, out_a, last) = build_tile_lists(records, radii, depths, width, height, tight, specs, consume=blend,
+                                                       tile_list=tile_list)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
         ctx.meta = (K, Kr, N, D, width, height, vsp_list, vsp is not None)
@@ -145,23 +146,25 @@ class _BlendRecords(torch.autograd.Function):
         a = L.BlendBwd(K, N, D, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
         L.call("mobgs_blend_bwd", a, _stream())
-        return v_rec, None, None, None, v_vsp, None, None, None, None, None, None
+        return v_rec, None, None, None, v_vsp, None, None, None, None, None, None, None
 
 
 def blend_records(records, radii, depths, backgrounds, D, width, height, specs=None, g_range=None, tight=True,
-                  vsp: Optional[torch.Tensor] = None, vsp_k: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                  vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, tile_list=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """-> (colors [K,H,W,D] incl. background, alphas [K,H,W]) for K lists.
 
     specs: [(record_set, g_begin, g_end)] per list (default: one full-range list per record set;
     `g_range=(g0, g1)` is shorthand for restricting every record set to one range).
     `vsp` is an optional leaf [1,N,2] that receives d loss / d means2d of list `vsp_k` as its .grad
-    (densification statistics, reference train.py:634-648)."""
+    (densification statistics, reference train.py:634-648).  `tile_list`: lists naming the same value share one
+    tile binning / sort (same geometry and range, different colours; ops.build_tile_lists)."""
     if specs is None and g_range is not None:
         specs = [(k, g_range[0], g_range[1]) for k in range(radii.shape[0])]
     if specs is not None:
         specs = tuple(tuple(int(v) for v in s) for s in specs)
     out_c, out_a, _ = _BlendRecords.apply(records, radii, depths, backgrounds, vsp, int(D), int(width),
-                                          int(height), specs, bool(tight), int(vsp_k))
+                                          int(height), specs, bool(tight), int(vsp_k),
+                                          None if tile_list is None else tuple(int(t) for t in tile_list))
     return out_c, out_a
 
 
@@ -218,7 +221,7 @@ class _BlendDecode(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
-                vsp_list, want_mean, mean_K=0):
+                vsp_list, want_mean, mean_K=0, flow_ref=-1):
         records = _f32c(records)
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
@@ -242,14 +245,15 @@ class _BlendDecode(torch.autograd.Function):
             last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
             rgb = torch.empty(K, 3, height, width, device=dev)
             depth = torch.empty(K, height, width, device=dev)
+            flow = torch.empty(K, height, width, 2, device=dev) if flow_ref >= 0 else None
             a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
                            _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
-                           _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth))
+                           _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth), max(flow_ref, 0), _p(flow))
             L.call("mobgs_blend_fwd", a, _stream())
-            return img10, alpha, last, rgb, depth
+            return img10, alpha, last, rgb, depth, flow
 
-        lists, (img10, alpha, last, rgb, depth) = build_tile_lists(records, radii, depths, width, height, tight,
-                                                                   specs, consume=blend)
+        lists, (img10, alpha, last, rgb, depth, flow) = build_tile_lists(records, radii, depths, width, height, tight,
+                                                                         specs, consume=blend)
         if want_mean:
             mean = torch.empty(3, height, width, device=dev)
             L.subframe_mean(_p(rgb), _p(mean), mK, 3 * height * width, _stream())
@@ -258,14 +262,21 @@ class _BlendDecode(torch.autograd.Function):
             ctx.mark_non_differentiable(mean)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
-        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK)
+        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK, flow_ref)
         ctx.n_isect = lists.n_isect
-        return rgb, depth, alpha, mean
+        if flow is None:
+            flow = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(flow)
+        return rgb, depth, alpha, mean, flow
 
     @staticmethod
-    def backward(ctx, g_rgb, g_depth, g_alpha, g_mean):
+    def backward(ctx, g_rgb, g_depth, g_alpha, g_mean, g_flow):
         records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2 = ctx.saved_tensors
-        K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK = ctx.meta
+        K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK, flow_ref = ctx.meta
+        if flow_ref >= 0:
+            g_flow = _f32c(g_flow) if g_flow is not None else torch.zeros(K, height, width, 2, device=records.device)
+        else:
+            g_flow = None
         dev = records.device
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
         g_depth = _f32c(g_depth) if g_depth is not None else None
@@ -280,22 +291,28 @@ class _BlendDecode(torch.autograd.Function):
         a = L.BlendBwd(K, N, 10, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
                        _p(rays), per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth), _p(g_alpha), _p(g_mean),
-                       mK, _p(v_rays), _p(v_wp))
+                       mK, _p(v_rays), _p(v_wp), max(flow_ref, 0), _p(g_flow))
         L.call("mobgs_blend_bwd", a, _stream())
         v_w = v_wp.sum(0)
         return (v_rec, None, None, None, v_vsp, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6),
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, height, specs=None, tight=True,
-                 vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False, mean_K: int = 0):
-    """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty).
+                 vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False, mean_K: int = 0,
+                 flow_ref: Optional[int] = None):
+    """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty[, flow [K,H,W,2]]).
     rays: [1,6,H,W] shared, [K,6,H,W] per list, or [record sets,6,H,W] per projection.
-    mean_K: the blur mean is taken over the first mean_K lists (0 = all)."""
+    mean_K: the blur mean is taken over the first mean_K lists (0 = all).
+    flow_ref: record set whose projected means define two extra colour channels composited in the same walk,
+    records[flow_ref][g].xy - records[own set][g].xy, no background (get_flow's exp2mid render, renderer :426-441);
+    when given, a fifth output `flow` is returned."""
     if specs is not None:
         specs = tuple(tuple(int(v) for v in s) for s in specs)
-    return _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
-                              specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K))
+    out = _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
+                             specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K),
+                             -1 if flow_ref is None else int(flow_ref))
+    return out if flow_ref is not None else out[:4]
 
 
 class _FlowRecords(torch.autograd.Function):
@@ -321,3 +338,30 @@ class _FlowRecords(torch.autograd.Function):
 
 def flow_records(records):
     return _FlowRecords.apply(records)
+
+
+class _MidFlowRecords(torch.autograd.Function):
+    """records [K+1,N,16] (set 0 = mid time, 1..K = exposure times) -> [ceil(2K/10),N,16]: mid geometry carrying
+    all 2K mid2exp flow channels, ten per record set (mobgs_midflow_records_fwd)."""
+
+    @staticmethod
+    def forward(ctx, records):
+        records = _f32c(records)
+        K, N = records.shape[0] - 1, records.shape[1]
+        M = (2 * K + 9) // 10
+        out = torch.empty(M, N, L.REC, device=records.device)
+        L.call("mobgs_midflow_records_fwd", L.FlowRecFwd(K, N, _p(records), _p(out)), _stream())
+        ctx.shape = (K, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        K, N = ctx.shape
+        g = _f32c(g)
+        v = torch.empty(K + 1, N, L.REC, device=g.device)
+        L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v)), _stream())
+        return v
+
+
+def midflow_records(records):
+    return _MidFlowRecords.apply(records)

@@ -129,7 +129,7 @@ def render(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, scal
         flow_2d = (ori_rec[..., 0:2] - records[..., 0:2].detach()).squeeze(0)
         rendered_flow, _ = ops.rasterize(records[..., 0:2], records[..., 3:6], flow_2d, records[0, :, 2],
                                          None, depths, radii, W, H, tight=TIGHT_TILES)
-        ori_coord_map = torch.tensor(cam.get_pixels(W, H, use_center=False)).type_as(rendered_flow) + rendered_flow
+        ori_coord_map = _pixel_grid(cam, W, H, dev) + rendered_flow
 
     means3d0 = means3d[0]
     return {"render": rendered_image,
@@ -168,12 +168,40 @@ def get_flow(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, de
     return exp2mid, mid2exp, latent_img[0], latent_alpha
 
 
+_GRID_CACHE = {}
+
+
+def _pixel_grid(cam, W, H, dev):
+    """cam.get_pixels(W, H, use_center=False) on the device.  It is the integer pixel grid [H,W,2] (x, y) for
+    every camera (dycheck_geometry/camera.py:600-613: np.meshgrid of aranges), so it is built once per
+    (W, H, device) on the device instead of a host meshgrid + a 16 MB upload per get_flow call."""
+    key = (W, H, str(dev))
+    g = _GRID_CACHE.get(key)
+    if g is None:
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev),
+                                torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
+        g = torch.stack([xs, ys], dim=-1)
+        if len(_GRID_CACHE) > 8:
+            _GRID_CACHE.clear()
+        _GRID_CACHE[key] = g
+    return g
+
+
 def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposures):
-    """K get_flow() calls (train.py:563-579 issues one per latent sub-frame) as ONE projection
-    launch (K+1 record sets: the mid time once + the K exposure times) and TWO binning/blend launch
-    chains: 2K flow lists (two colour channels) and 2K image lists (latent image + dynamic-only
-    alpha of every exposure time).  Returns (exp2mid_coord [K,H,W,2], mid2exp_coord [K,H,W,2],
-    latent_img [K,3,H,W], latent_alpha [K,H,W]) — `torch.cat` of what K reference calls return."""
+    """K get_flow() calls (train.py:563-579 issues one per latent sub-frame) as ONE projection launch (K+1
+    record sets: the mid time once + the K exposure times) and three launch chains that bin every distinct
+    geometry once and walk it once per payload group:
+
+      * K exposure-time lists: the latent image (:473, RGB+ED + decoder) and the exp2mid flow (:437) share
+        geometry and order, so ONE walk composites the 10 image channels and the 2 flow channels (colour
+        = mid - exp projected mean, taken from record set 0 on the fly; MobgsBlendFwd.flow_ref);
+      * K dynamic-only lists of the same record sets for latent_alpha (:379) — alpha only, one channel;
+      * the mid-time geometry ONCE: the K mid2exp flows (:456) differ only in their 2 colour channels, so all
+        2K channels ride ceil(2K/10) walks of a single shared binning (fused.midflow_records).
+
+    4K binned + walked lists before, 2K + 1 binned and 2K + ceil(2K/10) walked now (K of them over the dynamic
+    Gaussians only).  Returns (exp2mid_coord [K,H,W,2], mid2exp_coord [K,H,W,2], latent_img [K,3,H,W],
+    latent_alpha [K,H,W]) — `torch.cat` of what K reference calls return."""
     cam = viewpoint_camera
     dev = dyn_pc._scaling.device
     W, H = int(cam.image_width), int(cam.image_height)
@@ -187,22 +215,28 @@ def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Te
     rec, radii, depths, _ = fused.synth_project(
         _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
         viewmat[None].expand(K + 1, -1, -1), cam.K[None].expand(K + 1, -1, -1), t_poly.clamp(0, 1), t_poly, W, H)
+    grid = _pixel_grid(cam, W, H, dev)
 
-    # flows: set 2k = exposure-k geometry carrying (mid - exp), set 2k+1 = mid geometry carrying (exp - mid)
-    frec = fused.flow_records(rec)
-    sel = torch.tensor([v for k in range(K) for v in (k + 1, 0)], device=dev)
-    flows, _ = fused.blend_records(frec, radii[sel], depths[sel], None, 2, W, H, tight=TIGHT_TILES)
-    grid = torch.tensor(cam.get_pixels(W, H, use_center=False), device=dev, dtype=torch.float32)
-    exp2mid = grid + flows[0::2]
-    mid2exp = grid + flows[1::2]
-
-    # latent images (all Gaussians) and latent alphas (dynamic only) of the K exposure times
-    specs = [(k + 1, 0, N) for k in range(K)] + [(k + 1, Ns, N) for k in range(K)]
+    # exposure-time geometry: latent image + exp2mid flow in one walk
     dec = dyn_pc.rgbdecoder
-    rgb, _, alpha, _ = fused.blend_decode(rec, radii, depths, _bg10(bg_color, dev).expand(2 * K, -1), cam.cam_ray,
-                                          dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6), W, H,
-                                          specs=specs, tight=TIGHT_TILES)
-    return exp2mid, mid2exp, rgb[:K], _alpha_render(alpha[K:], bg_color)
+    rgb, _, _, _, flow_e2m = fused.blend_decode(
+        rec, radii, depths, _bg10(bg_color, dev).expand(K, -1), cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
+        dec.mlp2.weight.reshape(3, 6), W, H, specs=[(k + 1, 0, N) for k in range(K)], tight=TIGHT_TILES, flow_ref=0)
+    exp2mid = grid + flow_e2m
+
+    # latent alpha: the dynamic Gaussians of the same record sets, alpha only
+    _, alpha_d = fused.blend_records(rec, radii, depths, None, 1, W, H, specs=[(k + 1, Ns, N) for k in range(K)],
+                                     tight=TIGHT_TILES)
+
+    # mid-time geometry, binned once: all 2K mid2exp flow channels
+    frec = fused.midflow_records(rec)
+    M = frec.shape[0]
+    zero = torch.zeros(M, dtype=torch.long, device=dev)
+    mid, _ = fused.blend_records(frec, radii[zero], depths[zero], None, 10, W, H, tight=TIGHT_TILES,
+                                 tile_list=[0] * M)
+    flows_m2e = mid.permute(1, 2, 0, 3).reshape(H, W, M * 10)[..., :2 * K].reshape(H, W, K, 2).permute(2, 0, 1, 3)
+    mid2exp = grid + flows_m2e
+    return exp2mid, mid2exp, rgb, _alpha_render(alpha_d, bg_color)
 
 
 def get_flow_static(source_camera, target_camera, splat_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor):

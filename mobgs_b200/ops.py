@@ -124,18 +124,34 @@ _CAP_CACHE = {}
 SPECULATIVE_LISTS = os.environ.get("MOBGS_SPECULATIVE_LISTS", "1") != "0"
 
 
-def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None):
+def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None, tile_list=None):
     """mobgs_tile_count -> mobgs_tile_emit_sort (-> consume(lists)).
 
     specs: [(record_set, g_begin, g_end)] per list; default = one full-range list per record set.
+    tile_list: optional per-list index of the tile lists the list walks — lists with the same geometry and
+    index range (but different colour payloads) name the same index and are binned / sorted ONCE (the index
+    of a group is the position of its first member among the distinct values).  Default: every list its own.
     consume: optional callable(lists) that enqueues the kernels using the lists (blend); when given,
     returns (lists, consume(lists)) and sizes the lists speculatively (see above); otherwise reads I
     back synchronously and returns lists."""
     Kr, N = radii.shape
     if specs is None:
         specs = tuple((k, 0, N) for k in range(Kr))
-    K = len(specs)
-    lists = L.make_lists(specs)
+    if tile_list is None:
+        bin_specs, tl_idx = tuple(specs), None
+    else:
+        firsts = {}
+        for i, t in enumerate(tile_list):
+            firsts.setdefault(t, i)
+        order = sorted(firsts, key=lambda t: firsts[t])
+        bin_specs = tuple(specs[firsts[t]] for t in order)
+        tl_idx = tuple(order.index(t) for t in tile_list)
+        for i, t in enumerate(tl_idx):      # shared lists must agree on the index range (the geometry is the caller's promise)
+            if tuple(specs[i][1:]) != tuple(bin_specs[t][1:]):
+                raise ValueError("lists that share a tile binning must cover the same Gaussian index range")
+    K = len(bin_specs)
+    lists = L.make_lists(bin_specs)
+    blend_lists = L.make_lists(specs, tl_idx)
     dev = records.device
     tiles = math.ceil(width / L.TILE) * math.ceil(height / L.TILE)
     nt = K * tiles
@@ -153,10 +169,10 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
                        _p(counts), cap, _p(keys), _p(keys_tmp), _p(sorted_ids))
         L.call("mobgs_tile_emit_sort", b, _stream())
         tl = TileLists(offsets, sorted_ids, None, K, width, height)
-        tl.lists, tl.capacity = lists, cap
+        tl.lists, tl.capacity = blend_lists, cap
         return tl
 
-    key = (K, N, width, height, tuple(specs), bool(tight), dev.index)
+    key = (K, N, width, height, tuple(bin_specs), bool(tight), dev.index)
     guess = _CAP_CACHE.get(key)
     if consume is None or guess is None or not SPECULATIVE_LISTS:
         n_isect = int(offsets[-1].item())
