@@ -657,6 +657,15 @@ def measure_full_step(args, job, flush, local, views=2):
             (a.mean() + b.mean() + li.mean() + la.mean()).backward()
     parts["render_blurry_view_fwd_bwd_ms"], _ = timed(only_blurry, flush, 5, 2, local, 1)
     parts["get_flow_batched_fwd_bwd_ms"], _ = timed(only_flow, flush, 5, 2, local, 1)
+    # per-entry-point device time (CUDA events around every C-ABI call) of one full step / of the two render families
+    for name, fn in (("full_step", step), ("render_blurry_view", only_blurry), ("get_flow_batched", only_flow)):
+        torch.cuda.synchronize()
+        _lib.TIMING = {}
+        fn()
+        torch.cuda.synchronize()
+        parts[name + "_kernel_ms"] = {n: round(sum(a.elapsed_time(b) for a, b in ev), 4) for n, ev in _lib.TIMING.items()}
+        parts[name + "_kernel_calls"] = {n: len(ev) for n, ev in _lib.TIMING.items()}
+        _lib.TIMING = None
     with torch.no_grad():                       # the optimiser moved the scene: restore it for whatever follows
         for p, s in zip(job.all_params, saved):
             p.copy_(s)

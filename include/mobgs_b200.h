@@ -531,6 +531,33 @@ int mobgs_camera_rays_fwd(const MobgsCameraRays* a, void* stream);
 int mobgs_camera_rays_bwd(const MobgsCameraRays* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f4: densify / prune gather-compaction (scene/gaussian_model.py:1044-1123 `_prune_optimizer`,
+ * `cat_tensors_to_optimizer`; densification at :1417-1434): every per-Gaussian tensor — parameters, both
+ * Adam moments, densification statistics — is rebuilt by the same row gather, in ONE launch:
+ *   dst[t][i] = src[t][idx[i]]              if idx[i] <  n_old
+ *             = ext[t][idx[i] - n_old]      if idx[i] >= n_old      (ext[t] == NULL -> zero row)
+ * for i < n_out.  prune: idx = kept rows, ascending; append (clone / split): idx = 0 .. n_old + n_new - 1,
+ * ext = the new rows (NULL for the Adam moments: the reference extends them with zeros).  Rows are moved as
+ * row_words[t] 32-bit words (fp32 rows and the int64 current_control_num rows alike) — bit-exact.
+ * chunk_begin[t] = first chunk of tensor t when every tensor's n_out * row_words[t] output words are cut into
+ * mobgs_compact_chunk_words()-word chunks; chunk_begin[n_tensors] = total. */
+#define MOBGS_COMPACT_MAX_TENSORS 64
+typedef struct {
+  int32_t n_tensors;
+  int32_t reserved_;
+  int64_t n_old;             /* rows of every src[t] */
+  int64_t n_out;             /* rows of every dst[t] = entries of idx */
+  const int64_t* idx;        /* [n_out] device */
+  const void* src[MOBGS_COMPACT_MAX_TENSORS];
+  const void* ext[MOBGS_COMPACT_MAX_TENSORS];
+  void* dst[MOBGS_COMPACT_MAX_TENSORS];
+  int32_t row_words[MOBGS_COMPACT_MAX_TENSORS];
+  int32_t chunk_begin[MOBGS_COMPACT_MAX_TENSORS + 1];
+} MobgsCompactRows;
+int mobgs_compact_rows(const MobgsCompactRows* a, void* stream);
+int mobgs_compact_chunk_words(void);
+
+/* ------------------------------------------------------------------------------------------
  * f1 (second half): flow-warp loss of train.py:656-676, forward + backward fused.
  *   term1 = l1_loss(grid_sample(ori (expanded over K), norm(exp2mid)), latent, mask = latent_alpha)
  *   term2 = l1_loss(grid_sample(latent, norm(mid2exp)), ori (expanded), mask = d_alpha (expanded))

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -256,7 +256,17 @@ class RegLoss(C.Structure):
                 ("alpha", C.c_void_p), ("sums", C.c_void_p), ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p)]
 
 
-EXTRA_STRUCTS = {"MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+COMPACT_MAX_TENSORS = 64
+
+
+class CompactRows(C.Structure):
+    _fields_ = [("n_tensors", C.c_int32), ("reserved_", C.c_int32), ("n_old", C.c_int64), ("n_out", C.c_int64),
+                ("idx", C.c_void_p), ("src", C.c_void_p * COMPACT_MAX_TENSORS), ("ext", C.c_void_p * COMPACT_MAX_TENSORS),
+                ("dst", C.c_void_p * COMPACT_MAX_TENSORS), ("row_words", C.c_int32 * COMPACT_MAX_TENSORS),
+                ("chunk_begin", C.c_int32 * (COMPACT_MAX_TENSORS + 1))]
+
+
+EXTRA_STRUCTS = {"MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -290,6 +300,8 @@ ENTRY_POINTS = {
     "mobgs_camera_rays_fwd": CameraRays,
     "mobgs_camera_rays_bwd": CameraRays,
     "mobgs_adam_chunk_elems": "int",
+    "mobgs_compact_rows": CompactRows,
+    "mobgs_compact_chunk_words": "int",
 }
 
 _lib = None
