@@ -89,16 +89,30 @@ def test_oracle_matches_reference_optimizer_surgery():
                 pc.optimizer.zero_grad(set_to_none=True)
             return stat, dyn
 
+        def twins(which):
+            """(a, b): two models with bit-identical parameters and Adam state (b is overwritten from a: the
+            dynamic model's lstsq spline fit is not run-to-run reproducible)"""
+            a, b = fresh()[which], fresh()[which]
+            with torch.no_grad():
+                for ga, gb in zip(a.optimizer.param_groups, b.optimizer.param_groups):
+                    for pa, pb in zip(ga["params"], gb["params"]):
+                        pb.copy_(pa)
+                        sa, sb = a.optimizer.state.get(pa), b.optimizer.state.get(pb)
+                        if sa:
+                            for key in ("exp_avg", "exp_avg_sq"):
+                                sb[key].copy_(sa[key])
+            return a, b
+
         for which in (0, 1):
             g = torch.Generator().manual_seed(1)
             n = fresh()[which].get_xyz.shape[0]
             mask = torch.rand(n, generator=g) > 0.35
-            ref_pc, ora_pc = fresh()[which], fresh()[which]
+            ref_pc, ora_pc = twins(which)
             out_ref = ref_pc._prune_optimizer(mask)                 # the reference method, unmodified
             out_ora = O.prune_optimizer(ora_pc.optimizer, mask)
             _same(ref_pc.optimizer, ora_pc.optimizer, out_ref, out_ora)
             # append: extension rows for every single-parameter group
-            ref_pc, ora_pc = fresh()[which], fresh()[which]
+            ref_pc, ora_pc = twins(which)
             ext = {grp["name"]: (torch.randint(4, 13, (7,) + tuple(grp["params"][0].shape[1:]), generator=g)
                                  if grp["params"][0].dtype == torch.int64 else
                                  torch.randn((7,) + tuple(grp["params"][0].shape[1:]), generator=g))
