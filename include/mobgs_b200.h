@@ -144,7 +144,10 @@ int mobgs_synth_project_fwd(const MobgsSynthFwd* a, void* stream);
 
 /* VJP: consumes the packed gradient records [K,N,16] written by mobgs_blend_bwd and writes the
  * parameter gradients (each written exactly once, summed over K; control_xyz gradient buffer
- * must be zeroed by the caller).  v_viewmats accumulated atomically (zeroed by caller) or NULL. */
+ * must be zeroed by the caller).  v_viewmats accumulated atomically (zeroed by caller) or NULL.
+ * Pose-only mode: when EVERY parameter-gradient pointer (v_xyz .. v_offset) is NULL only v_viewmats is
+ * produced — eval.py's test-time pose optimisation freezes all Gaussians (eval.py:246-255) and differentiates
+ * render(w2c=...) with respect to the pose alone (eval.py:120-150). */
 typedef struct {
   MobgsCameras cams;
   MobgsStaticParams st;

@@ -261,6 +261,10 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
   const ProjCfg cfg = make_cfg(a.cams);
   const int K = a.cams.K;
   const int j = g - a.st.Ns;
+  // pose-only mode (every parameter-gradient pointer NULL): only v_viewmats is produced — eval.py's test-time
+  // pose optimisation freezes all Gaussians (eval.py:246-255) and differentiates render(w2c=...) w.r.t. the pose
+  const bool pose_only = a.v_xyz == nullptr && a.v_control_xyz == nullptr;
+  const bool v_ctrl_on = !pose_only;
 
   float p[3] = {0, 0, 0}, s[3] = {1, 1, 1}, q0[4] = {1, 0, 0, 0};
   float opac = 0.f;
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
     } else {
       load_dyn(a.dy, j, r);
       ctrl = a.dy.control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
-      v_ctrl = a.v_control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
+      if (v_ctrl_on) v_ctrl = a.v_control_xyz + (size_t)j * a.dy.n_ctrl_max * 3;
 #pragma unroll
       for (int i = 0; i < 3; ++i) s[i] = r.scale[i];
       opac = r.opac;
@@ -337,7 +341,7 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const float w = tp.w[t] * 1e-2f;
-          if (w != 0.f) {
+          if (w != 0.f && v_ctrl_on) {
             float* c = v_ctrl + 3 * tp.idx[t];
 #if MOBGS_CTRL_RED
             // fire-and-forget reductions: no load in the dependent chain (the row is zeroed by the caller)
@@ -352,7 +356,7 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
     if (a.v_viewmats) reduce_viewmat_grad(sm.v_view, k, gr, active);
   }
   if (a.v_viewmats) flush_viewmat_grad(sm.v_view, a.v_viewmats, K);
-  if (!in_range) return;
+  if (!in_range || pose_only) return;
   const float vo_logit = vop * opac * (1.f - opac);
   if (is_static) {
 #pragma unroll
@@ -463,12 +467,19 @@ extern "C" int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream) {
   const int N = a->st.Ns + a->dy.Nd;
   if (N == 0) return MOBGS_OK;
   MOBGS_REQUIRE(a->radii && a->v_records, "radii / v_records must not be NULL");
-  if (a->st.Ns > 0)
-    MOBGS_REQUIRE(a->v_xyz && a->v_rotation_s && a->v_scaling_s && a->v_opacity_s && a->v_features_dc_s,
-                  "static gradient outputs NULL");
-  if (a->dy.Nd > 0)
-    MOBGS_REQUIRE(a->v_control_xyz && a->v_rotation_d && a->v_omega && a->v_scaling_d && a->v_opacity_d &&
-                      a->v_features_dc_d && a->v_features_t, "dynamic gradient outputs NULL");
+  const bool none = !a->v_xyz && !a->v_rotation_s && !a->v_scaling_s && !a->v_opacity_s && !a->v_features_dc_s &&
+                    !a->v_control_xyz && !a->v_rotation_d && !a->v_omega && !a->v_scaling_d && !a->v_opacity_d &&
+                    !a->v_features_dc_d && !a->v_features_t && !a->v_offset;
+  if (none) {   // pose-only: eval.py's test-time pose optimisation (all Gaussians frozen)
+    MOBGS_REQUIRE(a->v_viewmats, "pose-only backward needs v_viewmats");
+  } else {
+    if (a->st.Ns > 0)
+      MOBGS_REQUIRE(a->v_xyz && a->v_rotation_s && a->v_scaling_s && a->v_opacity_s && a->v_features_dc_s,
+                    "static gradient outputs NULL");
+    if (a->dy.Nd > 0)
+      MOBGS_REQUIRE(a->v_control_xyz && a->v_rotation_d && a->v_omega && a->v_scaling_d && a->v_opacity_d &&
+                        a->v_features_dc_d && a->v_features_t, "dynamic gradient outputs NULL");
+  }
   const int grid = (N + kProjThreads - 1) / kProjThreads;
   synth_project_bwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("synth_project_bwd");

@@ -77,6 +77,17 @@ class _SynthProject(torch.autograd.Function):
         # autograd adopts the views as `.grad`, so a data-parallel caller all-reduces the buffer in place
         # (dist.FlatGradients) instead of packing / unpacking 12 tensors.  control_xyz needs the zeros
         # (accumulated in place); trbf_center gets no gradient: dt is detached in the reference (render():102).
+        v_off = torch.empty_like(off) if off is not None else None
+        v_view = torch.zeros(K, 4, 4, device=dev) if ctx.needs_input_grad[0] else None
+        cams = _cams(viewmats, Ks, width, height)
+        if not any(ctx.needs_input_grad[8:]):
+            # pose-only backward (eval.py:120-150: every Gaussian tensor is frozen, only w2c is optimised): no flat
+            # gradient buffer, no parameter-gradient stores
+            if v_view is not None:
+                a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
+                               _p(t_poly), _p(radii), _p(g_rec), *([None] * 13), _p(v_view))
+                L.call("mobgs_synth_project_bwd", a, _stream())
+            return (v_view,) + (None,) * 21
         outs = list(st) + list(dy[:7])
         starts, tot = [], 0
         for t in outs:
@@ -85,9 +96,6 @@ class _SynthProject(torch.autograd.Function):
         flat = torch.zeros(tot, device=dev)
         views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(starts, outs)]
         v_st, v_dy = views[:5], views[5:] + [None]
-        v_off = torch.empty_like(off) if off is not None else None
-        v_view = torch.zeros(K, 4, 4, device=dev) if ctx.needs_input_grad[0] else None
-        cams = _cams(viewmats, Ks, width, height)
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
                        _p(t_poly), _p(radii), _p(g_rec),
                        _p(v_st[0]), _p(v_st[1]), _p(v_st[2]), _p(v_st[3]), _p(v_st[4]),

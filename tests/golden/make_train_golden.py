@@ -191,5 +191,89 @@ def main(out_path=None):
     return blob
 
 
+EVAL_STEPS, EVAL_DECAY_START = 6, 2
+EVAL_LR = 3e-4          # eval.py:258-260 (lr_p = lr_q = 0.0003, lr_final = 1e-6)
+
+
+def make_eval_golden(out_path=None):
+    """tests/golden/eval_tto.npz: the UNMODIFIED `eval.render_test_tto` (eval.py:43-166, test-time pose optimisation
+    through render(w2c=...)) for one test view, EVAL_STEPS Adam steps, all Gaussians frozen as eval.py:246-255 does.
+    Recorded: frozen parameters, the view (pose, K, time, ground-truth image as eval.py loads it from PNG), and per
+    step the w2c handed to render(), the loss (-PSNR), d loss / d (t, q); plus the solved pose."""
+    import inspect
+    from PIL import Image
+    E.setup_paths()
+    blob = {}
+    with E.cuda_to_cpu():
+        import eval as EV
+        from arguments import PipelineParams
+        EV.models.PerceptualLoss = lambda *a, **k: None          # LPIPS (needs downloaded AlexNet weights) is built but unused in the loop
+        torch.manual_seed(0); random.seed(0); np.random.seed(0)
+        stat, dyn, scene, hyper = E.synthetic_reference_scene(W=W, H=H)
+        for pc in (dyn, stat):                                   # eval.py:246-255
+            for attr in inspect.getmembers(pc):
+                try:
+                    attr[1].requires_grad = False
+                except Exception:  # noqa: BLE001
+                    pass
+        for tag, pc in (("stat", stat), ("dyn", dyn)):
+            for g, attr in ATTR_OF.items():
+                blob[f"{tag}/{g}"] = _np(getattr(pc, attr))
+            blob[f"{tag}/current_control_num"] = _np(pc.current_control_num)
+        blob["dec/mlp1"], blob["dec/mlp2"] = _np(dyn.rgbdecoder.mlp1.weight), _np(dyn.rgbdecoder.mlp2.weight)
+        cam = scene.test_cams[2]
+        gt_dir = os.path.join(scene.model_path, "inference_images")
+        os.makedirs(gt_dir, exist_ok=True)
+        img8 = (cam.original_image.permute(1, 2, 0).numpy() * 255).astype("uint8")
+        Image.fromarray(img8).save(os.path.join(gt_dir, f"{cam.image_name}.png"))
+        blob["gt_rgb"] = (img8 / 255.0).astype(np.float32)       # what eval.py:89-95 ends up with ([H,W,3])
+        blob["w2c0"] = _np(cam.world_view_transform.transpose(0, 1))
+        blob["K"], blob["time"], blob["max_time"] = _np(cam.K), np.array(cam.time), np.array(cam.max_time)
+        blob["cam_ray"] = _np(cam.cam_ray)
+        blob["W"], blob["H"] = np.array(W), np.array(H)
+        blob["steps"], blob["decay_start"], blob["lr"], blob["lr_final"] = (np.array(EVAL_STEPS), np.array(EVAL_DECAY_START),
+                                                                             np.array(EVAL_LR), np.array(1e-6))
+        rec = {"w2c": [], "loss": [], "g_t": [], "g_q": []}
+        real_render, real_backward, real_step = EV.render, torch.Tensor.backward, torch.optim.Adam.step
+
+        def render_rec(camera, *a, **k):
+            if k.get("w2c") is not None and k["w2c"].requires_grad:
+                rec["w2c"].append(_np(k["w2c"]))
+            return real_render(camera, *a, **k)
+
+        def backward_rec(self, *a, **k):
+            if self.dim() == 0:
+                rec["loss"].append(float(self.detach()))
+            return real_backward(self, *a, **k)
+
+        def step_rec(self, *a, **k):
+            ps = [g["params"][0] for g in self.param_groups]
+            if len(ps) == 2 and tuple(ps[0].shape) == (3,) and tuple(ps[1].shape) == (4,):
+                rec["g_t"].append(_np(ps[0].grad)); rec["g_q"].append(_np(ps[1].grad))
+            return real_step(self, *a, **k)
+
+        EV.render, torch.Tensor.backward, torch.optim.Adam.step = render_rec, backward_rec, step_rec
+        try:
+            pipe = E.group_args(PipelineParams)
+            bg = torch.tensor([0] * 9 + [0], dtype=torch.float32)          # eval.py:222-223
+            save_dir = os.path.join(scene.model_path, "eval_out")
+            EV.render_test_tto(H=H, W=W, scene=scene, test_cams=[cam], save_dir=save_dir, gt_rgb_dir=gt_dir,
+                               tto_steps=EVAL_STEPS, decay_start=EVAL_DECAY_START, lr_p=EVAL_LR, lr_q=EVAL_LR, lr_final=1e-6,
+                               use_sgd=False, initialize_from_previous_camera=False, initialize_from_previous_step_factor=1,
+                               initialize_from_previous_lr_factor=1.0, fg_mask_th=0.1, local_viewdirs=None, batch_shape=None,
+                               renderArgs=[pipe, bg])
+        finally:
+            EV.render, torch.Tensor.backward, torch.optim.Adam.step = real_render, real_backward, real_step
+        blob["solved_pose"] = np.load(os.path.join(save_dir, "solved_poses.npy"))[0]
+        for k, v in rec.items():
+            blob["step/" + k] = np.stack(v) if k != "loss" else np.array(v)
+    out_path = out_path or os.path.join(HERE, "eval_tto.npz")
+    np.savez_compressed(out_path, **blob)
+    print("wrote", out_path, "losses", blob["step/loss"])
+    return blob
+
+
 if __name__ == "__main__":
-    main()
+    if "--only-eval" not in sys.argv:
+        main()
+    make_eval_golden()

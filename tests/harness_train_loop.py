@@ -204,3 +204,66 @@ def run_iteration(z, it, backend):
     return dict(photo=float(photo.detach()), reg=float(reg.detach()), grads=grads, grad_w2c=g_w2c, grad_cam_ray_sum=g_ray,
                 grad_viewspace=vsp_final, grad_viewspace_after_photo=vsp_grads, render_mean=np.array(render_mean),
                 depth_mean=np.array(depth_mean), flow_means=np.array(flow_means))
+
+
+EVAL_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "eval_tto.npz")
+
+
+def run_eval_tto(z, backend):
+    """eval.py:96-150 (render_test_tto's per-view body) restated: Adam on (t, q) of the world-to-camera pose through
+    render(cam, stat, dyn, pipe, bg, stage="fine", get_static=False, get_dynamic=False, w2c=curr_w2c), loss = -PSNR,
+    CosineAnnealingLR after `decay_start`; all Gaussian tensors frozen (eval.py:246-255).
+    -> dict(w2c [steps,4,4], loss [steps], g_t [steps,3], g_q [steps,4], solved_pose [4,4])."""
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "compat")
+    if compat not in sys.path:
+        sys.path.append(compat)
+    from pytorch3d.transforms import matrix_to_quaternion, quaternion_to_matrix   # compat/ stand-in (wxyz)
+    from mobgs_b200.scene import GaussianSet, Sandwich
+    device = "cpu" if backend == "oracle" else "cuda"
+    models = []
+    for tag in ("stat", "dyn"):
+        pc = GaussianSet()
+        for g, attr in ATTR_OF.items():
+            setattr(pc, attr, torch.from_numpy(z[f"{tag}/{g}"]).to(device))          # frozen: requires_grad False
+        pc.current_control_num = torch.from_numpy(z[f"{tag}/current_control_num"]).to(device)
+        models.append(pc)
+    stat, dyn = models
+    dec = Sandwich().to(device)
+    with torch.no_grad():
+        dec.mlp1.weight.copy_(torch.from_numpy(z["dec/mlp1"])); dec.mlp2.weight.copy_(torch.from_numpy(z["dec/mlp2"]))
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    dyn.rgbdecoder, stat.rgbdecoder = dec, dec
+    zz = {"W": z["W"], "H": z["H"], "max_time": z["max_time"], "cam0/K": z["K"]}
+    cam = make_cam(zz, 0, z["w2c0"], float(z["time"]), device, pose_grad=False)
+    if backend == "oracle":
+        from oracle.mobgs_ref import render_ref as render
+    else:
+        from mobgs_b200.gaussian_renderer import render
+    gt_rgb = torch.from_numpy(z["gt_rgb"]).to(device).float()
+    bg = torch.zeros(10, device=device)
+    steps, decay_start, lr, lr_final = int(z["steps"]), int(z["decay_start"]), float(z["lr"]), float(z["lr_final"])
+    T_bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], device=device)
+    w2c = cam.world_view_transform.transpose(0, 1).detach()
+    t_init = torch.nn.Parameter(w2c[:3, 3].clone().detach(), requires_grad=True)
+    q_init = torch.nn.Parameter(matrix_to_quaternion(w2c[:3, :3]).clone().detach(), requires_grad=True)
+    optimizer = torch.optim.Adam([{"params": t_init, "lr": lr}, {"params": q_init, "lr": lr}])
+    scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, T_max=steps - decay_start, eta_min=lr_final)
+    out = {"w2c": [], "loss": [], "g_t": [], "g_q": []}
+    for _step in range(steps):
+        optimizer.zero_grad()
+        curr = torch.cat([quaternion_to_matrix(q_init), t_init[:, None]], 1)
+        curr = torch.cat([curr, T_bottom[None]], 0)
+        pkg = render(cam, stat, dyn, None, bg, stage="fine", get_static=False, get_dynamic=False, cam_type="nvidia", w2c=curr)
+        pred = pkg["render"].permute(1, 2, 0)
+        mse = ((pred - gt_rgb) ** 2).mean()
+        loss = -(20 * torch.log10(1.0 / torch.sqrt(mse)))
+        loss.backward()
+        out["w2c"].append(curr.detach().cpu().numpy()); out["loss"].append(float(loss.detach()))
+        out["g_t"].append(t_init.grad.detach().cpu().numpy().copy()); out["g_q"].append(q_init.grad.detach().cpu().numpy().copy())
+        optimizer.step()
+        if _step >= decay_start:
+            scheduler.step()
+    solved = torch.cat([torch.cat([quaternion_to_matrix(q_init), t_init[:, None]], 1), T_bottom[None]], 0)
+    return {k: np.stack(v) if k != "loss" else np.array(v) for k, v in out.items()} | {"solved_pose": solved.detach().cpu().numpy()}

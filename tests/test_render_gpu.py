@@ -82,10 +82,18 @@ def test_render_matches_oracle(delta, flow):
            max_outlier_frac=1e-3)
 
 
-def test_render_pose_gradient_eval_path():
-    """eval.py:120-150 optimises the pose through render(..., w2c=...) only."""
+@pytest.mark.parametrize("frozen", [False, True])
+def test_render_pose_gradient_eval_path(frozen):
+    """eval.py:120-150 optimises the pose through render(..., w2c=...) only.  frozen: every Gaussian tensor has
+    requires_grad = False as eval.py:246-255 sets them — the backward then runs in pose-only mode (no parameter
+    gradient buffer, no parameter stores) and must give the same pose gradient."""
     from mobgs_b200.gaussian_renderer import render
     (so, do, cam_o), (sc, dc, cam_c) = _pair(ns=500, nd=200, W=96, H=64)
+    if frozen:
+        sc.requires_grad_(False)
+        dc.requires_grad_(False)
+        for p in dc.rgbdecoder.parameters():
+            p.requires_grad_(False)
     w2c_o = subframe_w2c(1, 3).clone().requires_grad_(True)
     w2c_c = subframe_w2c(1, 3, device="cuda").clone().requires_grad_(True)
     bg = torch.zeros(3)
@@ -96,6 +104,8 @@ def test_render_pose_gradient_eval_path():
     _loss(out_c, ws).backward()
     _loss(out_o, ws).backward()
     _close(w2c_c.grad[:3], w2c_o.grad[:3], "v_w2c", rtol=5e-3)
+    if frozen:
+        assert all(p.grad is None for p in sc.parameters()) and all(p.grad is None for p in dc.parameters())
 
 
 @pytest.mark.parametrize("delta", [0.6, -1.0])
