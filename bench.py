@@ -608,11 +608,16 @@ def measure_full_step(args, job, flush, local, views=2):
     parts = {}
 
     def cams_of(v, w2c):
-        rays = camera_rays_from_w2c(w2c, intr.fx, intr.fy, intr.cx, intr.cy, W, H)     # pose-differentiable
-        return [SimpleNamespace(world_view_transform=w2c[k].transpose(0, 1), K=job.Kmat, time=times[v], max_time=23,
-                                image_width=W, image_height=H, cam_ray=rays[k:k + 1],
-                                get_pixels=pixel_grid)
+        """K camera stand-ins of view v + their stacked rays (one camera_rays launch, pose-differentiable)"""
+        rays = camera_rays_from_w2c(w2c, intr.fx, intr.fy, intr.cx, intr.cy, W, H)
+        per_cam = rays.split(1)
+        cams = [SimpleNamespace(world_view_transform=w2c[k].transpose(0, 1), K=job.Kmat, time=times[v], max_time=23,
+                                image_width=W, image_height=H, cam_ray=per_cam[k], get_pixels=pixel_grid)
                 for k in range(K)]
+        # the centre sub-frame is the dataset camera itself: numpy pose, not learnable (train.py:441, scene/cameras.py:121-124)
+        cams[half].world_view_transform = w2c[half].detach().transpose(0, 1)
+        cams[half].cam_ray = per_cam[half].detach()
+        return cams, rays
 
     def step():
         for p in job.all_params:
@@ -620,8 +625,8 @@ def measure_full_step(args, job, flush, local, views=2):
         preds, depths, d_alphas, oris, lat_img, lat_alpha, e2m, m2e, vsps = [], [], [], [], [], [], [], [], []
         for v in range(views):
             w2c = view_d[v].clone().requires_grad_(True)
-            cams = cams_of(v, w2c)
-            pkg = render_blurry_view(cams[half], cams, exposure_time, stat, dyn, None, job.bg)
+            cams, rays = cams_of(v, w2c)
+            pkg = render_blurry_view(cams[half], cams, exposure_time, stat, dyn, None, job.bg, rays=rays)
             preds.append(pkg["render"]); depths.append(pkg["depth"]); d_alphas.append(pkg["d_alpha"])
             oris.append(pkg["render_center"]); vsps.append(pkg["viewspace_points"])
             a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas)
@@ -644,15 +649,15 @@ def measure_full_step(args, job, flush, local, views=2):
         for p in job.all_params:
             p.grad = None
         for v in range(views):
-            cams = cams_of(v, view_d[v].clone().requires_grad_(True))
-            pkg = render_blurry_view(cams[half], cams, exposure_time, stat, dyn, None, job.bg)
+            cams, rays = cams_of(v, view_d[v].clone().requires_grad_(True))
+            pkg = render_blurry_view(cams[half], cams, exposure_time, stat, dyn, None, job.bg, rays=rays)
             (pkg["render"].mean() + pkg["depth"].mean() + pkg["d_alpha"].mean()).backward()
 
     def only_flow():
         for p in job.all_params:
             p.grad = None
         for v in range(views):
-            cams = cams_of(v, view_d[v])
+            cams, _ = cams_of(v, view_d[v])
             a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas)
             (a.mean() + b.mean() + li.mean() + la.mean()).backward()
     parts["render_blurry_view_fwd_bwd_ms"], _ = timed(only_blurry, flush, 5, 2, local, 1)

@@ -411,6 +411,8 @@ typedef struct {
   int32_t K, N;
   const float* v_flow_records;   /* [2K,N,16] */
   float* v_records;              /* [K+1,N,16] */
+  int32_t accumulate;            /* mobgs_midflow_records_bwd only: 0 = write v_records, 1 = add to it (the buffer
+                                  * already holds the gradient of the other renders that share the projection) */
 } MobgsFlowRecBwd;
 int mobgs_flow_records_bwd(const MobgsFlowRecBwd* a, void* stream);
 

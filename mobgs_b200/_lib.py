@@ -203,7 +203,8 @@ class FlowRecFwd(C.Structure):
 
 
 class FlowRecBwd(C.Structure):
-    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("v_flow_records", C.c_void_p), ("v_records", C.c_void_p)]
+    _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("v_flow_records", C.c_void_p), ("v_records", C.c_void_p),
+                ("accumulate", C.c_int32)]
 
 
 class HexFeat(C.Structure):

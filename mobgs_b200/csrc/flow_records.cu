@@ -105,15 +105,29 @@ __global__ void __launch_bounds__(256) midflow_records_bwd_kernel(MobgsFlowRecBw
       const int k = 5 * m + i;
       if (k < a.K) {
         float4* oe = out + (size_t)(k + 1) * N4 + (size_t)g * 4;
-        oe[0] = make_float4(c[2 * i], c[2 * i + 1], 0.f, 0.f);
-        oe[1] = z; oe[2] = z; oe[3] = z;
+        if (a.accumulate) {
+          float2* o2 = reinterpret_cast<float2*>(oe);
+          const float2 cur = *o2;
+          *o2 = make_float2(cur.x + c[2 * i], cur.y + c[2 * i + 1]);
+        } else {
+          oe[0] = make_float4(c[2 * i], c[2 * i + 1], 0.f, 0.f);
+          oe[1] = z; oe[2] = z; oe[3] = z;
+        }
         gm0.x -= c[2 * i];
         gm0.y -= c[2 * i + 1];
       }
     }
   }
   float4* om = out + (size_t)g * 4;
-  om[0] = gm0; om[1] = make_float4(gm1.x, gm1.y, 0.f, 0.f); om[2] = z; om[3] = z;
+  if (a.accumulate) {
+    const float4 c0 = om[0];
+    float2* o1 = reinterpret_cast<float2*>(om + 1);
+    const float2 c1 = *o1;
+    om[0] = make_float4(c0.x + gm0.x, c0.y + gm0.y, c0.z + gm0.z, c0.w + gm0.w);
+    *o1 = make_float2(c1.x + gm1.x, c1.y + gm1.y);
+  } else {
+    om[0] = gm0; om[1] = make_float4(gm1.x, gm1.y, 0.f, 0.f); om[2] = z; om[3] = z;
+  }
 }
 
 }  // namespace mobgs

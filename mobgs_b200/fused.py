@@ -340,7 +340,7 @@ class _FlowRecords(torch.autograd.Function):
         K, N = ctx.shape
         g = _f32c(g)
         v = torch.empty(K + 1, N, L.REC, device=g.device)
-        L.call("mobgs_flow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v)), _stream())
+        L.call("mobgs_flow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v), 0), _stream())
         return v
 
 
@@ -367,9 +367,112 @@ class _MidFlowRecords(torch.autograd.Function):
         K, N = ctx.shape
         g = _f32c(g)
         v = torch.empty(K + 1, N, L.REC, device=g.device)
-        L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v)), _stream())
+        L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(g), _p(v), 0), _stream())
         return v
 
 
 def midflow_records(records):
     return _MidFlowRecords.apply(records)
+
+
+class _FlowRender(torch.autograd.Function):
+    """All rasterisations of K get_flow() calls that share ONE projection (records [K+1,N,16]: set 0 = mid time,
+    sets 1..K = exposure times) as ONE autograd node, so their three backward passes accumulate into a single
+    gradient-record buffer instead of three that autograd then has to add (0.5 GB each at the headline size):
+
+      exposure lists  (k+1, all)      latent image (decoded) + exp2mid flow, one walk      gaussian_renderer :437, :473
+      dynamic lists   (k+1, Ns..N)    latent alpha, one channel                             :379
+      mid lists       (0, all) x M    all 2K mid2exp flow channels over one shared binning  :456
+
+    -> rgb [K,3,H,W], flow_e2m [K,H,W,2], alpha_dyn [K,H,W], mid [M,H,W,10]."""
+
+    @staticmethod
+    def forward(ctx, records, radii, depths, bg10, rays, w1, w2, width, height, Ns, tight):
+        records = _f32c(records)
+        rays, w1, w2, bg10 = _f32c(rays), _f32c(w1), _f32c(w2), _f32c(bg10)
+        Kr, N = radii.shape
+        K = Kr - 1
+        dev = records.device
+        assert rays.shape[0] == 1 and rays.shape[1] == 6
+        st = _stream()
+
+        def exp_walk(lists):
+            img10 = torch.empty(K, height, width, 10, device=dev)
+            alpha = torch.empty(K, height, width, device=dev)
+            last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+            rgb = torch.empty(K, 3, height, width, device=dev)
+            flow = torch.empty(K, height, width, 2, device=dev)
+            a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
+                           _p(lists.sorted_ids), _p(bg10), _p(img10), _p(alpha), _p(last),
+                           _p(rays), 0, _p(w1), _p(w2), _p(rgb), None, 0, _p(flow))
+            L.call("mobgs_blend_fwd", a, st)
+            return img10, alpha, last, rgb, flow
+
+        le, (img10, alpha_e, last_e, rgb, flow) = build_tile_lists(
+            records, radii, depths, width, height, tight, tuple((k + 1, 0, N) for k in range(K)), consume=exp_walk)
+
+        def plain_walk(recs, D):
+            def walk(lists):
+                Kl = len(lists.specs)
+                out_c = torch.empty(Kl, height, width, D, device=dev)
+                out_a = torch.empty(Kl, height, width, device=dev)
+                last = torch.empty(Kl, height, width, dtype=torch.int32, device=dev)
+                a = L.BlendFwd(Kl, N, D, width, height, lists.lists, lists.capacity, _p(recs), _p(lists.tile_offsets),
+                               _p(lists.sorted_ids), None, _p(out_c), _p(out_a), _p(last))
+                L.call("mobgs_blend_fwd", a, st)
+                return out_c, out_a, last
+            return walk
+
+        ld, (_junk, alpha_d, last_d) = build_tile_lists(
+            records, radii, depths, width, height, tight, tuple((k + 1, Ns, N) for k in range(K)), consume=plain_walk(records, 1))
+
+        M = (2 * K + 9) // 10
+        frec = torch.empty(M, N, L.REC, device=dev)
+        L.call("mobgs_midflow_records_fwd", L.FlowRecFwd(K, N, _p(records), _p(frec)), st)
+        radii_m, depths_m = radii[0:1].expand(M, -1).contiguous(), depths[0:1].expand(M, -1).contiguous()
+        lm, (mid, alpha_m, last_m) = build_tile_lists(
+            frec, radii_m, depths_m, width, height, tight, tuple((m, 0, N) for m in range(M)),
+            consume=plain_walk(frec, 10), tile_list=(0,) * M)
+
+        ctx.save_for_backward(records, bg10, rays, w1, w2, img10, alpha_e, last_e, le.tile_offsets, le.sorted_ids,
+                              alpha_d, last_d, ld.tile_offsets, ld.sorted_ids, frec, alpha_m, last_m, lm.tile_offsets,
+                              lm.sorted_ids)
+        ctx.lists = (le.lists, le.capacity, ld.lists, ld.capacity, lm.lists, lm.capacity)
+        ctx.meta = (K, M, N, width, height)
+        return rgb, flow, alpha_d, mid
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_flow, g_alpha_d, g_mid):
+        (records, bg10, rays, w1, w2, img10, alpha_e, last_e, off_e, ids_e, alpha_d, last_d, off_d, ids_d, frec, alpha_m,
+         last_m, off_m, ids_m) = ctx.saved_tensors
+        le, cap_e, ld, cap_d, lm, cap_m = ctx.lists
+        K, M, N, width, height = ctx.meta
+        dev = records.device
+        st = _stream()
+        v_rec = torch.zeros(K + 1, N, L.REC, device=dev)
+        v_rays = torch.zeros_like(rays) if ctx.needs_input_grad[4] else None
+        v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
+        g_rgb = _f32c(g_rgb) if g_rgb is not None else None
+        g_flow = _f32c(g_flow) if g_flow is not None else torch.zeros(K, height, width, 2, device=dev)
+        a = L.BlendBwd(K, N, 10, width, height, le, cap_e, _p(records), _p(off_e), _p(ids_e), _p(bg10), _p(alpha_e),
+                       _p(last_e), None, None, _p(v_rec), -1, None, _p(rays), 0, _p(w1), _p(w2), _p(img10), _p(g_rgb),
+                       None, None, None, 0, _p(v_rays), _p(v_wp), 0, _p(g_flow))
+        L.call("mobgs_blend_bwd", a, st)
+        if g_alpha_d is not None:
+            zeros = torch.zeros(K, height, width, 1, device=dev)
+            a = L.BlendBwd(K, N, 1, width, height, ld, cap_d, _p(records), _p(off_d), _p(ids_d), None, _p(alpha_d),
+                           _p(last_d), _p(zeros), _p(_f32c(g_alpha_d)), _p(v_rec), -1, None)
+            L.call("mobgs_blend_bwd", a, st)
+        if g_mid is not None:
+            v_frec = torch.zeros(M, N, L.REC, device=dev)
+            a = L.BlendBwd(M, N, 10, width, height, lm, cap_m, _p(frec), _p(off_m), _p(ids_m), None, _p(alpha_m),
+                           _p(last_m), _p(_f32c(g_mid)), None, _p(v_frec), -1, None)
+            L.call("mobgs_blend_bwd", a, st)
+            L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(v_frec), _p(v_rec), 1), st)
+        v_w = v_wp.sum(0)
+        return (v_rec, None, None, None, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6), None, None, None, None)
+
+
+def flow_render(records, radii, depths, bg10, rays, w1, w2, width, height, n_static, tight=True):
+    """see _FlowRender; bg10 [K,10] (the exposure lists' background), rays [1,6,H,W] (one camera for all lists)."""
+    return _FlowRender.apply(records, radii, depths, bg10, rays, w1, w2, int(width), int(height), int(n_static), bool(tight))

@@ -217,23 +217,14 @@ def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Te
         viewmat[None].expand(K + 1, -1, -1), cam.K[None].expand(K + 1, -1, -1), t_poly.clamp(0, 1), t_poly, W, H)
     grid = _pixel_grid(cam, W, H, dev)
 
-    # exposure-time geometry: latent image + exp2mid flow in one walk
+    # one autograd node for all three render groups (fused._FlowRender): their backward passes accumulate into one
+    # gradient-record buffer
     dec = dyn_pc.rgbdecoder
-    rgb, _, _, _, flow_e2m = fused.blend_decode(
+    rgb, flow_e2m, alpha_d, mid = fused.flow_render(
         rec, radii, depths, _bg10(bg_color, dev).expand(K, -1), cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
-        dec.mlp2.weight.reshape(3, 6), W, H, specs=[(k + 1, 0, N) for k in range(K)], tight=TIGHT_TILES, flow_ref=0)
+        dec.mlp2.weight.reshape(3, 6), W, H, Ns, tight=TIGHT_TILES)
     exp2mid = grid + flow_e2m
-
-    # latent alpha: the dynamic Gaussians of the same record sets, alpha only
-    _, alpha_d = fused.blend_records(rec, radii, depths, None, 1, W, H, specs=[(k + 1, Ns, N) for k in range(K)],
-                                     tight=TIGHT_TILES)
-
-    # mid-time geometry, binned once: all 2K mid2exp flow channels
-    frec = fused.midflow_records(rec)
-    M = frec.shape[0]
-    zero = torch.zeros(M, dtype=torch.long, device=dev)
-    mid, _ = fused.blend_records(frec, radii[zero], depths[zero], None, 10, W, H, tight=TIGHT_TILES,
-                                 tile_list=[0] * M)
+    M = mid.shape[0]
     flows_m2e = mid.permute(1, 2, 0, 3).reshape(H, W, M * 10)[..., :2 * K].reshape(H, W, K, 2).permute(2, 0, 1, 3)
     mid2exp = grid + flows_m2e
     return exp2mid, mid2exp, rgb, _alpha_render(alpha_d, bg_color)

@@ -169,7 +169,7 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
                        _p(counts), cap, _p(keys), _p(keys_tmp), _p(sorted_ids))
         L.call("mobgs_tile_emit_sort", b, _stream())
         tl = TileLists(offsets, sorted_ids, None, K, width, height)
-        tl.lists, tl.capacity = blend_lists, cap
+        tl.lists, tl.capacity, tl.specs = blend_lists, cap, tuple(specs)
         return tl
 
     key = (K, N, width, height, tuple(bin_specs), bool(tight), dev.index)

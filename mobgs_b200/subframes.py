@@ -54,7 +54,8 @@ def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, 
 
 
 def render_blurry_view(viewpoint_cam, warped_cams, exposure_time, stat_pc, dyn_pc, pipe, bg_color,
-                       use_delta_exposure: bool = True, tight: bool = True) -> Dict[str, torch.Tensor]:
+                       use_delta_exposure: bool = True, tight: bool = True,
+                       rays: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """Fused equivalent of the reference's per-view render loop (train.py:441 + :497-541):
 
         render_pkg = render(viewpoint_cam, ..., get_static=True, get_dynamic=True)        # centre
@@ -71,6 +72,7 @@ def render_blurry_view(viewpoint_cam, warped_cams, exposure_time, stat_pc, dyn_p
     `viewpoint_cam` / `warped_cams[k]` are reference `Camera` objects (or mobgs_b200.scene
     stand-ins); `exposure_time` is blceKernel.get_warped_cams' second output ([K] tensor);
     use_delta_exposure mirrors `iteration > blceopt.start_warp_dynamic` (train.py:503-506).
+    `rays`: optional pre-stacked [K,6,H,W] camera rays of `warped_cams` (centre camera at K//2).
 
     Returns the keys train.py consumes: "render" (blurred prediction), "subframes" [K,3,H,W],
     "depths" [K,H,W], and the centre render's "render_center", "depth", "s_render", "s_depth",
@@ -92,7 +94,8 @@ def render_blurry_view(viewpoint_cam, warped_cams, exposure_time, stat_pc, dyn_p
     is_center = torch.arange(K, device=dev) == half
     t_poly = torch.where(is_center, t0, t_poly)
     t_spline = torch.where(is_center, t0, t_poly.clamp(0, 1))      # the centre render does not clamp (render():114)
-    rays = torch.cat([c.cam_ray for c in cams]).to(dev)
+    if rays is None:       # `rays` [K,6,H,W]: the K cameras' cam_ray already stacked (mobgs_b200.cameras.camera_rays builds them
+        rays = torch.cat([c.cam_ray for c in cams]).to(dev)     # in one launch), saving the concatenation and its backward
 
     records, radii, depths, _ = fused.synth_project(
         _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,

@@ -48,6 +48,22 @@ def _make_optimizer(n, device, seed=0, with_state=True):
     return opt
 
 
+def _to_cuda(opt):
+    """a CUDA twin of a CPU optimiser: same group layout, bit-identical parameters and Adam moments (stepping the
+    two on their own devices would not give identical bits)"""
+    groups, pairs = [], []
+    for g in opt.param_groups:
+        ps = [torch.nn.Parameter(p.detach().cuda(), requires_grad=p.requires_grad) for p in g["params"]]
+        pairs += list(zip(g["params"], ps))
+        groups.append({"params": ps, "lr": g["lr"], "name": g["name"]})
+    twin = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+    for p_cpu, p_gpu in pairs:
+        st = opt.state.get(p_cpu)
+        if st:
+            twin.state[p_gpu] = {"step": st["step"].clone(), "exp_avg": st["exp_avg"].cuda(), "exp_avg_sq": st["exp_avg_sq"].cuda()}
+    return twin
+
+
 def _same(a_opt, b_opt, a_out, b_out):
     assert list(a_out) == list(b_out)
     for k in a_out:
@@ -127,7 +143,8 @@ def test_oracle_matches_reference_optimizer_surgery():
 def test_prune_optimizer_matches_oracle_bit_exact(n, keep):
     from mobgs_b200.densify import prune_optimizer
     from oracle import densify_ref as O
-    cpu, gpu = _make_optimizer(n, "cpu", seed=n), _make_optimizer(n, "cuda", seed=n)
+    cpu = _make_optimizer(n, "cpu", seed=n)
+    gpu = _to_cuda(cpu)
     mask = torch.rand(n, generator=torch.Generator().manual_seed(7)) < keep
     stats = [torch.rand(n, 1), torch.rand(n), torch.rand(n, 3)]          # xyz_gradient_accum / max_radii2D / _deformation_accum
     want = O.prune_optimizer(cpu, mask)
@@ -148,7 +165,8 @@ def test_prune_optimizer_matches_oracle_bit_exact(n, keep):
 def test_cat_tensors_to_optimizer_matches_oracle_bit_exact(n, n_new):
     from mobgs_b200.densify import cat_tensors_to_optimizer
     from oracle import densify_ref as O
-    cpu, gpu = _make_optimizer(n, "cpu", seed=n + 1, with_state=n > 0), _make_optimizer(n, "cuda", seed=n + 1, with_state=n > 0)
+    cpu = _make_optimizer(n, "cpu", seed=n + 1, with_state=n > 0)
+    gpu = _to_cuda(cpu)
     g = torch.Generator().manual_seed(3)
     ext = {name: (torch.randint(4, 13, (n_new,) + shape, generator=g) if dt == torch.int64 else torch.randn((n_new,) + shape, generator=g))
            for name, shape, dt, _ in GROUPS}
