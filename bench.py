@@ -515,6 +515,12 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001  (the headline must survive a failure of the extra measurement)
             extra["full_step"] = {"error": f"{type(e).__name__}: {e}"}
 
+    if not args.no_extras:
+        try:    # BASELINE configs[3]: batch 2 x K = 9 sub-frames of the 1 M / 1080p scene, the 18 (view, sub-frame) items split over the ranks
+            extra["strong_scaling"] = measure_strong_scaling(args, dev, rank, world, flush, local)
+        except Exception as e:  # noqa: BLE001
+            extra["strong_scaling"] = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -541,6 +547,65 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_strong_scaling(args, dev, rank, world, flush, local, workload="c4_1M_1080p_K9", views=2):
+    """One optimiser step's renders at the reference's batch size (arguments/stereo/default.py:20: 2 views) and
+    num_warp (arguments/__init__.py:214: K = 9) on the 1 M / 1080p scene — BASELINE configs[3] — with the
+    views x K (view, sub-frame) work items split over the ranks in contiguous blocks (mobgs_b200.dist.shard_subframes).
+    TOTAL work is fixed: collective 1 = one all-reduce of the per-view partial image sums [views,3,H,W] in the
+    forward, collective 2 = the Gaussian-gradient all-reduce.  The same code runs at N = 1 (no collectives): the
+    driver's per-N lines give the strong-scaling curve."""
+    import torch
+    import torch.distributed as dist
+    from mobgs_b200.dist import FlatGradients, all_reduce_sum, shard_subframes
+    from mobgs_b200.losses import l1_loss
+    from mobgs_b200.subframes import render_subframes
+    job = GpuJob(workload, dev, 0, 1, False)            # same scene / inputs on every rank
+    W, H, K = job.W, job.H, job.K
+    mine = shard_subframes(views, K, rank, world)
+    gen = torch.Generator().manual_seed(77)
+    tgts = torch.rand(views, 3, H, W, generator=gen).to(dev)
+    view_v, tpoly_v, rays_v = [], [], []
+    for v in range(views):
+        a = math.radians(0.8 * (v - (views - 1) / 2))
+        R = torch.eye(4); R[0, 0], R[0, 2], R[2, 0], R[2, 2] = math.cos(a), math.sin(a), -math.sin(a), math.cos(a)
+        vm = (job.view_host @ R).to(dev)
+        view_v.append(vm); tpoly_v.append(job.tpoly_d + 0.05 * v); rays_v.append(build_rays(vm, job.intr, W, H))
+    fg = {}
+
+    def step():
+        for p in job.all_params:
+            p.grad = None
+        partial = []
+        for v in range(views):
+            ks = [r for (vv, r) in mine if vv == v]
+            if ks:
+                sl = slice(ks[0].start, ks[0].stop)
+                out = render_subframes(job.stat, job.dyn, view_v[v][sl], job.Kmat, tpoly_v[v][sl].clamp(0, 1), tpoly_v[v][sl],
+                                       rays_v[v][sl], job.bg, W, H)
+                partial.append(out["subframes"].sum(dim=0))
+            else:
+                partial.append(torch.zeros(3, H, W, device=dev))
+        pred = all_reduce_sum(torch.stack(partial)) / K + 1e-10          # train.py:540-541 for every view at once
+        loss = l1_loss(pred, tgts)
+        if loss.requires_grad:
+            loss.backward()
+        if world > 1:
+            if "fg" not in fg:
+                ps = [p for p in job.all_params if p is not job.stat.control_xyz and p is not job.stat._omega
+                      and p is not job.stat._features_t and p is not job.stat._trbf_center and p is not job.dyn._trbf_center
+                      and p is not job.dyn._xyz and all(p is not q for q in job.stat.rgbdecoder.parameters())]
+                fg["fg"] = FlatGradients(ps, inplace_shared=False)
+            fg["fg"].reduce()
+        return loss
+
+    ms, _ = timed(step, flush, max(3, min(args.steps, 10)), 3, local, world)
+    return {"workload": workload, "views": views, "subframes": K, "items": views * K, "n_gpus": world,
+            "items_on_rank0": sum(len(r) for _, r in shard_subframes(views, K, 0, world)),
+            "ms_per_step": ms, "scaling": "strong",
+            "Mpix_per_s": views * K * W * H / (ms * 1e-3) / 1e6,
+            "collectives": "all-reduce of [views,3,H,W] partial image sums (forward) + Gaussian-gradient all-reduce"}
 
 
 def measure_intersections(stat, dyn, view, Kmat, tpoly, W, H):

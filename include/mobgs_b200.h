@@ -393,6 +393,68 @@ typedef struct {
 int mobgs_hexplane_mlp_fwd(const MobgsHexMlpFwd* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a11 backward on the tensor cores (the reference differentiates deform_network through autograd:
+ * scene/deformation.py:158-199 + scene/hexplane.py:19-108; 18 grid_sample_backward + ~16 cuBLAS launches).
+ *
+ * Step 1, mobgs_hexplane_mlp_bwd — one CTA per 128 points, like the forward: recomputes the forward
+ * (features, three heads) on tcgen05, evaluates the post-processing VJP per point, then runs the DATA
+ * gradient chain  g_o -> (Wb) -> relu' -> (Wa) -> sum over heads -> relu' -> (W0) -> g_feat  as 3xTF32
+ * tcgen05 GEMMs against pre-tiled TRANSPOSED weights, with the accumulators in TMEM.  Besides the input
+ * gradients it leaves, feature-major ([rows][ld], ld = padded point count, zero for points >= N), the
+ * operands the weight gradients contract over the points.
+ * Step 2, mobgs_hexplane_wgrad — C[m][n] += sum_k A[m][k] B[n][k] with k = the points: split-K tcgen05
+ * GEMMs (K-major on both sides thanks to the feature-major layout), accumulators resident in TMEM over a
+ * CTA's whole K range, one atomic flush per CTA; row sums of one operand = the bias gradient.
+ * Step 3 is the existing mobgs_hexplane_features_bwd (plane scatter + coordinate gradients) on g_feat. */
+typedef struct {
+  int32_t N;
+  int32_t ld;                /* multiple of 128, >= N */
+  const float* pts;          /* [N,3] */
+  const float* rots;         /* [N,4] */
+  const float* times;        /* [N] */
+  float aabb[6];
+  int32_t levels, net_width, plane_features;
+  const float* planes[24];   /* channels-last [H,W,32] as MobgsHexMlpFwd */
+  int32_t plane_w[24];
+  int32_t plane_h[24];
+  const float* w0; const float* b0; const float* wa; const float* ba; const float* wb; const float* bb;   /* as MobgsHexMlpFwd */
+  /* transposed weights, tiled {hi,lo} x [K/4][rows][4] like the forward's:
+   *   w0_t: W0^T rows [0,64) then rows [64, 32*levels), K = 128
+   *   wa_t: per head, Wa^T rows [0,64) then [64,128), K = 128
+   *   wb_t: per head, (Wb zero-padded to 16 outputs)^T rows [0,64) then [64,128), K = 16 */
+  const float* w0_t; const float* wa_t; const float* wb_t;
+  const float* g_out_pts;    /* [N,3] or NULL (= zero) */
+  const float* g_out_scales; /* [N,3] or NULL */
+  const float* g_out_rots;   /* [N,4] or NULL */
+  float* g_pts;              /* [N,3] d loss / d pts through out_pts = R (pts + dx) only (the grid path is step 3) */
+  float* g_scales;           /* [N,3] */
+  float* g_rots;             /* [N,4] */
+  float* g_feat;             /* [N, 32*levels] */
+  float* featT;              /* [32*levels][ld] */
+  float* a1T;                /* [128][ld]     relu(h0)                       */
+  float* a2T;                /* [3][128][ld]  relu(z1) per head              */
+  float* gz1T;               /* [3][128][ld]  d loss / d z1 per head         */
+  float* goT;                /* [3][16][ld]   d loss / d head output (padded)*/
+  float* gh0T;               /* [128][ld]     d loss / d h0                  */
+} MobgsHexMlpBwd;
+int mobgs_hexplane_mlp_bwd(const MobgsHexMlpBwd* a, void* stream);
+
+#define MOBGS_WGRAD_MAX 8
+typedef struct {
+  int32_t n_problems;
+  int32_t ld;                          /* contraction length (padded points), multiple of 128 */
+  const float* A[MOBGS_WGRAD_MAX];     /* [128][ld] */
+  const float* B[MOBGS_WGRAD_MAX];     /* [n_cols][ld] */
+  int32_t n_cols[MOBGS_WGRAD_MAX];     /* 16..128, multiple of 16 */
+  float* C[MOBGS_WGRAD_MAX];           /* accumulated (zeroed by the caller): [128][ldc], or [n_cols][ldc] when transposed */
+  int32_t ldc[MOBGS_WGRAD_MAX];
+  int32_t transpose_out[MOBGS_WGRAD_MAX];
+  float* bias[MOBGS_WGRAD_MAX];        /* row sums of A (bias_from = 1: [128]) or B (2: [n_cols]), accumulated; NULL / 0 = none */
+  int32_t bias_from[MOBGS_WGRAD_MAX];
+} MobgsHexWgrad;
+int mobgs_hexplane_wgrad(const MobgsHexWgrad* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Flow records for get_flow() (gaussian_renderer/__init__.py:435-471), K exposure offsets at once.
  * records [K+1,N,16]: set 0 = geometry at the mid time, sets 1..K = geometry at the K exposure
  * times (same camera).  For every k two record sets are written to flow_records [2K,N,16]:

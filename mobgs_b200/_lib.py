@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "hexplane_mlp_bwd.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -198,6 +198,28 @@ class HexMlpFwd(C.Structure):
                 ("out_scales", C.c_void_p), ("out_rots", C.c_void_p)]
 
 
+class HexMlpBwd(C.Structure):
+    _fields_ = [("N", C.c_int32), ("ld", C.c_int32), ("pts", C.c_void_p), ("rots", C.c_void_p), ("times", C.c_void_p),
+                ("aabb", C.c_float * 6), ("levels", C.c_int32), ("net_width", C.c_int32), ("plane_features", C.c_int32),
+                ("planes", C.c_void_p * 24), ("plane_w", C.c_int32 * 24), ("plane_h", C.c_int32 * 24),
+                ("w0", C.c_void_p), ("b0", C.c_void_p), ("wa", C.c_void_p), ("ba", C.c_void_p), ("wb", C.c_void_p),
+                ("bb", C.c_void_p), ("w0_t", C.c_void_p), ("wa_t", C.c_void_p), ("wb_t", C.c_void_p),
+                ("g_out_pts", C.c_void_p), ("g_out_scales", C.c_void_p), ("g_out_rots", C.c_void_p),
+                ("g_pts", C.c_void_p), ("g_scales", C.c_void_p), ("g_rots", C.c_void_p), ("g_feat", C.c_void_p),
+                ("featT", C.c_void_p), ("a1T", C.c_void_p), ("a2T", C.c_void_p), ("gz1T", C.c_void_p),
+                ("goT", C.c_void_p), ("gh0T", C.c_void_p)]
+
+
+WGRAD_MAX = 8
+
+
+class HexWgrad(C.Structure):
+    _fields_ = [("n_problems", C.c_int32), ("ld", C.c_int32), ("A", C.c_void_p * WGRAD_MAX), ("B", C.c_void_p * WGRAD_MAX),
+                ("n_cols", C.c_int32 * WGRAD_MAX), ("C", C.c_void_p * WGRAD_MAX), ("ldc", C.c_int32 * WGRAD_MAX),
+                ("transpose_out", C.c_int32 * WGRAD_MAX), ("bias", C.c_void_p * WGRAD_MAX),
+                ("bias_from", C.c_int32 * WGRAD_MAX)]
+
+
 class FlowRecFwd(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("records", C.c_void_p), ("flow_records", C.c_void_p)]
 
@@ -286,6 +308,8 @@ ENTRY_POINTS = {
     "mobgs_decode_fwd": DecodeFwd,
     "mobgs_decode_bwd": DecodeBwd,
     "mobgs_hexplane_mlp_fwd": HexMlpFwd,
+    "mobgs_hexplane_mlp_bwd": HexMlpBwd,
+    "mobgs_hexplane_wgrad": HexWgrad,
     "mobgs_flow_records_fwd": FlowRecFwd,
     "mobgs_flow_records_bwd": FlowRecBwd,
     "mobgs_midflow_records_fwd": FlowRecFwd,

@@ -9,10 +9,10 @@ Covered configuration = the Stereo-Blur configs (arguments/stereo/*.py): net_wid
 defor_depth 1, 32 features per plane, no_grid/static_mlp/empty_voxel/apply_rotation False,
 grid_pe 0.  Anything else raises NotImplementedError (no fallback).
 
-Status: the forward is the fused tcgen05 kernel.  Backward: the HexPlane gather and its VJP
-(plane scatter + coordinate gradients) are native kernels (csrc/hexplane_grid.cu); the dense layers
-are recomputed and differentiated through cuBLAS fp32 GEMMs (plain library calls) — the module is
-not on the reference's live training path.  Round-2 item: tcgen05 dgrad/wgrad.
+Forward: the fused tcgen05 kernel.  Backward: tcgen05 as well (csrc/hexplane_mlp_bwd.cu) — forward recompute +
+post-processing VJP + data-gradient GEMMs per 128-point tile, split-K weight-gradient GEMMs over the points —
+plus the native HexPlane scatter (csrc/hexplane_grid.cu).  No library GEMM on the path.  (The module is not on
+the reference's live training path)
 """
 from __future__ import annotations
 
@@ -57,8 +57,30 @@ def pack_weights(w0, b0, heads):
             torch.cat(wb_list).contiguous(), torch.cat(bb_list).contiguous())
 
 
+def pack_weights_t(w0, heads):
+    """Transposed weights for the data-gradient GEMMs of mobgs_hexplane_mlp_bwd, tiled like the forward's:
+    W0^T rows [0,64) then [64,K0); per head Wa^T in two 64-row halves; per head (Wb padded to 16 outputs)^T in
+    two 64-row halves (K = 16)."""
+    dev = w0.device
+    w0t = w0.float().t().contiguous()                          # [K0, 128]
+    K0 = w0t.shape[0]
+    parts = [_tile(w0t[:min(64, K0)])]
+    if K0 > 64:
+        parts.append(_tile(w0t[64:]))
+    wa_t = torch.cat([_tile(Wa.float().t().contiguous()[h * 64:(h + 1) * 64]) for Wa, _, _, _ in heads for h in range(2)])
+    wb_parts = []
+    for _, _, Wb, _ in heads:
+        pad = torch.zeros(16, NET_WIDTH, device=dev)
+        pad[:Wb.shape[0]] = Wb.float()
+        padt = pad.t().contiguous()                            # [128, 16]
+        wb_parts += [_tile(padt[h * 64:(h + 1) * 64]) for h in range(2)]
+    return torch.cat(parts).contiguous(), wa_t.contiguous(), torch.cat(wb_parts).contiguous()
+
+
 class _FusedDeform(torch.autograd.Function):
-    """forward = fused kernel; backward = native gather/scatter + cuBLAS for the dense layers."""
+    """forward = the fused tcgen05 kernel; backward = tcgen05 too: mobgs_hexplane_mlp_bwd (forward recompute +
+    post-processing VJP + data-gradient GEMMs), mobgs_hexplane_wgrad (split-K weight / bias gradients) and the
+    native HexPlane scatter mobgs_hexplane_features_bwd.  No library GEMM anywhere on the path."""
 
     @staticmethod
     def forward(ctx, n_levels, aabb, pts, scales, rots, times, *params):
@@ -73,31 +95,84 @@ class _FusedDeform(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_pts, g_scales, g_rots):
-        """HexPlane gather and scatter are native kernels (csrc/hexplane_grid.cu); the dense layers are
-        differentiated through cuBLAS fp32 GEMMs (torch.nn.functional.linear) on the recomputed
-        features — plain library GEMMs, the only part of the path that is not hand-written."""
         aabb, pts, scales, rots, times, *params = ctx.saved_tensors
         nl = ctx.n_levels
         planes = [list(params[l * 6:(l + 1) * 6]) for l in range(nl)]
         rest = params[nl * 6:]
+        w0, b0 = rest[0], rest[1]
+        heads = [tuple(rest[2 + 4 * h: 6 + 4 * h]) for h in range(3)]
         need = ctx.needs_input_grad[2:]
-        prev = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
-        try:
-            feat = hexplane_features(pts, times, aabb, planes)
-            with torch.enable_grad():
-                leaves = [t.detach().requires_grad_(True) for t in (feat, pts, scales, rots, *rest)]
-                lf, lp, ls, lr, *lw = leaves
-                heads = [tuple(lw[2 + 4 * h: 6 + 4 * h]) for h in range(3)]
-                outs = _mlp_and_post(lf, lp, ls, lr, lw[0], lw[1], heads)
-                gs = [g if g is not None else torch.zeros_like(o) for g, o in zip((g_pts, g_scales, g_rots), outs)]
-                grads = torch.autograd.grad(outs, leaves, gs, allow_unused=True)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = prev
-        g_feat, g_p_direct, g_s, g_r, *g_w = grads
+        dev = pts.device
+        pts_c, rots_c = _f32c(pts[:, :3].detach()), _f32c(rots[:, :4].detach())
+        times_c = _f32c(times.detach().reshape(-1))
+        N = pts_c.shape[0]
+        K0 = PLANE_FEATURES * nl
+        ld = (N + 127) // 128 * 128
+        W = NET_WIDTH
+        stream = _stream()
+
+        # ---- step 1: forward recompute + data gradients (one CTA per 128 points) ----
+        a = L.HexMlpBwd()
+        a.N, a.ld = N, ld
+        a.pts, a.rots, a.times = _p(pts_c), _p(rots_c), _p(times_c)
+        ab = _aabb_host(aabb)
+        for i in range(6):
+            a.aabb[i] = ab[i]
+        a.levels, a.net_width, a.plane_features = nl, W, PLANE_FEATURES
+        cl, packed = _packed_operands(planes, w0, b0, heads)
+        for i, t in enumerate(cl):
+            a.planes[i] = t.data_ptr()
+            a.plane_h[i], a.plane_w[i] = t.shape[0], t.shape[1]
+        a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in packed)
+        packed_t = _packed_transposed(w0, heads)
+        a.w0_t, a.wa_t, a.wb_t = (_p(t) for t in packed_t)
+        gs = [None if g is None else _f32c(g) for g in (g_pts, g_scales, g_rots)]
+        a.g_out_pts, a.g_out_scales, a.g_out_rots = (_p(g) for g in gs)
+        g_p_direct = torch.empty(N, 3, device=dev)
+        g_s = torch.empty(N, 3, device=dev)
+        g_r = torch.empty(N, 4, device=dev)
+        g_feat = torch.empty(N, K0, device=dev)
+        a.g_pts, a.g_scales, a.g_rots, a.g_feat = _p(g_p_direct), _p(g_s), _p(g_r), _p(g_feat)
+        rows = (K0, W, 3 * W, 3 * W, 3 * 16, W)                 # featT a1T a2T gz1T goT gh0T
+        scratch = torch.empty(sum(rows) * ld, device=dev)
+        views, off = [], 0
+        for r in rows:
+            views.append(scratch[off * ld:(off + r) * ld].view(r, ld))
+            off += r
+        featT, a1T, a2T, gz1T, goT, gh0T = views
+        a.featT, a.a1T, a.a2T, a.gz1T, a.goT, a.gh0T = (_p(t) for t in views)
+        L.call("mobgs_hexplane_mlp_bwd", a, stream)
+
+        # ---- step 2: weight / bias gradients, contraction over the points ----
+        acc = torch.zeros(W * K0 + W + 3 * W * W + 3 * W + 3 * 16 * W + 3 * 16, device=dev)
+        o = 0
+        def take(n, shape):
+            nonlocal o
+            t = acc[o:o + n].view(shape)
+            o += n
+            return t
+        dW0, db0 = take(W * K0, (W, K0)), take(W, (W,))
+        dWa, dba = take(3 * W * W, (3, W, W)), take(3 * W, (3, W))
+        dWb, dbb = take(3 * 16 * W, (3, 16, W)), take(3 * 16, (3, 16))
+        wg = L.HexWgrad()
+        wg.ld = ld
+        probs = [(gh0T, featT, K0, dW0, K0, 0, db0, 1)]
+        probs += [(gz1T[h * W:(h + 1) * W], a1T, W, dWa[h], W, 0, dba[h], 1) for h in range(3)]
+        probs += [(a2T[h * W:(h + 1) * W], goT[h * 16:(h + 1) * 16], 16, dWb[h], W, 1, dbb[h], 2) for h in range(3)]
+        wg.n_problems = len(probs)
+        for i, (A, B, ncol, Cm, ldc, tr, bias, bfrom) in enumerate(probs):
+            wg.A[i], wg.B[i], wg.n_cols[i], wg.C[i], wg.ldc[i] = A.data_ptr(), B.data_ptr(), ncol, Cm.data_ptr(), ldc
+            wg.transpose_out[i], wg.bias[i], wg.bias_from[i] = tr, bias.data_ptr(), bfrom
+        L.call("mobgs_hexplane_wgrad", wg, stream)
+
+        # ---- step 3: HexPlane scatter + coordinate gradients ----
         g_planes, g_p_grid, g_t = hexplane_features_vjp(pts, times, aabb, planes, g_feat)
-        g_p = g_p_grid if g_p_direct is None else g_p_direct + g_p_grid
-        full = [g_p, g_s, g_r, g_t.reshape(times.shape)] + g_planes + list(g_w)
+        g_p = g_p_direct + g_p_grid
+        g_w = [dW0, db0]
+        for h in range(3):
+            n_out = heads[h][2].shape[0]
+            g_w += [dWa[h], dba[h], dWb[h, :n_out], dbb[h, :n_out]]
+        full = [g_p, g_s, g_r, g_t.reshape(times.shape)] + g_planes + g_w
         full = [g if n else None for g, n in zip(full, need)]
         return (None, None, *full)
 
@@ -145,28 +220,6 @@ def hexplane_features_vjp(pts, times, aabb, planes, g_feat):
     return [t.permute(2, 0, 1)[None].contiguous() for t in g_cl], g_pts, g_times
 
 
-def _mlp_and_post(feat, pts, scales, rots, w0, b0, heads):
-    """Dense layers + forward_dynamic2 post-processing as torch ops (differentiated in the backward)."""
-    import math
-    import torch.nn.functional as F
-    hidden = F.linear(feat, w0, b0)
-    dx, ds, dr = [F.linear(torch.relu(F.linear(torch.relu(hidden), Wa, ba)), Wb, bb) for Wa, ba, Wb, bb in heads]
-    nq = torch.cat([torch.ones_like(dx[:, :1]), dx[:, 3:]], dim=1)
-    nq = nq / nq.norm(dim=1, keepdim=True)
-    w, x, y, z = nq[:, 0], nq[:, 1], nq[:, 2], nq[:, 3]
-    R = torch.stack([w * w + x * x - y * y - z * z, 2 * x * y - 2 * w * z, 2 * w * y + 2 * x * z,
-                     2 * w * z + 2 * x * y, w * w - x * x + y * y - z * z, 2 * y * z - 2 * w * x,
-                     2 * x * z - 2 * w * y, 2 * w * x + 2 * y * z, w * w - x * x - y * y + z * z], dim=1).view(-1, 3, 3)
-    out_pts = R.bmm((pts + dx[:, :3]).unsqueeze(-1)).squeeze(-1)
-    out_scales = scales + torch.clamp(ds, -math.log(100), math.log(100))
-    q1, q2 = rots + dr, dx[:, 3:]
-    q = torch.stack((q1[:, 0] * q2[:, 0] - q1[:, 1] * q2[:, 1] - q1[:, 2] * q2[:, 2] - q1[:, 3] * q2[:, 3],
-                     q1[:, 0] * q2[:, 1] + q1[:, 1] * q2[:, 0] + q1[:, 2] * q2[:, 3] - q1[:, 3] * q2[:, 2],
-                     q1[:, 0] * q2[:, 2] - q1[:, 1] * q2[:, 3] + q1[:, 2] * q2[:, 0] + q1[:, 3] * q2[:, 1],
-                     q1[:, 0] * q2[:, 3] + q1[:, 1] * q2[:, 2] - q1[:, 2] * q2[:, 1] + q1[:, 3] * q2[:, 0]), dim=1)
-    return out_pts, out_scales, q / q.norm(dim=1, keepdim=True)
-
-
 def fused_forward_raw(pts, scales, rots, times, aabb, planes: Sequence[Sequence[torch.Tensor]], w0, b0, heads):
     """planes[l][p]: [1,32,H,W] parameters (reference layout); aabb: [2,3] tensor."""
     flat = [p for level in planes for p in level] + [w0, b0] + [t for h in heads for t in h]
@@ -211,6 +264,18 @@ def _packed_operands(planes, w0, b0, heads):
     packed = pack_weights(w0.detach(), b0.detach(), [tuple(t.detach() for t in h) for h in heads])
     _PACK_CACHE["last"] = (key, cl, packed)
     return cl, packed
+
+
+def _packed_transposed(w0, heads):
+    """cached like _packed_operands (tensor objects + version counters)"""
+    flat = [w0] + [t for h in heads for t in (h[0], h[2])]
+    key = [(t, t._version) for t in flat]
+    hit = _PACK_CACHE.get("last_t")
+    if hit is not None and len(hit[0]) == len(key) and all(a is b and va == vb for (a, va), (b, vb) in zip(hit[0], key)):
+        return hit[1]
+    packed = pack_weights_t(w0.detach(), [tuple(t.detach() for t in h) for h in heads])
+    _PACK_CACHE["last_t"] = (key, packed)
+    return packed
 
 
 def _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads):

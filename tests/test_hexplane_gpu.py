@@ -137,3 +137,76 @@ def test_fused_adam_step_invalidates_the_packed_operand_cache():
     assert (got[0] - p0.detach()).abs().max() > 1e-3          # the step moved the output ...
     for g, w, name in zip(got, want, ("pts", "scales", "rots")):
         _cmp(g, w, name)                                      # ... to what the updated weights give
+
+
+@pytest.mark.parametrize("ncol,transpose,n_pts", [(128, False, 1000), (96, False, 257), (16, True, 5000), (64, False, 128)])
+def test_wgrad_split_k_gemm_matches_fp64(ncol, transpose, n_pts):
+    """mobgs_hexplane_wgrad alone: C[m][n] += sum_k A[m][k] B[n][k] (3xTF32 on tcgen05, split-K with TMEM-resident
+    accumulators), row sums as bias gradients — against a float64 matmul; 1e-5 relative to the result's scale."""
+    from mobgs_b200 import _lib as L
+    g = torch.Generator().manual_seed(ncol + n_pts)
+    ld = (n_pts + 127) // 128 * 128
+    A = torch.zeros(128, ld)
+    B = torch.zeros(ncol, ld)
+    A[:, :n_pts] = torch.randn(128, n_pts, generator=g)
+    B[:, :n_pts] = torch.randn(ncol, n_pts, generator=g)
+    want = A.double() @ B.double().t()
+    Ac, Bc = A.cuda(), B.cuda()
+    C = torch.zeros((ncol, 128) if transpose else (128, ncol), device="cuda")
+    bias_a, bias_b = torch.zeros(128, device="cuda"), torch.zeros(ncol, device="cuda")
+    wg = L.HexWgrad()
+    wg.n_problems, wg.ld = 2, ld
+    for i, (bias, bfrom) in enumerate(((bias_a, 1), (bias_b, 2))):
+        wg.A[i], wg.B[i], wg.n_cols[i] = Ac.data_ptr(), Bc.data_ptr(), ncol
+        wg.C[i], wg.ldc[i], wg.transpose_out[i] = C.data_ptr(), (128 if transpose else ncol), int(transpose)
+        wg.bias[i], wg.bias_from[i] = bias.data_ptr(), bfrom
+    L.call("mobgs_hexplane_wgrad", wg, L.current_stream())
+    torch.cuda.synchronize()
+    got = (C.t() if transpose else C).cpu().double() / 2          # both problems accumulate into the same C
+    scale = float(want.abs().max())
+    assert (got - want).abs().max() <= 1e-5 * scale, float((got - want).abs().max() / scale)
+    assert (bias_a.cpu().double() - A.double().sum(1)).abs().max() <= 1e-4 * float(A.double().sum(1).abs().max())
+    assert (bias_b.cpu().double() - B.double().sum(1)).abs().max() <= 1e-4 * float(B.double().sum(1).abs().max())
+
+
+@pytest.mark.parametrize("n,base_res", [(3000, 16), (129, 16), (1, 16)])
+def test_tcgen05_backward_matches_oracle_autograd(n, base_res):
+    """Every gradient of the fused module (inputs, planes, all MLP weights and biases) through the tcgen05 backward
+    (mobgs_hexplane_mlp_bwd + mobgs_hexplane_wgrad + the native plane scatter) against autograd of the oracle
+    restatement on the CPU; 1e-4 of the tensor's max / 1e-3 relative."""
+    from mobgs_b200.deformation import HexPlaneMLP
+    from oracle.hexplane_ref import deform_forward_ref
+    torch.manual_seed(n + 5)
+    net = HexPlaneMLP(_hexplane_args(base_res))
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.2, 0.2)
+            elif "grids" in name:
+                p.add_(0.1 * torch.randn_like(p))
+            elif p.requires_grad:
+                torch.nn.init.xavier_uniform_(p)
+    net.set_aabb([1.3, 1.1, 1.2], [-1.2, -1.0, -1.4])
+    pts = (torch.rand(n, 3) * 3 - 1.5).requires_grad_(True)
+    scales = (torch.randn(n, 3) * 0.3 - 3).requires_grad_(True)
+    rots = torch.randn(n, 4).requires_grad_(True)
+    t = torch.rand(n, 1)
+    w = [torch.randn(n, 3), torch.randn(n, 3), torch.randn(n, 4)]
+    outs = deform_forward_ref(net, pts, scales, rots, t)
+    sum((o * wi).sum() for o, wi in zip(outs, w)).backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    ref_in = [pts.grad.clone(), scales.grad.clone(), rots.grad.clone()]
+    net.zero_grad(set_to_none=True)
+    net.cuda()
+    ins = [x.detach().cuda().requires_grad_(True) for x in (pts, scales, rots)]
+    got = net(ins[0], ins[1], ins[2], t.cuda())
+    sum((o * wi.cuda()).sum() for o, wi in zip(got, w)).backward()
+    for g, r, name in zip(ins, ref_in, ("pts", "scales", "rots")):
+        _cmp(g.grad, r, "grad_" + name, atol=1e-4 * max(1.0, float(r.abs().max())))
+    checked = 0
+    for k, p in net.named_parameters():
+        if k in ref:
+            assert p.grad is not None, k
+            _cmp(p.grad, ref[k], k, atol=1e-4 * max(1.0, float(ref[k].abs().max())))
+            checked += 1
+    assert checked >= 30
