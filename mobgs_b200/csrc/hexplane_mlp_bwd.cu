@@ -250,9 +250,9 @@ __global__ void __launch_bounds__(kHexThreads, 1) hexplane_mlp_bwd_kernel(const 
     ga[2] = -g4[0] * q2[2] + g4[1] * q2[3] + g4[2] * q2[0] - g4[3] * q2[1];
     ga[3] = -g4[0] * q2[3] - g4[1] * q2[2] + g4[2] * q2[1] + g4[3] * q2[0];
     gb[0] = g4[0] * q1[0] + g4[1] * q1[1] + g4[2] * q1[2] + g4[3] * q1[3];
-    gb[1] = -g4[0] * q1[1] + g4[1] * q1[0] - g4[2] * q1[3] + g4[3] * q1[2];
-    gb[2] = -g4[0] * q1[2] + g4[1] * q1[3] + g4[2] * q1[0] - g4[3] * q1[1];
-    gb[3] = -g4[0] * q1[3] - g4[1] * q1[2] + g4[2] * q1[1] + g4[3] * q1[0];
+    gb[1] = -g4[0] * q1[1] + g4[1] * q1[0] + g4[2] * q1[3] - g4[3] * q1[2];
+    gb[2] = -g4[0] * q1[2] - g4[1] * q1[3] + g4[2] * q1[0] + g4[3] * q1[1];
+    gb[3] = -g4[0] * q1[3] + g4[1] * q1[2] - g4[2] * q1[1] + g4[3] * q1[0];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { go2[i] = ga[i]; go0[3 + i] = gb[i]; }
     // out_pts = R(w,x,y,z) (pts + dx[0:3]),  (w,x,y,z) = (1, dx3, dx4, dx5) / |(1, dx3, dx4, dx5, dx6)|

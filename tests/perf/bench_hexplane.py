@@ -44,9 +44,34 @@ def main(n=150_000, iters=20):
         a = net(pts, scales, rots, t)
         b = deform_forward_ref(net, pts, scales, rots, t)
         err = max(float((x - y).abs().max()) for x, y in zip(a, b))
+    # forward + backward (every gradient: inputs, planes, weights): tcgen05 path vs torch autograd (cuBLAS fp32)
+    ins = [x.clone().requires_grad_(True) for x in (pts, scales, rots)]
+    params = [p for p in net.parameters() if p.requires_grad]
+
+    def train_fused():
+        for p in params + ins:
+            p.grad = None
+        o = net(ins[0], ins[1], ins[2], t)
+        (o[0].sum() + o[1].sum() + o[2].sum()).backward()
+
+    def train_torch():
+        for p in params + ins:
+            p.grad = None
+        o = deform_forward_ref(net, ins[0], ins[1], ins[2], t)
+        (o[0].sum() + o[1].sum() + o[2].sum()).backward()
+
+    ms_fb_fused, ms_fb_torch = timeit(train_fused), timeit(train_torch)
+    from mobgs_b200 import _lib
+    _lib.TIMING = {}
+    train_fused()
+    torch.cuda.synchronize()
+    kern = {k: round(sum(a.elapsed_time(b) for a, b in v), 4) for k, v in _lib.TIMING.items()}
+    _lib.TIMING = None
     flops = 2 * 63232 * n * 3          # 3xTF32: three tensor-core MACs per logical MAC
     print(json.dumps({"points": n, "fused_ms": ms_fused, "torch_fp32_ms": ms_torch, "speedup": ms_torch / ms_fused,
                       "max_abs_err_vs_torch": err, "issued_tf32_tflops": flops / ms_fused / 1e9,
+                      "fwd_bwd_fused_ms": ms_fb_fused, "fwd_bwd_torch_fp32_ms": ms_fb_torch,
+                      "fwd_bwd_speedup": ms_fb_torch / ms_fb_fused, "fwd_bwd_kernel_ms": kern,
                       "note": "fused_ms includes the per-call host-side weight tiling + channels-last plane copies"}))
 
 

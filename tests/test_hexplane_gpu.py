@@ -207,6 +207,8 @@ def test_tcgen05_backward_matches_oracle_autograd(n, base_res):
     for k, p in net.named_parameters():
         if k in ref:
             assert p.grad is not None, k
-            _cmp(p.grad, ref[k], k, atol=1e-4 * max(1.0, float(ref[k].abs().max())))
+            # plane gradients are fp32 atomic sums over up to thousands of points (order not reproducible): 3e-4
+            tol = (3e-4 if "grids" in k else 1e-4) * max(1.0, float(ref[k].abs().max()))
+            _cmp(p.grad, ref[k], k, atol=tol)
             checked += 1
     assert checked >= 30
