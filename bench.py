@@ -437,6 +437,10 @@ def run_ours(args):
     _lib.load()
 
     shard_sub = args.shard == "subframes" and world > 1
+    overlap = world > 1 and not shard_sub and not args.no_overlap
+    if overlap:     # chunked projection backward, each chunk's gradient all-reduce on a side stream (mobgs_b200.fused.GradSink)
+        from mobgs_b200.dist import overlap_gradient_allreduce
+        overlap_gradient_allreduce(True, n_chunks=args.overlap_chunks)
     job = GpuJob(args.workload, dev, rank, world, shard_sub)
     W, H, K, N = job.W, job.H, job.K, job.N
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
@@ -515,6 +519,9 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001  (the headline must survive a failure of the extra measurement)
             extra["full_step"] = {"error": f"{type(e).__name__}: {e}"}
 
+    if overlap:
+        from mobgs_b200.dist import overlap_gradient_allreduce
+        overlap_gradient_allreduce(False)
     if not args.no_extras:
         try:    # BASELINE configs[3]: batch 2 x K = 9 sub-frames of the 1 M / 1080p scene, the 18 (view, sub-frame) items split over the ranks
             extra["strong_scaling"] = measure_strong_scaling(args, dev, rank, world, flush, local)
@@ -544,6 +551,9 @@ def run_ours(args):
         line.update(extra)
         if world > 1:
             line["allreduce_bytes_per_step"] = job.stats.get("allreduce_bytes")
+            line["gradient_allreduce"] = (f"overlapped: projection backward in {args.overlap_chunks} Gaussian ranges, NCCL "
+                                          "all-reduce of each range on a side stream" if overlap else
+                                          "one all-reduce after the backward")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -756,6 +766,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra keys of the N=1 line (gpu_on_reference_config, full_step)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking gradient all-reduce after the backward")
+    ap.add_argument("--overlap-chunks", type=int, default=4)
     ap.add_argument("--shard", default="views", choices=["views", "subframes"],
                     help="N>1: 'views' = one view per rank (weak scaling, default); 'subframes' = the K "
                          "sub-frames of one view split across ranks (strong scaling, BASELINE configs[3])")

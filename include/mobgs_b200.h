@@ -160,6 +160,11 @@ typedef struct {
   float* v_control_xyz; float* v_rotation_d; float* v_omega; float* v_scaling_d; float* v_opacity_d;
   float* v_features_dc_d; float* v_features_t; float* v_offset;
   float* v_viewmats;
+  /* Optional Gaussian range [g_lo, g_hi) in the concatenated (static, dynamic) index space (0, 0 = all).  The
+   * gradient pointers keep their meaning (row g of the FULL tensor), so a caller that stores a range's rows in
+   * a private block passes block - g0 * row_floats.  Used to split the backward into chunks whose gradient
+   * all-reduce (NCCL, side stream) overlaps the next chunk's kernel. */
+  int32_t g_lo, g_hi;
 } MobgsSynthBwd;
 int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream);
 
@@ -623,6 +628,19 @@ typedef struct {
 } MobgsCompactRows;
 int mobgs_compact_rows(const MobgsCompactRows* a, void* stream);
 int mobgs_compact_chunk_words(void);
+
+/* dst[i][0..n_words[i]) = src[i][0..n_words[i]) for up to 64 segments in one launch (32-bit words): unpacks the
+ * chunk-major gradient buffer of the overlapped data-parallel backward into the per-parameter gradient tensors. */
+#define MOBGS_COPY_MAX_SEGMENTS 64
+typedef struct {
+  int32_t n_segments;
+  int32_t reserved_;
+  const void* src[MOBGS_COPY_MAX_SEGMENTS];
+  void* dst[MOBGS_COPY_MAX_SEGMENTS];
+  int64_t n_words[MOBGS_COPY_MAX_SEGMENTS];
+  int32_t chunk_begin[MOBGS_COPY_MAX_SEGMENTS + 1];   /* in chunks of mobgs_compact_chunk_words() words */
+} MobgsCopySegments;
+int mobgs_copy_segments(const MobgsCopySegments* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f1 (second half): flow-warp loss of train.py:656-676, forward + backward fused.

@@ -106,7 +106,7 @@ class SynthBwd(C.Structure):
                 ("v_control_xyz", C.c_void_p), ("v_rotation_d", C.c_void_p), ("v_omega", C.c_void_p),
                 ("v_scaling_d", C.c_void_p), ("v_opacity_d", C.c_void_p),
                 ("v_features_dc_d", C.c_void_p), ("v_features_t", C.c_void_p),
-                ("v_offset", C.c_void_p), ("v_viewmats", C.c_void_p)]
+                ("v_offset", C.c_void_p), ("v_viewmats", C.c_void_p), ("g_lo", C.c_int32), ("g_hi", C.c_int32)]
 
 
 class Pack(C.Structure):
@@ -289,7 +289,16 @@ class CompactRows(C.Structure):
                 ("chunk_begin", C.c_int32 * (COMPACT_MAX_TENSORS + 1))]
 
 
-EXTRA_STRUCTS = {"MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+COPY_MAX_SEGMENTS = 64
+
+
+class CopySegments(C.Structure):
+    _fields_ = [("n_segments", C.c_int32), ("reserved_", C.c_int32), ("src", C.c_void_p * COPY_MAX_SEGMENTS),
+                ("dst", C.c_void_p * COPY_MAX_SEGMENTS), ("n_words", C.c_int64 * COPY_MAX_SEGMENTS),
+                ("chunk_begin", C.c_int32 * (COPY_MAX_SEGMENTS + 1))]
+
+
+EXTRA_STRUCTS = {"MobgsHexMlpBwd": HexMlpBwd, "MobgsHexWgrad": HexWgrad, "MobgsCopySegments": CopySegments, "MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -327,6 +336,7 @@ ENTRY_POINTS = {
     "mobgs_adam_chunk_elems": "int",
     "mobgs_compact_rows": CompactRows,
     "mobgs_compact_chunk_words": "int",
+    "mobgs_copy_segments": CopySegments,
 }
 
 _lib = None

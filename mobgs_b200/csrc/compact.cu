@@ -47,9 +47,41 @@ __global__ void __launch_bounds__(kCompactThreads) compact_rows_kernel(const __g
   }
 }
 
+__global__ void __launch_bounds__(kCompactThreads) copy_segments_kernel(const __grid_constant__ MobgsCopySegments a) {
+  __shared__ int s_begin[MOBGS_COPY_MAX_SEGMENTS + 1];
+  for (int i = threadIdx.x; i <= a.n_segments; i += blockDim.x) s_begin[i] = a.chunk_begin[i];
+  __syncthreads();
+  const int total = s_begin[a.n_segments];
+  for (int chunk = blockIdx.x; chunk < total; chunk += gridDim.x) {
+    int lo = 0, hi = a.n_segments - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_begin[mid] <= chunk) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(a.src[lo]);
+    uint32_t* __restrict__ dst = reinterpret_cast<uint32_t*>(a.dst[lo]);
+    const int64_t w0 = (int64_t)(chunk - s_begin[lo]) * kCompactChunk;
+    const int64_t w1 = min(a.n_words[lo], w0 + kCompactChunk);
+    for (int64_t w = w0 + threadIdx.x; w < w1; w += kCompactThreads) dst[w] = src[w];
+  }
+}
+
 }  // namespace mobgs
 
 using namespace mobgs;
+
+extern "C" int mobgs_copy_segments(const MobgsCopySegments* a, void* stream) {
+  MOBGS_REQUIRE(a, "NULL args");
+  MOBGS_REQUIRE(a->n_segments >= 0 && a->n_segments <= MOBGS_COPY_MAX_SEGMENTS, "n_segments out of range");
+  if (a->n_segments == 0) return MOBGS_OK;
+  for (int i = 0; i < a->n_segments; ++i)
+    MOBGS_REQUIRE(a->n_words[i] == 0 || (a->src[i] && a->dst[i]), "segment %d: NULL pointer", i);
+  const int total = a->chunk_begin[a->n_segments];
+  if (total <= 0) return MOBGS_OK;
+  const int grid = total < 148 * 8 ? total : 148 * 8;
+  copy_segments_kernel<<<grid, kCompactThreads, 0, (cudaStream_t)stream>>>(*a);
+  return check_launch("copy_segments");
+}
 
 extern "C" int mobgs_compact_chunk_words(void) { return kCompactChunk; }
 

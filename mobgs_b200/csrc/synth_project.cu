@@ -255,8 +255,10 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSy
   __shared__ CamSmem sm;
   load_cams(sm, a.cams, a.t_spline, a.t_poly);
   const int N = a.st.Ns + a.dy.Nd;
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool in_range = g < N;
+  // [g_lo, g_hi): the Gaussians this launch differentiates (0, 0 = all) — a data-parallel caller splits the
+  // backward into ranges so that the all-reduce of one range's gradients overlaps the next range's kernel
+  const int g = a.g_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in_range = g < (a.g_hi > 0 ? a.g_hi : N);
   const bool is_static = g < a.st.Ns;
   const ProjCfg cfg = make_cfg(a.cams);
   const int K = a.cams.K;
@@ -473,14 +475,18 @@ extern "C" int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream) {
   if (none) {   // pose-only: eval.py's test-time pose optimisation (all Gaussians frozen)
     MOBGS_REQUIRE(a->v_viewmats, "pose-only backward needs v_viewmats");
   } else {
-    if (a->st.Ns > 0)
+    const int lo = a->g_lo, hi = a->g_hi > 0 ? a->g_hi : N;        // only the tensors the range touches are needed
+    if (a->st.Ns > 0 && lo < a->st.Ns)
       MOBGS_REQUIRE(a->v_xyz && a->v_rotation_s && a->v_scaling_s && a->v_opacity_s && a->v_features_dc_s,
                     "static gradient outputs NULL");
-    if (a->dy.Nd > 0)
+    if (a->dy.Nd > 0 && hi > a->st.Ns)
       MOBGS_REQUIRE(a->v_control_xyz && a->v_rotation_d && a->v_omega && a->v_scaling_d && a->v_opacity_d &&
                         a->v_features_dc_d && a->v_features_t, "dynamic gradient outputs NULL");
   }
-  const int grid = (N + kProjThreads - 1) / kProjThreads;
+  MOBGS_REQUIRE(a->g_lo >= 0 && a->g_hi >= 0 && a->g_hi <= N && (a->g_hi == 0 || a->g_lo < a->g_hi),
+                "bad Gaussian range [%d, %d)", a->g_lo, a->g_hi);
+  const int count = (a->g_hi > 0 ? a->g_hi : N) - a->g_lo;
+  const int grid = (count + kProjThreads - 1) / kProjThreads;
   synth_project_bwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("synth_project_bwd");
 }

@@ -96,7 +96,13 @@ class FlatGradients:
         shared = self.shared_storages() if self.inplace_shared else []
         covered = {i for _, idx in shared for i in idx}
         self.last_collective_elems = 0
+        from . import fused
+        sink = fused.GRAD_SINK
         for alias, _ in shared:                      # in place: these gradients need no copy at all
+            if sink is not None and sink.reduced_storage == alias.untyped_storage().data_ptr():
+                sink.reduced_storage = None          # already summed over the ranks inside the backward (GradSink)
+                self.last_collective_elems += sink.last_collective_elems
+                continue
             if multi:
                 dist.all_reduce(alias, group=group)
                 if average:
@@ -131,6 +137,27 @@ class FlatGradients:
                     p.grad.copy_(g)
             off += n
         return self.flat
+
+
+def overlap_gradient_allreduce(enable: bool = True, n_chunks: int = 4, group=None):
+    """Install (or remove) the overlapped Gaussian-gradient all-reduce: the projection backward then runs in
+    `n_chunks` Gaussian ranges and all-reduces each range's gradient block on a side stream while the next range's
+    kernel runs (mobgs_b200.fused.GradSink).  The gradients autograd delivers are then ALREADY summed over the
+    ranks; `FlatGradients.reduce()` recognises that buffer and only reduces what is left (decoder weights, poses).
+    No-op semantics on a single rank (the collective is skipped, the chunked launches still run)."""
+    from . import fused
+    if not enable:
+        fused.GRAD_SINK = None
+        return None
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def reduce(t):
+        if not multi:
+            return None
+        return dist.all_reduce(t, group=group, async_op=True)
+
+    fused.GRAD_SINK = fused.GradSink(reduce, torch.cuda.Stream(), n_chunks)
+    return fused.GRAD_SINK
 
 
 def trainable(params: Iterable[torch.Tensor]) -> List[torch.Tensor]:

@@ -18,6 +18,23 @@ import torch
 from . import _lib as L
 from .ops import _cams, _f32c, _p, _stream, build_tile_lists, EPS2D, NEAR, FAR, RADIUS_CLIP
 
+class GradSink:
+    """Data-parallel gradient sink for `_SynthProject.backward` ("the all-reduce launched as soon as
+    the last backward block retires").  While installed (`fused.GRAD_SINK = GradSink(...)`, done by
+    mobgs_b200.dist.overlap_gradient_allreduce) the projection backward runs as `n_chunks` launches over Gaussian
+    ranges; each range writes its parameter gradients into one contiguous block of a chunk-major buffer, and the
+    block's NCCL all-reduce is issued on `comm_stream` as soon as its launch is enqueued — it overlaps the next
+    range's kernel.  One mobgs_copy_segments launch then unpacks the reduced blocks into the per-parameter gradient
+    tensors.  `reduce(tensor)` is the collective (sum over ranks, in place, async handle or None)."""
+
+    def __init__(self, reduce, comm_stream, n_chunks=4):
+        self.reduce, self.comm_stream, self.n_chunks = reduce, comm_stream, int(n_chunks)
+        self.reduced_storage = None      # untyped-storage pointer of the last flat gradient buffer delivered reduced
+        self.last_collective_elems = 0
+
+
+GRAD_SINK = None
+
 STATIC_KEYS = ("xyz", "rotation", "scaling", "opacity", "features_dc")
 DYNAMIC_KEYS = ("control_xyz", "rotation", "omega", "scaling", "opacity", "features_dc", "features_t",
                 "trbf_center")
@@ -96,6 +113,11 @@ class _SynthProject(torch.autograd.Function):
         flat = torch.zeros(tot, device=dev)
         views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(starts, outs)]
         v_st, v_dy = views[:5], views[5:] + [None]
+        sink = GRAD_SINK
+        if sink is not None and off is None and sink.n_chunks > 1:
+            _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view)
+            sink.reduced_storage = flat.untyped_storage().data_ptr()
+            return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, None)
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
                        _p(t_poly), _p(radii), _p(g_rec),
                        _p(v_st[0]), _p(v_st[1]), _p(v_st[2]), _p(v_st[3]), _p(v_st[4]),
@@ -103,6 +125,66 @@ class _SynthProject(torch.autograd.Function):
                        _p(v_dy[6]), _p(v_off), _p(v_view))
         L.call("mobgs_synth_project_bwd", a, _stream())
         return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, v_off)
+
+
+def _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view):
+    """see GradSink.  outs = the 12 parameter tensors (5 static, 7 dynamic), views = their gradient tensors."""
+    dev = g_rec.device
+    Ns, Nd = st[0].shape[0], dy[0].shape[0]
+    nc = sink.n_chunks
+    n_s = max(1, min(nc, round(nc * 17 * Ns / max(1, 17 * Ns + 57 * Nd)))) if Ns > 0 else 0     # chunks ~ equal bytes
+    n_d = max(1, nc - n_s) if Nd > 0 else 0
+    ranges = [("s", Ns * i // n_s, Ns * (i + 1) // n_s) for i in range(n_s)] + \
+             [("d", Nd * i // n_d, Nd * (i + 1) // n_d) for i in range(n_d)]
+    ranges = [r for r in ranges if r[2] > r[1]]
+    row = [int(t[0].numel()) if t.shape[0] else int(torch.Size(t.shape[1:]).numel()) for t in outs]
+    # chunk-major buffer: per range, the rows of its 5 (static) or 7 (dynamic) tensors back to back (16-byte aligned)
+    plan, tot = [], 0
+    for kind, lo, hi in ranges:
+        idx = range(0, 5) if kind == "s" else range(5, 12)
+        blocks, start = [], tot
+        for t in idx:
+            blocks.append((t, tot))
+            tot += ((hi - lo) * row[t] + 3) // 4 * 4
+        plan.append((kind, lo, hi, blocks, start, tot))
+    cm = torch.zeros(tot, device=dev)
+    main = torch.cuda.current_stream()
+    works = []
+    stream = _stream()
+    base_ptr = cm.data_ptr()
+    for kind, lo, hi, blocks, start, end in plan:
+        ptr = [None] * 12
+        for t, o in blocks:
+            ptr[t] = base_ptr + 4 * (o - lo * row[t])          # "row g of the full tensor" addressing
+        g_lo, g_hi = (lo, hi) if kind == "s" else (Ns + lo, Ns + hi)
+        a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, None), _p(t_spline), _p(t_poly),
+                       _p(radii), _p(g_rec), *ptr[:5], *ptr[5:12], None, _p(v_view), g_lo, g_hi)
+        L.call("mobgs_synth_project_bwd", a, stream)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(sink.comm_stream):
+            sink.comm_stream.wait_event(ev)
+            works.append(sink.reduce(cm[start:end]))
+    sink.last_collective_elems = tot
+    for w in works:
+        if w is not None:
+            w.wait()                                  # the main stream waits for the collective (no host block)
+    main.wait_stream(sink.comm_stream)
+    cm.record_stream(sink.comm_stream)
+    # unpack: block (tensor t, rows lo..hi) -> views[t][lo:hi]
+    chunk = L.load().mobgs_compact_chunk_words()
+    seg = [(base_ptr + 4 * o, views[t].data_ptr() + 4 * lo * row[t], (hi - lo) * row[t])
+           for kind, lo, hi, blocks, _s, _e in plan for t, o in blocks]
+    for s0 in range(0, len(seg), L.COPY_MAX_SEGMENTS):
+        part = seg[s0:s0 + L.COPY_MAX_SEGMENTS]
+        c = L.CopySegments()
+        c.n_segments = len(part)
+        chunks = 0
+        for i, (src, dst, nw) in enumerate(part):
+            c.src[i], c.dst[i], c.n_words[i], c.chunk_begin[i] = src, dst, nw, chunks
+            chunks += (nw + chunk - 1) // chunk
+        c.chunk_begin[len(part)] = chunks
+        L.call("mobgs_copy_segments", c, stream)
 
 
 def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_spline, t_poly,
