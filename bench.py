@@ -767,7 +767,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra keys of the N=1 line (gpu_on_reference_config, full_step)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking gradient all-reduce after the backward")
-    ap.add_argument("--overlap-chunks", type=int, default=4)
+    ap.add_argument("--overlap-chunks", type=int, default=2)
     ap.add_argument("--shard", default="views", choices=["views", "subframes"],
                     help="N>1: 'views' = one view per rank (weak scaling, default); 'subframes' = the K "
                          "sub-frames of one view split across ranks (strong scaling, BASELINE configs[3])")

@@ -139,7 +139,7 @@ class FlatGradients:
         return self.flat
 
 
-def overlap_gradient_allreduce(enable: bool = True, n_chunks: int = 4, group=None):
+def overlap_gradient_allreduce(enable: bool = True, n_chunks: int = 2, group=None):
     """Install (or remove) the overlapped Gaussian-gradient all-reduce: the projection backward then runs in
     `n_chunks` Gaussian ranges and all-reduces each range's gradient block on a side stream while the next range's
     kernel runs (mobgs_b200.fused.GradSink).  The gradients autograd delivers are then ALREADY summed over the

@@ -74,8 +74,12 @@ def test_chunked_backward_with_gradient_sink_equals_plain_backward():
         finally:
             D.overlap_gradient_allreduce(False)
         assert fused.GRAD_SINK is None
-        for a, b in zip(plain, chunked):
+        for a, b, p in zip(plain, chunked, params):
             assert (a is None) == (b is None)
-            if a is not None:
-                assert torch.equal(a, b)
+            if a is None:
+                continue
+            if p.shape[0] in (1500, 900) and p.dim() >= 2:            # per-Gaussian tensors: written once, bit-exact
+                assert torch.equal(a, b), (tuple(p.shape), float((a - b).abs().max()))
+            else:                                                       # decoder weights: atomic partial sums
+                assert (a - b).abs().max() <= 1e-5 * a.abs().max()
         assert (v_plain - v_chunked).abs().max() <= 1e-5 * v_plain.abs().max()
