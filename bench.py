@@ -311,6 +311,7 @@ class GpuJob:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.pending = {}
         self.stats = {}
+        self.symmetric = None        # mobgs_b200.dist.SymmetricGradients when the NVLS gradient buffer is in use
 
     @property
     def h2d_bytes(self):
@@ -334,6 +335,8 @@ class GpuJob:
         stats, my_k = self.stats, self.my_k
         for p in self.all_params:
             p.grad = None
+        if self.symmetric is not None:
+            self.symmetric.begin_step()
         if resident:
             view, tpoly, tgt, rays = self.view_d, self.tpoly_d, self.tgt_d, self.rays_d
         else:   # e2e: host buffers in, loss out
@@ -437,11 +440,23 @@ def run_ours(args):
     _lib.load()
 
     shard_sub = args.shard == "subframes" and world > 1
-    overlap = world > 1 and not shard_sub and not args.no_overlap
+    overlap = world > 1 and not shard_sub and args.overlap
+    symmetric = None
+    if world > 1 and not shard_sub and not args.no_symmetric:
+        # flat gradient buffer in NVLS symmetric memory, reduced by the multimem (in-switch) all-reduce
+        from mobgs_b200.dist import SymmetricGradients
+        symmetric = SymmetricGradients()
+        try:
+            if not symmetric.install():
+                symmetric = None
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] symmetric-memory gradients unavailable ({e}); using NCCL", file=sys.stderr)
+            symmetric = None
     if overlap:     # chunked projection backward, each chunk's gradient all-reduce on a side stream (mobgs_b200.fused.GradSink)
         from mobgs_b200.dist import overlap_gradient_allreduce
         overlap_gradient_allreduce(True, n_chunks=args.overlap_chunks)
     job = GpuJob(args.workload, dev, rank, world, shard_sub)
+    job.symmetric = symmetric
     W, H, K, N = job.W, job.H, job.K, job.N
     flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)   # > 126 MB L2
 
@@ -522,6 +537,8 @@ def run_ours(args):
     if overlap:
         from mobgs_b200.dist import overlap_gradient_allreduce
         overlap_gradient_allreduce(False)
+    if symmetric is not None:
+        symmetric.uninstall()
     if not args.no_extras:
         try:    # BASELINE configs[3]: batch 2 x K = 9 sub-frames of the 1 M / 1080p scene, the 18 (view, sub-frame) items split over the ranks
             extra["strong_scaling"] = measure_strong_scaling(args, dev, rank, world, flush, local)
@@ -553,7 +570,9 @@ def run_ours(args):
             line["allreduce_bytes_per_step"] = job.stats.get("allreduce_bytes")
             line["gradient_allreduce"] = (f"overlapped: projection backward in {args.overlap_chunks} Gaussian ranges, NCCL "
                                           "all-reduce of each range on a side stream" if overlap else
-                                          "one all-reduce after the backward")
+                                          ("one in-place multimem (NVLS symmetric-memory) all-reduce of the flat gradient "
+                                           "buffer after the backward" if symmetric is not None else
+                                           "one in-place NCCL all-reduce of the flat gradient buffer after the backward"))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -766,7 +785,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra keys of the N=1 line (gpu_on_reference_config, full_step)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking gradient all-reduce after the backward")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N>1: chunked projection backward with the gradient all-reduce on a side stream (measured slower "
+                         "than one all-reduce at N = 8: NCCL's kernels compete with the backward for SMs; off by default)")
+    ap.add_argument("--no-symmetric", action="store_true", help="N>1: NCCL all-reduce instead of the NVLS multimem one")
     ap.add_argument("--overlap-chunks", type=int, default=2)
     ap.add_argument("--shard", default="views", choices=["views", "subframes"],
                     help="N>1: 'views' = one view per rank (weak scaling, default); 'subframes' = the K "

@@ -37,6 +37,11 @@ class GradSink:
 
 GRAD_SINK = None
 
+# Optional allocator of the flat parameter-gradient buffer: fn(n_floats, device) -> zeroed fp32 tensor.  A data-parallel
+# caller installs one that hands out a persistent NVLS symmetric-memory buffer (mobgs_b200.dist.SymmetricGradients), so
+# that the gradient all-reduce is a multimem (in-switch) reduction on the very buffer the backward kernel wrote.
+FLAT_ALLOCATOR = None
+
 STATIC_KEYS = ("xyz", "rotation", "scaling", "opacity", "features_dc")
 DYNAMIC_KEYS = ("control_xyz", "rotation", "omega", "scaling", "opacity", "features_dc", "features_t",
                 "trbf_center")
@@ -112,7 +117,7 @@ class _SynthProject(torch.autograd.Function):
         for t in outs:
             starts.append(tot)
             tot += (t.numel() + 3) // 4 * 4
-        flat = torch.zeros(tot, device=dev)
+        flat = FLAT_ALLOCATOR(tot, dev) if FLAT_ALLOCATOR is not None else torch.zeros(tot, device=dev)
         views = [flat[o:o + t.numel()].view(t.shape) for o, t in zip(starts, outs)]
         v_st, v_dy = views[:5], views[5:] + [None]
         sink = GRAD_SINK
