@@ -442,7 +442,9 @@ def run_ours(args):
     shard_sub = args.shard == "subframes" and world > 1
     overlap = world > 1 and not shard_sub and args.overlap
     symmetric = None
-    if world > 1 and not shard_sub and not args.no_symmetric:
+    # measured (profiles/r2_allreduce_n*.json): 116 MB multimem all-reduce 0.285 ms vs NCCL 0.36 ms on 8 GPUs, but 1.03 ms vs
+    # 0.245 ms on 2 — the in-switch reduction only pays with many peers, so it is used from 8 ranks up
+    if world >= 8 and not shard_sub and not args.no_symmetric:
         # flat gradient buffer in NVLS symmetric memory, reduced by the multimem (in-switch) all-reduce
         from mobgs_b200.dist import SymmetricGradients
         symmetric = SymmetricGradients()

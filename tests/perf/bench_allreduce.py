@@ -41,6 +41,9 @@ def main():
         hdl = symm_mem.rendezvous(t, gname)
         t.fill_(1.0)
         out["multicast"] = bool(getattr(hdl, "multicast_ptr", 0))
+        out["zero_symm_ms"] = timeit(lambda: t.zero_())
+        out["zero_plain_ms"] = timeit(lambda: x.zero_())
+        t.fill_(1.0)
         for opname in ("multimem_all_reduce_", "two_shot_all_reduce_", "one_shot_all_reduce"):
             op = getattr(torch.ops.symm_mem, opname, None)
             if op is None:
