@@ -1,9 +1,6 @@
 #!/bin/bash
-# N GPUs: weak scaling, symmetric (default) vs NCCL
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-N=${1:-2}
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 20 --warmup 5 --no-extras > gpurun_out/i_n$N.json 2> gpurun_out/i_n$N.err
+N=${1:-8}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/i_n$N.json 2> gpurun_out/i_n$N.err
 echo "rc=$?"; grep -v "OMP_NUM\|\*\*\*\*\|^$" gpurun_out/i_n$N.err | tail -4
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 bench.py --gpus $N --steps 20 --warmup 5 --no-extras --no-symmetric > gpurun_out/i_n${N}_nccl.json 2> gpurun_out/i_n${N}_nccl.err
-echo "rc=$?"
