@@ -143,3 +143,52 @@ def test_cuda_path_reproduces_the_reference_eval_pose_optimisation():
     1e-3 relative gradient difference moves the pose by << lr = 3e-4 per step."""
     z = np.load(HT.EVAL_GOLD)
     _check_eval(z, HT.run_eval_tto(z, "dropin"), rtol=5e-3, pose_tol=2e-5)
+
+
+@pytest.mark.skipif(not E.reference_available(), reason="/root/reference not present on this machine")
+def test_batched_warped_cameras_equal_the_reference_get_warped_cams():
+    """a10: mobgs_b200.blce.get_warped_cams_batched (one batched inverse + one ray launch) against the reference's
+    blceKernel.get_warped_cams (K Camera constructions) on the reference's real kernel / Camera objects: every
+    attribute train.py and the renderer read, and the gradients that reach the BLCE network's parameters."""
+    E.setup_paths()
+    with E.cuda_to_cpu():
+        from mobgs_b200.blce import get_warped_cams_batched
+        from oracle.mobgs_ref import camera_rays_ref
+        from scene.blce import blceKernel
+        torch.manual_seed(4)
+        _, _, scene, _ = E.synthetic_reference_scene(n_static=40, n_dynamic=30)
+        Kw = 5
+        kern = blceKernel(num_views=len(scene.train_cams), view_dim=32, num_warp=Kw, method="euler", adjoint=False, iteration=100)
+        with torch.no_grad():                 # the network's last layers start at zero: give the poses something to do
+            for p in kern.model.get_params():
+                p.add_(0.05 * torch.randn_like(p))
+        cam = scene.train_cams[2]
+        ref_cams, ref_expo = kern.get_warped_cams(cam, scene.train_cams[3], scene.train_cams[1])
+        got, expo = get_warped_cams_batched(kern, cam, scene.train_cams[3], scene.train_cams[1], rays_fn=camera_rays_ref)
+        assert len(got) == Kw and torch.equal(expo, ref_expo)
+        assert tuple(got.viewmats.shape) == (Kw, 4, 4) and tuple(got.rays.shape) == (Kw, 6, cam.image_height, cam.image_width)
+        for a, b in zip(got, ref_cams):
+            assert (a.world_view_transform - b.world_view_transform).abs().max() < 1e-6
+            assert (a.R - b.R).abs().max() < 1e-6 and (a.T - b.T).abs().max() < 1e-6
+            assert (a.camera_center - b.camera_center).abs().max() < 1e-5
+            assert (a.cam_ray - b.cam_ray).abs().max() < 2e-6
+            assert torch.equal(a.K, b.K) and a.time == b.time and a.max_time == b.max_time and a.uid == b.uid
+            assert a.image_width == b.image_width and a.image_height == b.image_height
+        assert (got.viewmats - torch.stack([c.world_view_transform.T for c in ref_cams])).abs().max() < 1e-6
+        # the pose gradient reaches the network identically
+        params = list(kern.model.get_params())
+        g = torch.Generator().manual_seed(0)
+        w_ray = torch.rand(got.rays.shape, generator=g)
+        w_mat = torch.rand(Kw, 4, 4, generator=g)
+        loss_a = (got.rays * w_ray).sum() + (got.viewmats * w_mat).sum()
+        loss_b = (torch.cat([c.cam_ray for c in ref_cams]) * w_ray).sum() + \
+                 (torch.stack([c.world_view_transform.T for c in ref_cams]) * w_mat).sum()
+        ga = torch.autograd.grad(loss_a, params, allow_unused=True)
+        gb = torch.autograd.grad(loss_b, params, allow_unused=True)
+        n = 0
+        for x, y in zip(ga, gb):
+            assert (x is None) == (y is None)
+            if x is not None:
+                assert (x - y).abs().max() <= 1e-4 * max(1e-6, float(y.abs().max()))
+                n += 1
+        assert n > 0
