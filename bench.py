@@ -268,11 +268,19 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
+RAY_IMAGES = False      # --ray-images: materialise Camera.cam_ray [K,6,H,W] (round-1 path) instead of in-kernel rays
+
+
 def build_rays(viewmats, intr, W, H):
-    """Camera.cam_ray for the K sub-frame cameras on the device (scene/cameras.py:132-146): [K,6,H,W],
-    one mobgs_camera_rays_fwd launch instead of K meshgrid + matmul chains."""
-    from mobgs_b200.cameras import camera_rays_from_w2c
-    return camera_rays_from_w2c(viewmats, intr.fx, intr.fy, intr.cx, intr.cy, W, H)
+    """Camera.cam_ray of the K sub-frame cameras (scene/cameras.py:132-146).  Default: a RayPose — 12 pose floats per
+    camera from one batched inverse; the blend kernels generate every pixel's ray in registers and reduce the pose
+    gradient themselves.  --ray-images: the [K,6,H,W] tensor from one
+    mobgs_camera_rays_fwd launch, read back by the decoder epilogue / prologue."""
+    from mobgs_b200.cameras import camera_rays_from_w2c, ray_pose_from_w2c
+    # the synthetic poses are rigid transforms: closed-form inverse (torch.inverse synchronises the stream for its info check)
+    if RAY_IMAGES:
+        return camera_rays_from_w2c(viewmats, intr.fx, intr.fy, intr.cx, intr.cy, W, H, rigid=True)
+    return ray_pose_from_w2c(viewmats, intr.fx, intr.fy, intr.cx, intr.cy, rigid=True)
 
 
 class GpuJob:
@@ -311,6 +319,8 @@ class GpuJob:
         self.copy_stream = torch.cuda.Stream(device=dev)
         self.pending = {}
         self.stats = {}
+        self.loss_ring = torch.zeros(256, dtype=torch.float32).pin_memory()
+        self.loss_i = 0
         self.symmetric = None        # mobgs_b200.dist.SymmetricGradients when the NVLS gradient buffer is in use
 
     @property
@@ -380,13 +390,27 @@ class GpuJob:
         view.grad = None
         stats["out"] = out
         if not resident:
-            return float(loss.detach())          # D2H read of the step's result
+            # D2H read of the step's result: an asynchronous copy into a pinned ring inside the step (complete when the
+            # step's closing event is), consumed by the host afterwards (`losses()`), so the host keeps enqueueing
+            slot = self.loss_ring[self.loss_i % self.loss_ring.shape[0]]
+            slot.copy_(loss.detach(), non_blocking=True)
+            self.loss_i += 1
+            return slot
         return loss
 
+    def losses(self):
+        """host view of the e2e steps' results (after a synchronize)"""
+        n = min(self.loss_i, self.loss_ring.shape[0])
+        return [float(v) for v in self.loss_ring[:n]]
 
-def timed(step_fn, flush, steps, warmup, dev_index, world, sample_clocks=False, reset_lib_timing=False):
+
+def timed(step_fn, flush, steps, warmup, dev_index, world, sample_clocks=False, reset_lib_timing=False, host_sync=False):
     """W untimed warm-up calls, then `steps` calls timed one by one with CUDA events (L2 flushed, untimed,
-    between them), barrier + synchronize on both sides, max over ranks.  -> (ms per step, clocks)"""
+    between them), barrier + synchronize on both sides, max over ranks.  -> (ms per step, clocks)
+    Default: the host only ENQUEUES (as a training loop does): every step is bracketed by its own event pair and the
+    host synchronises once after the K steps, so the Python prologue of step i+1 overlaps the GPU work of step i.
+    host_sync=True: the host waits for every step before starting the next (round 1's loop; exposes ~0.1-0.3 ms of
+    host prologue per step as GPU idle time)."""
     import torch
     import torch.distributed as dist
     from mobgs_b200 import _lib
@@ -404,16 +428,18 @@ def timed(step_fn, flush, steps, warmup, dev_index, world, sample_clocks=False, 
     if reset_lib_timing:
         _lib.TIMING = {}
         _lib.LAUNCH_COUNT = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tot = 0.0
+    pairs = []
     for _ in range(steps):
         flush.zero_()                      # evict L2 between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step_fn()
         e1.record()
-        e1.synchronize()
-        tot += e0.elapsed_time(e1)
+        if host_sync:
+            e1.synchronize()
+        pairs.append((e0, e1))
     torch.cuda.synchronize()
+    tot = sum(a.elapsed_time(b) for a, b in pairs)
     clocks = sampler.stop() if sampler else None
     if world > 1:
         dist.barrier()
@@ -510,6 +536,11 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers ----
     e2e_ms, _ = timed(lambda: job.step(False), flush, args.steps, max(1, args.warmup // 2), local, world)
+    e2e_losses = job.losses()
+    # the same two loops with the host waiting for every step (round 1's measurement loop), for comparison
+    hs_steps = max(3, min(args.steps, 10))
+    hs_ms, _ = timed(lambda: job.step(True), flush, hs_steps, 1, local, world, host_sync=True)
+    hs_e2e_ms, _ = timed(lambda: float(job.step(False)), flush, hs_steps, 1, local, world, host_sync=True)
 
     extra = {}
     if world == 1 and not args.no_extras:
@@ -564,7 +595,14 @@ def run_ours(args):
             "config": make_config(args.workload, world, shard_sub),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": Pjob / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": 4,
+                    "last_loss_on_host": e2e_losses[-1] if e2e_losses else None,
+                    "pipeline": "inputs: pinned host -> device on a side stream one step ahead; result: async D2H of the "
+                                "loss into a pinned ring inside the step; the host enqueues ahead and synchronises after "
+                                "the K timed steps"},
+            "host_sync_per_step": {"ms_per_step": hs_ms, "e2e_ms_per_step": hs_e2e_ms, "steps": hs_steps,
+                                   "note": "same steps with the host waiting for each one (float(loss) / event "
+                                           "synchronize) before enqueueing the next"},
             "gpu_launches": launches, "kernel_ms_per_step": kernel_ms, "clocks": clocks,
         }
         line.update(extra)
@@ -670,7 +708,7 @@ def measure_full_step(args, job, flush, local, views=2):
     :629, loss.backward() at :680, optimizer steps at :796-800).  Inputs resident; CUDA events."""
     import torch
     from mobgs_b200 import _lib
-    from mobgs_b200.cameras import camera_rays_from_w2c
+    from mobgs_b200.cameras import camera_rays_from_w2c, ray_pose_from_w2c
     from mobgs_b200.gaussian_renderer import get_flow_batched
     from mobgs_b200.losses import flow_warp_loss, photo_loss, reg_loss
     from mobgs_b200.optim import FusedAdam, fused_step
@@ -704,15 +742,20 @@ def measure_full_step(args, job, flush, local, views=2):
     parts = {}
 
     def cams_of(v, w2c):
-        """K camera stand-ins of view v + their stacked rays (one camera_rays launch, pose-differentiable)"""
-        rays = camera_rays_from_w2c(w2c, intr.fx, intr.fy, intr.cx, intr.cy, W, H)
-        per_cam = rays.split(1)
-        cams = [SimpleNamespace(world_view_transform=w2c[k].transpose(0, 1), K=job.Kmat, time=times[v], max_time=23,
+        """K camera stand-ins of view v + their rays: a pose-differentiable RayPose (12 floats per camera, rays generated
+        inside the blend kernels) or, with --ray-images, the stacked [K,6,H,W] tensor of one camera_rays launch"""
+        # the centre sub-frame is the dataset camera itself: numpy pose, not learnable (train.py:441, scene/cameras.py:121-124)
+        centre = torch.arange(K, device=dev)[:, None, None] == half
+        w2c_r = torch.where(centre, w2c.detach(), w2c)
+        if RAY_IMAGES:
+            rays = camera_rays_from_w2c(w2c_r, intr.fx, intr.fy, intr.cx, intr.cy, W, H, rigid=True)
+            per_cam = rays.split(1)
+        else:
+            rays = ray_pose_from_w2c(w2c_r, intr.fx, intr.fy, intr.cx, intr.cy, rigid=True)
+            per_cam = [rays[k] for k in range(K)]
+        cams = [SimpleNamespace(world_view_transform=w2c_r[k].transpose(0, 1), K=job.Kmat, time=times[v], max_time=23,
                                 image_width=W, image_height=H, cam_ray=per_cam[k], get_pixels=pixel_grid)
                 for k in range(K)]
-        # the centre sub-frame is the dataset camera itself: numpy pose, not learnable (train.py:441, scene/cameras.py:121-124)
-        cams[half].world_view_transform = w2c[half].detach().transpose(0, 1)
-        cams[half].cam_ray = per_cam[half].detach()
         return cams, rays
 
     def step():
@@ -725,7 +768,7 @@ def measure_full_step(args, job, flush, local, views=2):
             pkg = render_blurry_view(cams[half], cams, exposure_time, stat, dyn, None, job.bg, rays=rays)
             preds.append(pkg["render"]); depths.append(pkg["depth"]); d_alphas.append(pkg["d_alpha"])
             oris.append(pkg["render_center"]); vsps.append(pkg["viewspace_points"])
-            a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas)
+            a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas, rays=cams[half].cam_ray)
             e2m.append(a); m2e.append(b); lat_img.append(li); lat_alpha.append(la)
         image = torch.stack(preds)
         photo = photo_loss(image, gt, lam_dssim)
@@ -754,7 +797,7 @@ def measure_full_step(args, job, flush, local, views=2):
             p.grad = None
         for v in range(views):
             cams, _ = cams_of(v, view_d[v])
-            a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas)
+            a, b, li, la = get_flow_batched(cams[half], stat, dyn, None, job.bg, deltas, rays=cams[half].cam_ray)
             (a.mean() + b.mean() + li.mean() + la.mean()).backward()
     parts["render_blurry_view_fwd_bwd_ms"], _ = timed(only_blurry, flush, 5, 2, local, 1)
     parts["get_flow_batched_fwd_bwd_ms"], _ = timed(only_flow, flush, 5, 2, local, 1)
@@ -785,6 +828,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ray-images", action="store_true",
+                    help="materialise Camera.cam_ray [K,6,H,W] (mobgs_camera_rays_fwd/bwd) instead of generating rays inside "
+                         "the blend kernels from 12 pose floats per camera (the default)")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra keys of the N=1 line (gpu_on_reference_config, full_step)")
     ap.add_argument("--overlap", action="store_true",
@@ -799,6 +845,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
     else:
+        global RAY_IMAGES
+        RAY_IMAGES = bool(args.ray_images)
         run_ours(args)
 
 

@@ -219,6 +219,16 @@ typedef struct {
   MobgsLists lists;          /* K lists over the record sets (see MobgsLists) */
   int32_t* tile_counts;      /* [K*T] workspace, overwritten */
   int32_t* tile_offsets;     /* [K*T+1] out */
+  /* Optional (entries != NULL): the counting pass also records every intersection it finds as a 16-byte entry
+   * (segment, slot inside the segment, Gaussian index, depth bits), so that step 2 is a streaming scatter of these
+   * entries (MobgsTileSort.entries) instead of a second pass over all K*N records.  entries [entry_capacity,4] u32,
+   * entry_cursor [1] (zeroed inside; ends as the number of intersections I), depths [K,N].  Intersections beyond
+   * entry_capacity are counted but not recorded: when tile_offsets[K*T] > entry_capacity the caller must run step 2
+   * WITHOUT entries (the two-pass path). */
+  const float* depths;
+  void* entries;
+  int64_t entry_capacity;
+  int32_t* entry_cursor;
 } MobgsTileCount;
 int mobgs_tile_count(const MobgsTileCount* a, void* stream);
 
@@ -235,6 +245,11 @@ typedef struct {
   uint64_t* keys;            /* [capacity] workspace */
   uint64_t* keys_tmp;        /* [capacity] workspace */
   int32_t* sorted_ids;       /* [capacity] out: Gaussian index per list entry */
+  /* Optional (entries != NULL): emit from the entries recorded by mobgs_tile_count (see there) — records, radii,
+   * depths and tile_cursor are then not read.  n_entries = MobgsTileCount.entry_cursor (device). */
+  const void* entries;
+  int64_t entry_capacity;
+  const int32_t* n_entries;
 } MobgsTileSort;
 int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream);
 
@@ -271,6 +286,13 @@ typedef struct {
    * the latent image render :473) and no background.  out_flow [K,H,W,2]. */
   int32_t flow_ref;
   float* out_flow;
+  /* Optional camera rays generated in registers (dec_pose != NULL; dec_rays may then be NULL): instead of reading
+   * Camera.cam_ray [.,6,H,W] (348 MB per blurry view at 1080p, K = 7) the epilogue evaluates the ray of its pixel from
+   * 12 pose floats per camera — dec_pose [n_cam,12] = camera-to-world rotation R (row-major 9) | camera centre c (3) —
+   * exactly as mobgs_camera_rays_fwd does (scene/cameras.py:132-146): l = normalise(((x+.5-ppx)/sfx, (y+.5-ppy)/sfy, 1)),
+   * ray = [c | normalise(R l)].  The camera of list k is chosen by dec_rays_per_k as for dec_rays. */
+  const float* dec_pose;
+  float dec_ppx, dec_ppy, dec_sfx, dec_sfy;
 } MobgsBlendFwd;
 int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
 
@@ -308,9 +330,16 @@ typedef struct {
    * v_records[flow_ref][g].xy and subtracted from v_records[rec_k][g].xy. */
   int32_t flow_ref;
   const float* g_flow;
+  /* Rays generated in registers (see MobgsBlendFwd.dec_pose).  v_pose_partial [n_cam, MOBGS_POSE_SLOTS, 12] (zeroed by
+   * the caller, summed over the slot axis afterwards; NULL = pose gradient not needed) receives the gradient of the
+   * 12 pose floats — what mobgs_camera_rays_bwd would have reduced from a [.,6,H,W] ray-gradient image. */
+  const float* dec_pose;
+  float dec_ppx, dec_ppy, dec_sfx, dec_sfy;
+  float* v_pose_partial;
 } MobgsBlendBwd;
 
 #define MOBGS_DEC_SLOTS 1024
+#define MOBGS_POSE_SLOTS 64
 
 /* mean[i] = (1/K) sum_k rgb[k][i] + 1e-10 for i < n  (train.py:540-541). */
 int mobgs_subframe_mean(const float* rgb, float* mean, int32_t K, int64_t n, void* stream);

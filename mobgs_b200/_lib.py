@@ -136,7 +136,9 @@ class TileCount(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("tight", C.c_int32),
                 ("lists", Lists),
-                ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p)]
+                ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p),
+                ("depths", C.c_void_p), ("entries", C.c_void_p), ("entry_capacity", C.c_int64),
+                ("entry_cursor", C.c_void_p)]
 
 
 class TileSort(C.Structure):
@@ -145,7 +147,8 @@ class TileSort(C.Structure):
                 ("tight", C.c_int32), ("lists", Lists),
                 ("tile_offsets", C.c_void_p), ("tile_cursor", C.c_void_p),
                 ("capacity", C.c_int64), ("keys", C.c_void_p), ("keys_tmp", C.c_void_p),
-                ("sorted_ids", C.c_void_p)]
+                ("sorted_ids", C.c_void_p),
+                ("entries", C.c_void_p), ("entry_capacity", C.c_int64), ("n_entries", C.c_void_p)]
 
 
 class BlendFwd(C.Structure):
@@ -156,7 +159,9 @@ class BlendFwd(C.Structure):
                 ("out_alphas", C.c_void_p), ("last_idx", C.c_void_p),
                 ("dec_rays", C.c_void_p), ("dec_rays_per_k", C.c_int32), ("dec_w1", C.c_void_p),
                 ("dec_w2", C.c_void_p), ("out_rgb", C.c_void_p), ("out_depth", C.c_void_p),
-                ("flow_ref", C.c_int32), ("out_flow", C.c_void_p)]
+                ("flow_ref", C.c_int32), ("out_flow", C.c_void_p),
+                ("dec_pose", C.c_void_p), ("dec_ppx", C.c_float), ("dec_ppy", C.c_float), ("dec_sfx", C.c_float),
+                ("dec_sfy", C.c_float)]
 
 
 class BlendBwd(C.Structure):
@@ -170,7 +175,9 @@ class BlendBwd(C.Structure):
                 ("dec_w2", C.c_void_p), ("out_colors", C.c_void_p), ("g_rgb", C.c_void_p),
                 ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p), ("g_mean", C.c_void_p),
                 ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p),
-                ("flow_ref", C.c_int32), ("g_flow", C.c_void_p)]
+                ("flow_ref", C.c_int32), ("g_flow", C.c_void_p),
+                ("dec_pose", C.c_void_p), ("dec_ppx", C.c_float), ("dec_ppy", C.c_float), ("dec_sfx", C.c_float),
+                ("dec_sfy", C.c_float), ("v_pose_partial", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):
@@ -395,6 +402,7 @@ TIMING = None
 
 
 DEC_SLOTS = 1024
+POSE_SLOTS = 64
 
 
 def knn3_mean_dist2(points_ptr, out_ptr, n, stream) -> None:

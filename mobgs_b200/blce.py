@@ -12,8 +12,9 @@ centres, and ONE `mobgs_camera_rays_fwd` launch for all K ray images (differenti
 centre, so the pose gradient still reaches the BLCE network).  The result is a list of light camera objects with
 the attributes train.py and the renderer read from a warped camera (`R`, `T`, `world_view_transform`,
 `camera_center`, `cam_ray`, `K`, `time`, `max_time`, `image_width`, `image_height`, `uid`, `metadata`,
-`get_pixels`) plus the stacked tensors (`.viewmats [K,4,4]`, `.rays [K,6,H,W]`) that
-`mobgs_b200.subframes.render_blurry_view(..., rays=cams.rays)` consumes without re-concatenating.
+`get_pixels`) plus the stacked tensors (`.viewmats [K,4,4]`, `.ray_pose` = 12 pose floats per camera, `.rays [K,6,H,W]` built only on
+demand) that `mobgs_b200.subframes.render_blurry_view(..., rays=cams.ray_pose)` consumes: the blend kernels generate
+every pixel's ray in registers, so on the fused path no ray image is ever written or read.
 """
 from __future__ import annotations
 
@@ -28,21 +29,35 @@ class WarpedCamera:
     """Attribute view of one warped sub-frame camera (what scene/cameras.py:Camera exposes to train.py:497-530 and
     to gaussian_renderer.render)."""
 
-    def __init__(self, base, R, T, wvt, centre, cam_ray):
+    def __init__(self, base, R, T, wvt, centre, batch, k):
         self._base = base
         self.R, self.T = R, T                          # camera-to-world rotation, world-to-camera translation (torch)
         self.world_view_transform = wvt                # [4,4], transposed world-to-camera (cameras.py:126)
         self.camera_center = centre
-        self.cam_ray = cam_ray                         # [1,6,H,W]
+        self._batch, self._k = batch, k
+
+    @property
+    def cam_ray(self):                                 # [1,6,H,W]; materialised (for all K cameras, one launch) on first use
+        return self._batch.rays[self._k:self._k + 1]
 
     def __getattr__(self, name):                       # everything else (K, time, max_time, image sizes, uid, metadata,
         return getattr(self._base, name)               # image, depth, mask, get_pixels, ...) is the dataset camera's
 
 
 class WarpedCameras(list):
-    """list of WarpedCamera + the stacked tensors of the batch"""
-    viewmats: torch.Tensor      # [K,4,4] world-to-camera
-    rays: torch.Tensor          # [K,6,H,W]
+    """list of WarpedCamera + the stacked tensors of the batch: `viewmats` [K,4,4] world-to-camera, `ray_pose`
+    (mobgs_b200.cameras.RayPose: 12 pose floats per camera — what render_blurry_view(..., rays=cams.ray_pose) consumes;
+    no ray image is built) and `rays` [K,6,H,W], built lazily by one camera_rays launch only if somebody reads it or a
+    camera's `cam_ray` (the drop-in render() does)."""
+    viewmats: torch.Tensor
+    _rays = None
+    _rays_fn = None
+
+    @property
+    def rays(self):
+        if self._rays is None:
+            self._rays = self._rays_fn()
+        return self._rays
 
 
 def get_warped_cams_batched(kernel, cam, fwd_cam=None, bwd_cam=None, rays_fn: Optional[Callable] = None):
@@ -66,9 +81,11 @@ def get_warped_cams_batched(kernel, cam, fwd_cam=None, bwd_cam=None, rays_fn: Op
     centres = torch.inverse(wvt)[:, 3, :3]                               # cameras.py:130, batched
     m = cam.metadata
     W, H = int(m.image_size_x), int(m.image_size_y)
-    rays = rays_fn(R.contiguous(), centres.contiguous(), float(m.principal_point_x), float(m.principal_point_y),
-                   float(m.scale_factor_x), float(m.scale_factor_y), W, H)
-    per_cam = rays.split(1)
-    out = WarpedCameras(WarpedCamera(cam, R[k], T[k], wvt[k], centres[k], per_cam[k]) for k in range(Kc))
-    out.viewmats, out.rays = viewmats, rays
+    intr = (float(m.principal_point_x), float(m.principal_point_y), float(m.scale_factor_x), float(m.scale_factor_y))
+    out = WarpedCameras()
+    out.extend(WarpedCamera(cam, R[k], T[k], wvt[k], centres[k], out, k) for k in range(Kc))
+    out.viewmats = viewmats
+    out._rays_fn = lambda: rays_fn(R.contiguous(), centres.contiguous(), *intr, W, H)
+    from .cameras import ray_pose
+    out.ray_pose = ray_pose(R, centres, *intr)
     return out, exposure_time

@@ -104,36 +104,143 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const __grid_constant__
                 [&](int tile) { atomicAdd(counts + tile, 1); });
 }
 
-// exclusive prefix sum over n ints by a single CTA; out[n] = total.
+// Counting pass that also REMEMBERS what it found (a.entries != NULL): the atomicAdd on the tile counter returns the
+// entry's slot inside its segment, so (segment, slot, key) is everything the emit pass needs — it becomes a streaming
+// scatter over the entries (tile_scatter_kernel) instead of a second pass over all K*N records that repeats the
+// exact tile tests and hits the same L2 atomics again.  Entries land in one global array in arbitrary order; a warp
+// reserves its range with ONE atomicAdd on the cursor (prefix sum of the lanes' hit counts).  A Gaussian's hits are
+// kept as a bit mask over its tile rectangle between counting and writing (rectangles of more than 64 tiles repeat
+// the test instead).  Entries beyond entry_capacity are dropped; the counters stay exact, so the caller sees the
+// overflow in tile_offsets[K*T] and redoes the binning with the two-pass kernels (the lists of the overflowed attempt
+// hold unwritten keys: the blend kernels clamp every Gaussian index they read).
+struct BinEntry { int seg; int slot; uint32_t gid; uint32_t depth_bits; };   // 16 bytes, stored as one uint4
+
+__global__ void __launch_bounds__(256) tile_count_entries_kernel(const __grid_constant__ MobgsTileCount a, int tiles_x, int tiles_y) {
+  const size_t iv = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int tiles = tiles_x * tiles_y;
+  bool live = iv < (size_t)a.K * a.N;
+  int k = 0, gid = 0, radius = 0;
+  size_t i = 0;
+  if (live) {
+    k = (int)(iv / a.N);
+    gid = (int)(iv - (size_t)k * a.N);
+    live = gid >= a.lists.g_begin[k] && gid < a.lists.g_end[k];
+  }
+  if (live) {
+    i = (size_t)a.lists.rec_k[k] * a.N + gid;     // physical record
+    radius = a.radii[i];
+    live = radius > 0;
+  }
+  GaussGeom g = {0.f, 0.f, 0.f, 1.f, 0.f, 1.f};
+  TileRect r = {0, 0, 0, 0};
+  float tau = 0.f, nb_c = 0.f, nb_a = 0.f;
+  if (live) {
+    g = load_geom(a.records + i * kRecFloats);
+    r = tile_rect(g.mx, g.my, radius, tiles_x, tiles_y);
+    if (a.tight) {
+      nb_c = -g.cb * __fdividef(1.f, g.cc);
+      nb_a = -g.cb * __fdividef(1.f, g.ca);
+      tau = __logf(255.f * g.opac) + 0.01f;
+      if (!(tau >= 0.f)) live = false;
+    }
+  }
+  const int rw = live ? r.x1 - r.x0 : 0, rh = live ? r.y1 - r.y0 : 0;
+  auto hit = [&](int tx, int ty) {
+    if (!a.tight) return true;
+    const float xlo = tx * kTile + 0.5f, ylo = ty * kTile + 0.5f;
+    const float xhi = fminf((float)(tx * kTile + kTile), (float)a.width) - 0.5f;
+    const float yhi = fminf((float)(ty * kTile + kTile), (float)a.height) - 0.5f;
+    return !(min_sigma_rect(g.mx, g.my, g.ca, g.cb, g.cc, nb_c, nb_a, xlo, xhi, ylo, yhi) > tau);
+  };
+  const bool small = rw * rh <= 64;
+  unsigned long long mask = 0ull;
+  int n = 0;
+  for (int y = 0; y < rh; ++y)
+    for (int x = 0; x < rw; ++x)
+      if (hit(r.x0 + x, r.y0 + y)) {
+        if (small) mask |= 1ull << (y * rw + x);
+        ++n;
+      }
+  // one reservation per warp
+  int incl = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 31) base = atomicAdd(a.entry_cursor, total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (n == 0) return;
+  int64_t pos = (int64_t)base + incl - n;
+  int* counts = a.tile_counts + (size_t)k * tiles;
+  const uint32_t dbits = __float_as_uint(a.depths[i]);
+  uint4* entries = reinterpret_cast<uint4*>(a.entries);
+  for (int y = 0; y < rh; ++y)
+    for (int x = 0; x < rw; ++x) {
+      const bool h = small ? ((mask >> (y * rw + x)) & 1ull) != 0ull : hit(r.x0 + x, r.y0 + y);
+      if (!h) continue;
+      const int tile = (r.y0 + y) * tiles_x + (r.x0 + x);
+      const int slot = atomicAdd(counts + tile, 1);
+      if (pos < a.entry_capacity) entries[pos] = make_uint4((unsigned)(k * tiles + tile), (unsigned)slot, (unsigned)gid, dbits);
+      ++pos;
+    }
+}
+
+// emit pass over the entries of tile_count_entries_kernel: keys[tile_offsets[seg] + slot] = depth_bits << 32 | gid
+__global__ void __launch_bounds__(256) tile_scatter_kernel(const __grid_constant__ MobgsTileSort a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n = min((int64_t)*a.n_entries, a.entry_capacity);
+  if (i >= n) return;
+  const uint4 e = __ldcs(reinterpret_cast<const uint4*>(a.entries) + i);
+  const int64_t dst = (int64_t)a.tile_offsets[e.x] + (int)e.y;
+  if (dst < a.capacity) a.keys[dst] = ((uint64_t)e.w << 32) | e.z;
+}
+
+// exclusive prefix sum over n ints by a single CTA; out[n] = total.  Thread t owns the contiguous chunk
+// [t c, (t + 1) c), c = ceil(n / 1024) rounded up to a multiple of 4 (int4 accesses): one pass sums it, a block scan
+// gives its base, a second pass writes the prefixes — two barriers instead of four per 1024 elements.
 __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
   __shared__ int warp_tot[32];
-  __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < n ? in[i] : 0;
-    int s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-    if (lane == 31) warp_tot[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      int w = warp_tot[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
-      warp_tot[lane] = w;   // inclusive over warps
-    }
-    __syncthreads();
-    const int prev_warps = warp ? warp_tot[warp - 1] : 0;
-    const int c = carry;
-    if (i < n) out[i] = c + prev_warps + s - v;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = c + prev_warps + s;
-    __syncthreads();
+  const int c = (((n + 1023) / 1024) + 3) & ~3;
+  const int beg = min(n, (int)threadIdx.x * c), end = min(n, beg + c);
+  const bool vec = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  int sum = 0;
+  if (vec) {
+    int j = beg;
+    for (; j + 4 <= end; j += 4) { const int4 v = *reinterpret_cast<const int4*>(in + j); sum += v.x + v.y + v.z + v.w; }
+    for (; j < end; ++j) sum += in[j];
+  } else {
+    for (int j = beg; j < end; ++j) sum += in[j];
   }
-  if (threadIdx.x == 0) out[n] = carry;
+  int s = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+  if (lane == 31) warp_tot[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    warp_tot[lane] = w;   // inclusive over warps
+  }
+  __syncthreads();
+  int run = (warp ? warp_tot[warp - 1] : 0) + s - sum;   // exclusive prefix of this thread's chunk
+  if (vec) {
+    int j = beg;
+    for (; j + 4 <= end; j += 4) {
+      const int4 v = *reinterpret_cast<const int4*>(in + j);
+      int4 o;
+      o.x = run; o.y = o.x + v.x; o.z = o.y + v.y; o.w = o.z + v.z;
+      run = o.w + v.w;
+      *reinterpret_cast<int4*>(out + j) = o;
+    }
+    for (; j < end; ++j) { const int v = in[j]; out[j] = run; run += v; }
+  } else {
+    for (int j = beg; j < end; ++j) { const int v = in[j]; out[j] = run; run += v; }
+  }
+  if (threadIdx.x == 1023) out[n] = warp_tot[31];
 }
 
 __global__ void __launch_bounds__(256) tile_emit_kernel(const __grid_constant__ MobgsTileSort a, int tiles_x, int tiles_y) {
@@ -320,10 +427,19 @@ extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
   const int nt = a->K * tiles_x * tiles_y;
   cudaMemsetAsync(a->tile_counts, 0, sizeof(int) * (size_t)nt, s);
+  if (a->entries) {
+    MOBGS_REQUIRE(a->entry_cursor && a->entry_capacity >= 0, "entries need entry_cursor and a capacity");
+    cudaMemsetAsync(a->entry_cursor, 0, sizeof(int), s);
+  }
   if (a->N > 0) {
     MOBGS_REQUIRE(a->records && a->radii, "NULL records / radii");
     const size_t total = (size_t)a->K * a->N;
-    tile_count_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+    if (a->entries) {
+      MOBGS_REQUIRE(a->depths, "entries need depths");
+      tile_count_entries_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+    } else {
+      tile_count_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+    }
   }
   scan_kernel<<<1, 1024, 0, s>>>(a->tile_counts, a->tile_offsets, nt);
   return check_launch("tile_count");
@@ -332,15 +448,23 @@ extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
 extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
   MOBGS_REQUIRE(a->K >= 1 && a->K <= MOBGS_MAX_K && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
-  MOBGS_REQUIRE(a->tile_offsets && a->tile_cursor, "NULL workspace");
+  MOBGS_REQUIRE(a->tile_offsets && (a->tile_cursor || a->entries), "NULL workspace");
   if (a->N == 0 || a->capacity == 0) return MOBGS_OK;
-  MOBGS_REQUIRE(a->records && a->radii && a->depths && a->keys && a->keys_tmp && a->sorted_ids, "NULL pointer");
+  MOBGS_REQUIRE(a->keys && a->keys_tmp && a->sorted_ids, "NULL pointer");
   cudaStream_t s = (cudaStream_t)stream;
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
   const int nt = a->K * tiles_x * tiles_y;
-  cudaMemsetAsync(a->tile_cursor, 0, sizeof(int) * (size_t)nt, s);
-  const size_t total = (size_t)a->K * a->N;
-  tile_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+  if (a->entries) {
+    // the counting pass already recorded (segment, slot, key) of every intersection: streaming scatter
+    MOBGS_REQUIRE(a->n_entries && a->entry_capacity >= 0, "entries need n_entries and their capacity");
+    if (a->entry_capacity > 0)
+      tile_scatter_kernel<<<(unsigned)((a->entry_capacity + 255) / 256), 256, 0, s>>>(*a);
+  } else {
+    MOBGS_REQUIRE(a->records && a->radii && a->depths, "NULL pointer");
+    cudaMemsetAsync(a->tile_cursor, 0, sizeof(int) * (size_t)nt, s);
+    const size_t total = (size_t)a->K * a->N;
+    tile_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
+  }
   const size_t smem = 2 * sizeof(uint64_t) * kSortSmemCap + sizeof(int) * kSortWarps * 256;
   cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tile_rank_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);

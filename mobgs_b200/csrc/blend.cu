@@ -22,6 +22,7 @@
 #include "blend_units.cuh"
 #include "decode_math.cuh"
 #include "tma.cuh"
+#include "ray_math.cuh"
 
 namespace mobgs {
 
@@ -175,14 +176,17 @@ __device__ __forceinline__ void unit_pixel(int tid, int& lx, int& ly) {
   ly = (u / kUX) * kUH + (q / kUW);
 }
 
-template <int D, bool DEC, bool FLOW = false>
+// POSE: camera rays of the fused epilogue generated in registers from a.dec_pose (ray_math.cuh) instead of read
+// from a.dec_rays — a template parameter so that neither variant carries the other's code and registers.
+template <int D, bool DEC, bool FLOW = false, bool POSE = false>
 __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 : MOBGS_FWD_MIN_CTAS) blend_fwd_kernel(const __grid_constant__ MobgsBlendFwd a, int tiles_x, int tiles_y) {
   static_assert(!FLOW || (DEC && !MOBGS_FWD_PREDICATED), "fused flow channels ride the decode launch of the divergent body");
+  static_assert(!POSE || DEC, "in-kernel rays belong to the fused decode epilogue");
   __shared__ __align__(128) float4 srec[kBlendThreads][4];
   __shared__ __align__(8) float2 sflow[FLOW ? kBlendThreads : 1];   // per staged entry: records[flow_ref][g].xy - own xy
   __shared__ unsigned smask[kBlendThreads];
   __shared__ __align__(8) unsigned char swl[kUnits][kBlendThreads + 8];   // +8: 8-byte loads of a warp's units differ in bank
-  __shared__ __align__(16) float sdec[DEC ? 96 : 4];
+  __shared__ __align__(16) float sdec[DEC ? (POSE ? 112 : 96) : 4];   // decoder weights [0,90) | camera pose [96,108)
   __shared__ __align__(8) uint64_t sbar;
   const int tiles = tiles_x * tiles_y;
   const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
@@ -197,6 +201,10 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // made visible by the first barrier below
   }
   if (DEC && tid < 90) sdec[tid] = tid < 72 ? a.dec_w1[tid] : a.dec_w2[tid - 72];   // visible after the first barrier
+  if (POSE && tid >= 96 && tid < 108) {
+    const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+    sdec[tid] = a.dec_pose[12 * rk + (tid - 96)];
+  }
   int lx, ly;
   unit_pixel(tid, lx, ly);
   const int ix = tx * kTile + lx, iy = ty * kTile + ly;
@@ -359,10 +367,15 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
       float v[10], rays[6], x[12], hpre[6], out[3];
 #pragma unroll
       for (int c = 0; c < 10; ++c) v[c] = pix[c % D];
-      const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
-      const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
+      if (POSE) {                  // the ray of this pixel from 12 pose floats: no [.,6,H,W] image is read
+        const RayIntr in = {a.dec_ppx, a.dec_ppy, a.dec_sfx, a.dec_sfy};
+        pixel_ray(sdec + (POSE ? 96 : 0), in, ix, iy, rays);
+      } else {
+        const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+        const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+        for (int i = 0; i < 6; ++i) rays[i] = __ldg(rp + i * P);
+      }
       sandwich_fwd(w, v, rays, x, hpre, out);
 #pragma unroll
       for (int c = 0; c < 3; ++c) a.out_rgb[((size_t)k * 3 + c) * P + pp] = out[c];
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
 // are scratch that may alias buffers which are idle until the list walk starts.  Called by all
 // threads of the CTA (contains barriers).
 constexpr int kProPad = kBlendThreads + 4;
-template <int D, bool DEC>
+template <int D, bool DEC, bool POSE = false>
 __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k, int tid, bool inside, int ix, int iy,
                                                    float* sx, float* sg, float* sdec, float* swg,
                                                    float& T_final, int& last, float (&v_c)[D], float& v_a) {
@@ -389,6 +402,11 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
   for (int c = 0; c < D; ++c) v_c[c] = 0.f;
   if (DEC) {
     if (tid < 96) { sdec[tid] = tid < 72 ? a.dec_w1[tid] : (tid < 90 ? a.dec_w2[tid - 72] : 0.f); swg[tid] = 0.f; }
+    else if (POSE && tid < 112) {  // camera pose [96,108) and its gradient accumulator
+      const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+      sdec[tid] = tid < 108 ? a.dec_pose[12 * rk + (tid - 96)] : 0.f;
+      swg[tid] = 0.f;
+    }
     __syncthreads();
   }
   if (inside) {
@@ -413,20 +431,33 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
     const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix;
     const float* w1 = sdec;
     const float* w2 = sdec + (DEC ? 72 : 0);
+    const RayIntr rin = {a.dec_ppx, a.dec_ppy, a.dec_sfx, a.dec_sfy};
+    const bool want_pose = POSE && a.v_pose_partial;
+    float depth_acc = 0.f;
+    float gray[6];                 // d loss / d rays of this pixel (pose mode)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) gray[i] = 0.f;
     if (inside) {
       const size_t p = (size_t)k * P + pp;
       const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
       const float2* vp2 = reinterpret_cast<const float2*>(a.out_colors + p * 10);
-      float albedo[3], depth_acc, hpre[6];
+      float albedo[3], hpre[6];
       {
         float x[12];
         const float2 t0 = __ldg(vp2), t1 = __ldg(vp2 + 1), t2 = __ldg(vp2 + 2), t3 = __ldg(vp2 + 3), t4 = __ldg(vp2 + 4);
         albedo[0] = t0.x; albedo[1] = t0.y; albedo[2] = t1.x;
         x[0] = t1.y; x[1] = t2.x; x[2] = t2.y; x[3] = t3.x; x[4] = t3.y; x[5] = t4.x;
         depth_acc = t4.y;
-        const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
+        if (POSE) {
+          float r6[6];
+          pixel_ray(sdec + (POSE ? 96 : 0), rin, ix, iy, r6);
 #pragma unroll
-        for (int i = 0; i < 6; ++i) x[6 + i] = __ldg(rp + i * P);
+          for (int i = 0; i < 6; ++i) x[6 + i] = r6[i];
+        } else {
+          const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) x[6 + i] = __ldg(rp + i * P);
+        }
 #pragma unroll
         for (int i = 0; i < 12; ++i) sx[i * kPad + tid] = x[i];
 #pragma unroll
@@ -467,20 +498,36 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
         for (int j = 0; j < 6; ++j) gx += w1[12 * j + i] * ghpre[j];
         if (i < 6) {
           v_c[(3 + i) % D] = gx;
+        } else if (POSE) {
+          gray[i - 6] = gx;
         } else if (a.v_rays) {
           if (a.dec_rays_per_k == 1) a.v_rays[((size_t)k * 6 + (i - 6)) * P + pp] = gx;
           else atomicAdd(a.v_rays + ((size_t)rk * 6 + (i - 6)) * P + pp, gx);   // rays shared between lists
         }
       }
-      const float al = 1.f - T_final, den = fmaxf(al, kEdFloor);
-      const float gd = a.g_depth ? __ldg(a.g_depth + p) : 0.f;
-      v_c[9 % D] = gd / den;
-      v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * depth_acc / (den * den) : 0.f);
     } else {
 #pragma unroll
       for (int i = 0; i < 12; ++i) sx[i * kPad + tid] = 0.f;
 #pragma unroll
       for (int i = 0; i < 15; ++i) sg[i * kPad + tid] = 0.f;
+    }
+    if (POSE && want_pose) {
+      // pose gradient (what mobgs_camera_rays_bwd reduces from a [.,6,H,W] image): 12 sums over the tile's pixels,
+      // warp shuffles -> CTA accumulator swg[96..107] -> one atomicAdd per CTA and value (after the barrier below)
+      float v12[12];
+      pixel_ray_vjp(sdec + (POSE ? 96 : 0), rin, ix, iy, gray, v12);
+#pragma unroll
+      for (int i = 0; i < 12; ++i) {
+        const float sum = warp_sum(v12[i]);
+        if ((tid & 31) == 0 && sum != 0.f) atomicAdd(&swg[(POSE ? 96 : 0) + i], sum);
+      }
+    }
+    if (inside) {
+      const size_t p = (size_t)k * P + pp;
+      const float al = 1.f - T_final, den = fmaxf(al, kEdFloor);
+      const float gd = a.g_depth ? __ldg(a.g_depth + p) : 0.f;
+      v_c[9 % D] = gd / den;
+      v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * depth_acc / (den * den) : 0.f);
     }
     __syncthreads();
     if (tid < 180) {
@@ -500,6 +547,7 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
 
 template <int D, bool DEC>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
+  constexpr bool POSE = false;             // in-kernel rays exist in the transposing kernel only
   __shared__ __align__(128) float4 srec[kBlendThreads][4];
   __shared__ __align__(8) uint64_t sbar;
   __shared__ __align__(16) float sacc[kBlendThreads][kRecFloats];
@@ -557,6 +605,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
   __syncthreads();
   if (DEC && tid < 90 && swg[tid] != 0.f)
     atomicAdd(a.v_w_partial + (size_t)(blockIdx.x % MOBGS_DEC_SLOTS) * 90 + tid, swg[tid]);
+  if (POSE && a.v_pose_partial && tid >= 96 && tid < 108 && swg[tid] != 0.f) {
+    const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+    atomicAdd(a.v_pose_partial + ((size_t)rk * MOBGS_POSE_SLOTS + tile % MOBGS_POSE_SLOTS) * 12 + (tid - 96), swg[tid]);
+  }
   int tile_last = -1;
 #pragma unroll
   for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
@@ -756,7 +808,7 @@ constexpr int kAccRow = 17;                    // accumulator row stride: row t 
 constexpr int kAccFloats = MOBGS_BWD_DIRECT_RED ? 0 : kBwdBatch * kAccRow;
 constexpr int kTrScratch = kBwdBatch * kRecRow + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
 static_assert(kTrScratch >= 27 * kProPad, "prologue scratch must fit the aliased buffers");
-constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 96 + 96) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
+constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 112 + 112) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
@@ -764,7 +816,7 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 
 // FLOW: two more colour channels per entry, (records[flow_ref][g].xy - own xy), parked in floats 16..17 of the
 // staged row (rows are 20 floats, the TMA copy fills 16); their pixel gradients g_flow sit in slots 10..11 of sV.
-template <int D, bool DEC, bool FLOW = false>
+template <int D, bool DEC, bool FLOW = false, bool POSE = false>
 __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_tr_kernel(const __grid_constant__ MobgsBlendBwd a, int tiles_x, int tiles_y) {
   static_assert(kUL == 16, "transposing backward is written for 4x4-pixel units");
   static_assert(!FLOW || (D == 10 && MOBGS_BWD_DIRECT_RED), "fused flow channels need the D = 10 layout and direct reductions");
@@ -773,9 +825,9 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   float* sacc = srec + kBwdBatch * kRecRow;                      // [kBwdBatch][kAccRow]
   float* sF = sacc + kAccFloats;                                 // [8 warps][F | VS][kBlk][kFRow]
   float* sV = smem + kTrScratch;                                 // [8 warps][kVWarp]
-  float* sdec = sV + 8 * kVWarp;                                 // [96]
-  float* swg = sdec + 96;                                        // [96]
-  int* sid = reinterpret_cast<int*>(swg + 96);                   // [kBwdBatch]
+  float* sdec = sV + 8 * kVWarp;                                 // [112] decoder weights | camera pose
+  float* swg = sdec + 112;                                       // [112] their gradient accumulators
+  int* sid = reinterpret_cast<int*>(swg + 112);                  // [kBwdBatch]
   unsigned* smask = reinterpret_cast<unsigned*>(sid + kBwdBatch);   // [kBwdBatch]
   int* warp_max = reinterpret_cast<int*>(smask + kBwdBatch);     // [8]
   uint64_t* sbar = reinterpret_cast<uint64_t*>(warp_max + 8);    // 8-byte aligned: everything before is a multiple of 8 B
@@ -806,7 +858,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   float T_final, v_a, bg_dot = 0.f;
   float v_c[D];
   int last;
-  bwd_pixel_prologue<D, DEC>(a, k, tid, inside, ix, iy, smem, smem + 12 * kProPad, sdec, swg,
+  bwd_pixel_prologue<D, DEC, POSE>(a, k, tid, inside, ix, iy, smem, smem + 12 * kProPad, sdec, swg,
                              T_final, last, v_c, v_a);
   float v_fl0 = 0.f, v_fl1 = 0.f;
   if (FLOW && inside) {
@@ -849,6 +901,10 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   const int tile_zero = __syncthreads_and(px_zero);   // prologue scratch is free, sV / swg / warp_max are complete
   if (DEC && tid < 90 && swg[tid] != 0.f)
     atomicAdd(a.v_w_partial + (size_t)(blockIdx.x % MOBGS_DEC_SLOTS) * 90 + tid, swg[tid]);
+  if (POSE && a.v_pose_partial && tid >= 96 && tid < 108 && swg[tid] != 0.f) {
+    const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
+    atomicAdd(a.v_pose_partial + ((size_t)rk * MOBGS_POSE_SLOTS + tile % MOBGS_POSE_SLOTS) * 12 + (tid - 96), swg[tid]);
+  }
   if (tile_zero) return;
   int tile_last = -1;
 #pragma unroll
@@ -1077,18 +1133,18 @@ static void launch_fwd(const MobgsBlendFwd& a, int tiles_x, int tiles_y, cudaStr
 #ifndef MOBGS_BWD_TRANSPOSE
 #define MOBGS_BWD_TRANSPOSE 1
 #endif
-template <int D, bool DEC, bool FLOW = false>
+template <int D, bool DEC, bool FLOW = false, bool POSE = false>
 static void launch_bwd_kernel(const MobgsBlendBwd& a, int tiles_x, int tiles_y, cudaStream_t s) {
 #if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16
   static bool configured = false;   // per instantiation; the attribute is idempotent, a race only repeats the call
   if (!configured) {
-    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrSmemBytes);
-    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW, POSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrSmemBytes);
+    cudaFuncSetAttribute(blend_bwd_tr_kernel<D, DEC, FLOW, POSE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
-  blend_bwd_tr_kernel<D, DEC, FLOW><<<a.K * tiles_x * tiles_y, kBlendThreads, kTrSmemBytes, s>>>(a, tiles_x, tiles_y);
+  blend_bwd_tr_kernel<D, DEC, FLOW, POSE><<<a.K * tiles_x * tiles_y, kBlendThreads, kTrSmemBytes, s>>>(a, tiles_x, tiles_y);
 #else
-  static_assert(!FLOW, "fused flow channels need the transposing backward");
+  static_assert(!FLOW && !POSE, "fused flow channels / in-kernel rays need the transposing backward");
   blend_bwd_kernel<D, DEC><<<a.K * tiles_x * tiles_y, kBlendThreads, 0, s>>>(a, tiles_x, tiles_y);
 #endif
 }
@@ -1118,18 +1174,21 @@ extern "C" int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream) {
   MOBGS_REQUIRE(a->tile_offsets && a->out_colors && a->out_alphas && a->last_idx, "NULL pointer");
   MOBGS_REQUIRE(a->N == 0 || (a->records && a->sorted_ids), "NULL records / sorted_ids");
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
-  if (a->dec_rays) {
+  if (a->dec_rays || a->dec_pose) {
     MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_rgb, "fused decode epilogue needs D=10, w1, w2, out_rgb");
+    MOBGS_REQUIRE(!a->dec_pose || (a->dec_sfx != 0.f && a->dec_sfy != 0.f), "dec_pose needs non-zero scale factors");
     if (a->out_flow) {
 #if !MOBGS_FWD_PREDICATED
       MOBGS_REQUIRE(a->flow_ref >= 0, "flow_ref must name a record set");
-      blend_fwd_kernel<10, true, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+      if (a->dec_pose) blend_fwd_kernel<10, true, true, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+      else blend_fwd_kernel<10, true, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
       return check_launch("blend_decode_flow_fwd");
 #else
       MOBGS_REQUIRE(false, "fused flow channels are not built into the predicated ablation build");
 #endif
     }
-    blend_fwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+    if (a->dec_pose) blend_fwd_kernel<10, true, false, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
+    else blend_fwd_kernel<10, true><<<a->K * tiles_x * tiles_y, kBlendThreads, 0, (cudaStream_t)stream>>>(*a, tiles_x, tiles_y);
     return check_launch("blend_decode_fwd");
   }
   MOBGS_REQUIRE(!a->out_flow, "fused flow channels need the fused decode epilogue (dec_rays)");
@@ -1145,19 +1204,30 @@ extern "C" int mobgs_blend_bwd(const MobgsBlendBwd* a, void* stream) {
   MOBGS_REQUIRE(a->records && a->tile_offsets && a->sorted_ids && a->out_alphas && a->last_idx && a->v_records,
                 "NULL pointer");
   const int tiles_x = (a->width + kTile - 1) / kTile, tiles_y = (a->height + kTile - 1) / kTile;
-  if (a->dec_rays) {
+  if (a->dec_rays || a->dec_pose) {
     MOBGS_REQUIRE(a->D == 10 && a->dec_w1 && a->dec_w2 && a->out_colors && a->v_w_partial,
                   "fused decode prologue needs D=10, w1, w2, out_colors, v_w_partial");
+    MOBGS_REQUIRE(!a->dec_pose || (a->dec_sfx != 0.f && a->dec_sfy != 0.f), "dec_pose needs non-zero scale factors");
+    MOBGS_REQUIRE(a->dec_pose || !a->v_pose_partial, "v_pose_partial needs dec_pose");
     if (a->g_flow) {
 #if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16 && MOBGS_BWD_DIRECT_RED
       MOBGS_REQUIRE(a->flow_ref >= 0, "flow_ref must name a record set");
-      launch_bwd_kernel<10, true, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+      if (a->dec_pose) launch_bwd_kernel<10, true, true, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+      else launch_bwd_kernel<10, true, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
       return check_launch("blend_decode_flow_bwd");
 #else
       MOBGS_REQUIRE(false, "fused flow channels need the transposing backward build");
 #endif
     }
-    launch_bwd_kernel<10, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+    if (a->dec_pose) {
+#if MOBGS_BWD_TRANSPOSE && MOBGS_UNIT_LANES == 16
+      launch_bwd_kernel<10, true, false, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+#else
+      MOBGS_REQUIRE(false, "in-kernel rays need the transposing backward build");
+#endif
+    } else {
+      launch_bwd_kernel<10, true>(*a, tiles_x, tiles_y, (cudaStream_t)stream);
+    }
     return check_launch("blend_decode_bwd");
   }
   MOBGS_REQUIRE(!a->g_flow, "fused flow channels need the fused decode prologue (dec_rays)");

@@ -8,27 +8,16 @@
 // (pixel, camera).  Backward (R and c carry the pose gradient): 12 sums over the pixels of
 // each camera, warp shuffle -> CTA -> one atomicAdd per CTA and value.
 #include "common.cuh"
+#include "ray_math.cuh"
 
 namespace mobgs {
 
 constexpr int kRayThreads = 256;
 
-struct RayCam { float r[9], c[3]; };
-
-__device__ __forceinline__ RayCam load_ray_cam(const float* rot, const float* centre, int k) {
-  RayCam m;
-#pragma unroll
-  for (int i = 0; i < 9; ++i) m.r[i] = rot[9 * k + i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) m.c[i] = centre[3 * k + i];
-  return m;
-}
-
 __device__ __forceinline__ void local_dir(const MobgsCameraRays& a, int p, float (&l)[3]) {
   const int y = p / a.W, x = p - y * a.W;
-  const float lx = ((float)x + 0.5f - a.ppx) / a.sfx, ly = ((float)y + 0.5f - a.ppy) / a.sfy;
-  const float n = sqrtf(lx * lx + ly * ly + 1.f);
-  l[0] = lx / n; l[1] = ly / n; l[2] = 1.f / n;
+  const RayIntr in = {a.ppx, a.ppy, a.sfx, a.sfy};
+  ray_local_dir(in, x, y, l);
 }
 
 __global__ void __launch_bounds__(kRayThreads) camera_rays_fwd_kernel(const __grid_constant__ MobgsCameraRays a) {

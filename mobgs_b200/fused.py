@@ -353,13 +353,15 @@ class _BlendDecode(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
-                vsp_list, want_mean, mean_K=0, flow_ref=-1):
+                vsp_list, want_mean, mean_K=0, flow_ref=-1, ray_intr=None):
         records = _f32c(records)
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
         dev = records.device
         K = Kr if specs is None else len(specs)
-        assert rays.shape[1] == 6
+        # ray_intr = (ppx, ppy, sfx, sfy): `rays` is then the [n_cam,12] pose tensor (R row-major | centre) and every
+        # pixel's ray is generated in registers (MobgsBlendFwd.dec_pose) instead of read from a [n_cam,6,H,W] image
+        assert rays.shape[1] == (6 if ray_intr is None else 12)
         if rays.shape[0] == 1:
             per_k = 0
         elif rays.shape[0] == K:
@@ -380,7 +382,9 @@ class _BlendDecode(torch.autograd.Function):
             flow = torch.empty(K, height, width, 2, device=dev) if flow_ref >= 0 else None
             a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
                            _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
-                           _p(rays), per_k, _p(w1), _p(w2), _p(rgb), _p(depth), max(flow_ref, 0), _p(flow))
+                           _p(rays) if ray_intr is None else None, per_k, _p(w1), _p(w2), _p(rgb), _p(depth),
+                           max(flow_ref, 0), _p(flow), *((None, 0.0, 0.0, 0.0, 0.0) if ray_intr is None else
+                                                         (_p(rays), *ray_intr)))
             L.call("mobgs_blend_fwd", a, _stream())
             return img10, alpha, last, rgb, depth, flow
 
@@ -394,7 +398,7 @@ class _BlendDecode(torch.autograd.Function):
             ctx.mark_non_differentiable(mean)
         ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
-        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK, flow_ref)
+        ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK, flow_ref, ray_intr)
         ctx.n_isect = lists.n_isect
         if flow is None:
             flow = torch.empty(0, device=dev)
@@ -404,7 +408,7 @@ class _BlendDecode(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_alpha, g_mean, g_flow):
         records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2 = ctx.saved_tensors
-        K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK, flow_ref = ctx.meta
+        K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK, flow_ref, ray_intr = ctx.meta
         if flow_ref >= 0:
             g_flow = _f32c(g_flow) if g_flow is not None else torch.zeros(K, height, width, 2, device=records.device)
         else:
@@ -416,34 +420,45 @@ class _BlendDecode(torch.autograd.Function):
         g_mean = _f32c(g_mean) if (g_mean is not None and g_mean.numel() > 0) else None
         v_rec = torch.zeros(Kr, N, L.REC, device=dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
-        v_rays = None
+        v_rays = v_pose = None
         if ctx.needs_input_grad[5]:
-            v_rays = torch.empty_like(rays) if per_k == 1 else torch.zeros_like(rays)
+            if ray_intr is not None:
+                v_pose = torch.zeros(rays.shape[0], L.POSE_SLOTS, 12, device=dev)
+            else:
+                v_rays = torch.empty_like(rays) if per_k == 1 else torch.zeros_like(rays)
         v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
         a = L.BlendBwd(K, N, 10, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
-                       _p(rays), per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth), _p(g_alpha), _p(g_mean),
-                       mK, _p(v_rays), _p(v_wp), max(flow_ref, 0), _p(g_flow))
+                       _p(rays) if ray_intr is None else None, per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth),
+                       _p(g_alpha), _p(g_mean), mK, _p(v_rays), _p(v_wp), max(flow_ref, 0), _p(g_flow),
+                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))))
         L.call("mobgs_blend_bwd", a, _stream())
+        if v_pose is not None:
+            v_rays = v_pose.sum(1)
         v_w = v_wp.sum(0)
         return (v_rec, None, None, None, v_vsp, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6),
-                None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, height, specs=None, tight=True,
                  vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False, mean_K: int = 0,
                  flow_ref: Optional[int] = None):
     """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty[, flow [K,H,W,2]]).
-    rays: [1,6,H,W] shared, [K,6,H,W] per list, or [record sets,6,H,W] per projection.
+    rays: [1,6,H,W] shared, [K,6,H,W] per list, or [record sets,6,H,W] per projection — or a
+    mobgs_b200.cameras.RayPose (same leading-axis conventions, 12 pose floats per camera): the kernels then generate
+    every pixel's ray in registers and reduce the pose gradient themselves, no ray image exists.
     mean_K: the blur mean is taken over the first mean_K lists (0 = all).
     flow_ref: record set whose projected means define two extra colour channels composited in the same walk,
     records[flow_ref][g].xy - records[own set][g].xy, no background (get_flow's exp2mid render, renderer :426-441);
     when given, a fifth output `flow` is returned."""
     if specs is not None:
         specs = tuple(tuple(int(v) for v in s) for s in specs)
+    ray_intr = None
+    if not isinstance(rays, torch.Tensor):          # cameras.RayPose
+        rays, ray_intr = rays.pose, tuple(float(v) for v in rays.intr)
     out = _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
                              specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K),
-                             -1 if flow_ref is None else int(flow_ref))
+                             -1 if flow_ref is None else int(flow_ref), ray_intr)
     return out if flow_ref is not None else out[:4]
 
 
@@ -511,13 +526,13 @@ class _FlowRender(torch.autograd.Function):
     -> rgb [K,3,H,W], flow_e2m [K,H,W,2], alpha_dyn [K,H,W], mid [M,H,W,10]."""
 
     @staticmethod
-    def forward(ctx, records, radii, depths, bg10, rays, w1, w2, width, height, Ns, tight):
+    def forward(ctx, records, radii, depths, bg10, rays, w1, w2, width, height, Ns, tight, ray_intr=None):
         records = _f32c(records)
         rays, w1, w2, bg10 = _f32c(rays), _f32c(w1), _f32c(w2), _f32c(bg10)
         Kr, N = radii.shape
         K = Kr - 1
         dev = records.device
-        assert rays.shape[0] == 1 and rays.shape[1] == 6
+        assert rays.shape[0] == 1 and rays.shape[1] == (6 if ray_intr is None else 12)   # ray image or pose (_BlendDecode)
         st = _stream()
 
         def exp_walk(lists):
@@ -528,7 +543,8 @@ class _FlowRender(torch.autograd.Function):
             flow = torch.empty(K, height, width, 2, device=dev)
             a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
                            _p(lists.sorted_ids), _p(bg10), _p(img10), _p(alpha), _p(last),
-                           _p(rays), 0, _p(w1), _p(w2), _p(rgb), None, 0, _p(flow))
+                           _p(rays) if ray_intr is None else None, 0, _p(w1), _p(w2), _p(rgb), None, 0, _p(flow),
+                           *((None, 0.0, 0.0, 0.0, 0.0) if ray_intr is None else (_p(rays), *ray_intr)))
             L.call("mobgs_blend_fwd", a, st)
             return img10, alpha, last, rgb, flow
 
@@ -562,7 +578,7 @@ class _FlowRender(torch.autograd.Function):
                               alpha_d, last_d, ld.tile_offsets, ld.sorted_ids, frec, alpha_m, last_m, lm.tile_offsets,
                               lm.sorted_ids)
         ctx.lists = (le.lists, le.capacity, ld.lists, ld.capacity, lm.lists, lm.capacity)
-        ctx.meta = (K, M, N, width, height)
+        ctx.meta = (K, M, N, width, height, ray_intr)
         return rgb, flow, alpha_d, mid
 
     @staticmethod
@@ -570,18 +586,26 @@ class _FlowRender(torch.autograd.Function):
         (records, bg10, rays, w1, w2, img10, alpha_e, last_e, off_e, ids_e, alpha_d, last_d, off_d, ids_d, frec, alpha_m,
          last_m, off_m, ids_m) = ctx.saved_tensors
         le, cap_e, ld, cap_d, lm, cap_m = ctx.lists
-        K, M, N, width, height = ctx.meta
+        K, M, N, width, height, ray_intr = ctx.meta
         dev = records.device
         st = _stream()
         v_rec = torch.zeros(K + 1, N, L.REC, device=dev)
-        v_rays = torch.zeros_like(rays) if ctx.needs_input_grad[4] else None
+        v_rays = v_pose = None
+        if ctx.needs_input_grad[4]:
+            if ray_intr is None:
+                v_rays = torch.zeros_like(rays)
+            else:
+                v_pose = torch.zeros(1, L.POSE_SLOTS, 12, device=dev)
         v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
         g_rgb = _f32c(g_rgb) if g_rgb is not None else None
         g_flow = _f32c(g_flow) if g_flow is not None else torch.zeros(K, height, width, 2, device=dev)
         a = L.BlendBwd(K, N, 10, width, height, le, cap_e, _p(records), _p(off_e), _p(ids_e), _p(bg10), _p(alpha_e),
-                       _p(last_e), None, None, _p(v_rec), -1, None, _p(rays), 0, _p(w1), _p(w2), _p(img10), _p(g_rgb),
-                       None, None, None, 0, _p(v_rays), _p(v_wp), 0, _p(g_flow))
+                       _p(last_e), None, None, _p(v_rec), -1, None, _p(rays) if ray_intr is None else None, 0, _p(w1),
+                       _p(w2), _p(img10), _p(g_rgb), None, None, None, 0, _p(v_rays), _p(v_wp), 0, _p(g_flow),
+                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))))
         L.call("mobgs_blend_bwd", a, st)
+        if v_pose is not None:
+            v_rays = v_pose.sum(1)
         if g_alpha_d is not None:
             zeros = torch.zeros(K, height, width, 1, device=dev)
             a = L.BlendBwd(K, N, 1, width, height, ld, cap_d, _p(records), _p(off_d), _p(ids_d), None, _p(alpha_d),
@@ -594,9 +618,14 @@ class _FlowRender(torch.autograd.Function):
             L.call("mobgs_blend_bwd", a, st)
             L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(v_frec), _p(v_rec), 1), st)
         v_w = v_wp.sum(0)
-        return (v_rec, None, None, None, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6), None, None, None, None)
+        return (v_rec, None, None, None, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6), None, None, None, None, None)
 
 
 def flow_render(records, radii, depths, bg10, rays, w1, w2, width, height, n_static, tight=True):
-    """see _FlowRender; bg10 [K,10] (the exposure lists' background), rays [1,6,H,W] (one camera for all lists)."""
-    return _FlowRender.apply(records, radii, depths, bg10, rays, w1, w2, int(width), int(height), int(n_static), bool(tight))
+    """see _FlowRender; bg10 [K,10] (the exposure lists' background), rays [1,6,H,W] (one camera for all lists) or a
+    one-camera mobgs_b200.cameras.RayPose."""
+    ray_intr = None
+    if not isinstance(rays, torch.Tensor):
+        rays, ray_intr = rays.pose, tuple(float(v) for v in rays.intr)
+    return _FlowRender.apply(records, radii, depths, bg10, rays, w1, w2, int(width), int(height), int(n_static), bool(tight),
+                             ray_intr)

@@ -187,7 +187,7 @@ def _pixel_grid(cam, W, H, dev):
     return g
 
 
-def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposures):
+def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Tensor, delta_exposures, rays=None):
     """K get_flow() calls (train.py:563-579 issues one per latent sub-frame) as ONE projection launch (K+1
     record sets: the mid time once + the K exposure times) and three launch chains that bin every distinct
     geometry once and walk it once per payload group:
@@ -201,7 +201,9 @@ def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Te
 
     4K binned + walked lists before, 2K + 1 binned and 2K + ceil(2K/10) walked now (K of them over the dynamic
     Gaussians only).  Returns (exp2mid_coord [K,H,W,2], mid2exp_coord [K,H,W,2], latent_img [K,3,H,W],
-    latent_alpha [K,H,W]) — `torch.cat` of what K reference calls return."""
+    latent_alpha [K,H,W]) — `torch.cat` of what K reference calls return.
+    `rays`: optional replacement for `viewpoint_camera.cam_ray` — a [1,6,H,W] tensor or a one-camera
+    mobgs_b200.cameras.RayPose (rays generated inside the blend kernels, no ray image read)."""
     cam = viewpoint_camera
     dev = dyn_pc._scaling.device
     W, H = int(cam.image_width), int(cam.image_height)
@@ -221,8 +223,8 @@ def get_flow_batched(viewpoint_camera, stat_pc, dyn_pc, pipe, bg_color: torch.Te
     # gradient-record buffer
     dec = dyn_pc.rgbdecoder
     rgb, flow_e2m, alpha_d, mid = fused.flow_render(
-        rec, radii, depths, _bg10(bg_color, dev).expand(K, -1), cam.cam_ray, dec.mlp1.weight.reshape(6, 12),
-        dec.mlp2.weight.reshape(3, 6), W, H, Ns, tight=TIGHT_TILES)
+        rec, radii, depths, _bg10(bg_color, dev).expand(K, -1), cam.cam_ray if rays is None else rays,
+        dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6), W, H, Ns, tight=TIGHT_TILES)
     exp2mid = grid + flow_e2m
     M = mid.shape[0]
     flows_m2e = mid.permute(1, 2, 0, 3).reshape(H, W, M * 10)[..., :2 * K].reshape(H, W, K, 2).permute(2, 0, 1, 3)

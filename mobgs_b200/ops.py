@@ -122,6 +122,8 @@ class TileLists:
 # (rare) overflow case, so results are always those of the exactly-sized lists.
 _CAP_CACHE = {}
 SPECULATIVE_LISTS = os.environ.get("MOBGS_SPECULATIVE_LISTS", "1") != "0"
+# 0: always the two-pass count / emit kernels (ablation; the default records entries in the counting pass)
+RECORD_ENTRIES = os.environ.get("MOBGS_RECORD_ENTRIES", "1") != "0"
 
 
 def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None, tile_list=None):
@@ -157,24 +159,33 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     nt = K * tiles
     counts = torch.empty(nt, dtype=torch.int32, device=dev)
     offsets = torch.empty(nt + 1, dtype=torch.int32, device=dev)
-    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), lists, _p(counts), _p(offsets))
+    key = (K, N, width, height, tuple(bin_specs), bool(tight), dev.index)
+    guess = _CAP_CACHE.get(key)
+    speculative = consume is not None and guess is not None and SPECULATIVE_LISTS
+    # Speculative calls also let the counting pass RECORD the intersections it finds (MobgsTileCount.entries), which turns
+    # the emit pass into a streaming scatter; the exact-size (first / overflow) calls use the two-pass kernels.
+    entries = cursor = None
+    if speculative and RECORD_ENTRIES:
+        entries = torch.empty(max(int(guess), 1), 4, dtype=torch.int32, device=dev)
+        cursor = torch.empty(1, dtype=torch.int32, device=dev)
+    a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), lists, _p(counts), _p(offsets),
+                    _p(depths), _p(entries), 0 if entries is None else entries.shape[0], _p(cursor))
     L.call("mobgs_tile_count", a, _stream())
 
-    def emit_sort(cap):
+    def emit_sort(cap, use_entries=False):
         cap = max(int(cap), 1)
         keys = torch.empty(cap, dtype=torch.int64, device=dev)
         keys_tmp = torch.empty(cap, dtype=torch.int64, device=dev)
         sorted_ids = torch.empty(cap, dtype=torch.int32, device=dev)
         b = L.TileSort(K, N, width, height, _p(records), _p(radii), _p(depths), int(tight), lists, _p(offsets),
-                       _p(counts), cap, _p(keys), _p(keys_tmp), _p(sorted_ids))
+                       _p(counts), cap, _p(keys), _p(keys_tmp), _p(sorted_ids),
+                       *((_p(entries), entries.shape[0], _p(cursor)) if use_entries else (None, 0, None)))
         L.call("mobgs_tile_emit_sort", b, _stream())
         tl = TileLists(offsets, sorted_ids, None, K, width, height)
         tl.lists, tl.capacity, tl.specs = blend_lists, cap, tuple(specs)
         return tl
 
-    key = (K, N, width, height, tuple(bin_specs), bool(tight), dev.index)
-    guess = _CAP_CACHE.get(key)
-    if consume is None or guess is None or not SPECULATIVE_LISTS:
+    if not speculative:
         n_isect = int(offsets[-1].item())
         tl = emit_sort(n_isect)
         tl.n_isect = n_isect
@@ -184,11 +195,11 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     host_n.copy_(offsets[-1:], non_blocking=True)
     ev = torch.cuda.Event()
     ev.record()
-    tl = emit_sort(guess)
+    tl = emit_sort(guess, use_entries=entries is not None)
     out = consume(tl)
     ev.synchronize()
     n_isect = int(host_n[0])
-    if n_isect > tl.capacity:           # overflow: redo with the exact size
+    if n_isect > tl.capacity:           # overflow: redo with the exact size (two-pass emit: the entry list overflowed too)
         tl = emit_sort(n_isect)
         out = consume(tl)
     tl.n_isect = n_isect

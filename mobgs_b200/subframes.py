@@ -29,7 +29,8 @@ def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, 
                      offset: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """viewmats [K,4,4] (may require grad: they come from the BLCE pose network), Ks [K,3,3] or
     [3,3], t_spline / t_poly [K] device tensors (see gaussian_renderer._times), rays [K,6,H,W]
-    (Camera.cam_ray of each warped camera) or [1,6,H,W].
+    (Camera.cam_ray of each warped camera) or [1,6,H,W] — or a mobgs_b200.cameras.RayPose (12 pose floats per camera;
+    rays are then generated inside the blend kernels and no ray image exists).
 
     Returns: "render" [3,H,W] (the blurred prediction, mean over K + 1e-10), "subframes"
     [K,3,H,W], "depth" [K,H,W], "alpha" [K,H,W], "radii" [K,N], "viewspace_points" [1,N,2] (leaf whose
@@ -72,7 +73,8 @@ def render_blurry_view(viewpoint_cam, warped_cams, exposure_time, stat_pc, dyn_p
     `viewpoint_cam` / `warped_cams[k]` are reference `Camera` objects (or mobgs_b200.scene
     stand-ins); `exposure_time` is blceKernel.get_warped_cams' second output ([K] tensor);
     use_delta_exposure mirrors `iteration > blceopt.start_warp_dynamic` (train.py:503-506).
-    `rays`: optional pre-stacked [K,6,H,W] camera rays of `warped_cams` (centre camera at K//2).
+    `rays`: optional pre-stacked [K,6,H,W] camera rays of `warped_cams` (centre camera at K//2), or their
+    mobgs_b200.cameras.RayPose (get_warped_cams_batched(...).ray_pose): rays generated inside the blend kernels.
 
     Returns the keys train.py consumes: "render" (blurred prediction), "subframes" [K,3,H,W],
     "depths" [K,H,W], and the centre render's "render_center", "depth", "s_render", "s_depth",

@@ -220,6 +220,39 @@ def test_speculative_list_capacity_overflow_is_redone_exactly():
     assert all(v > 7 for v in ops._CAP_CACHE.values())
 
 
+@pytest.mark.parametrize("tight", [False, True])
+@pytest.mark.parametrize("n,W,H,big", [(3000, 150, 100, False), (400, 272, 208, True), (1, 48, 48, False), (5000, 64, 48, False)])
+def test_recorded_entries_give_identical_lists(n, W, H, big, tight):
+    """The counting pass that records (segment, slot, key) entries + the streaming scatter (the steady-state path) must
+    produce exactly the lists of the two-pass count / emit kernels: same offsets, same (depth, index) order — with several
+    lists over record sets and index ranges, rectangles of more than 64 tiles (`big`: repeat-the-test branch), an entry
+    buffer that is exactly full, and one that overflows (-> the caller redoes the binning with the two-pass kernels)."""
+    from mobgs_b200 import ops
+    means, quats, scales, opac, colors, view, Kmat = _scene(n, W, H, 5, 3)
+    if big:
+        scales = scales * 12          # 3-sigma squares of well over 8 x 8 tiles
+    radii, m2d, dep, con = ops.project(means.cuda(), quats.cuda(), scales.cuda(), torch.stack([view, view]).cuda(),
+                                       torch.stack([Kmat, Kmat]).cuda(), W, H)
+    rec = torch.zeros(2, n, 16, device="cuda")
+    rec[..., 0:2], rec[..., 2], rec[..., 3:6] = m2d, opac.cuda(), con
+    rec[1, :, 0] += 3.0
+    specs = ((0, 0, n), (1, n // 3, n), (1, 0, n // 3))
+    consume = lambda tl: tl.sorted_ids.clone()
+    ops._CAP_CACHE.clear()
+    ref, ref_ids = ops.build_tile_lists(rec, radii, dep, W, H, tight=tight, specs=specs, consume=consume)   # two-pass (no guess yet)
+    I = ref.n_isect
+    ref_off = ref.tile_offsets.clone()
+    for cap in (None, I, max(I // 2, 1)):
+        if cap is not None:
+            for k in list(ops._CAP_CACHE):
+                ops._CAP_CACHE[k] = cap
+        assert ops.RECORD_ENTRIES and len(ops._CAP_CACHE) == 1
+        got, got_ids = ops.build_tile_lists(rec, radii, dep, W, H, tight=tight, specs=specs, consume=consume)
+        assert got.n_isect == I
+        assert torch.equal(got.tile_offsets, ref_off)
+        assert torch.equal(got_ids[:I], ref_ids[:I]), f"capacity {cap}"
+
+
 @pytest.mark.parametrize("n,note", [(500, "rank sort (<= 768 per tile)"), (2500, "shared-memory radix (<= 4096)"),
                                     (7000, "global-memory radix (> 4096)")])
 def test_dense_tiles_exercise_every_sort_path(n, note):
