@@ -347,6 +347,87 @@ __global__ void __launch_bounds__(kSortThreads) tile_rank_sort_kernel(MobgsTileS
   }
 }
 
+// Bucketed rank sort (the default for n <= kRankSortMax): the all-pairs count above costs n / 2 iterations per key.  Here
+// the keys are first split into kBuckets ranges of their depth bits — bucket = (depth_bits - min) >> shift, monotone in
+// the key, so buckets are already in final order — with one shared-memory atomic per key (histogram position), an
+// exclusive scan over the buckets, and a scatter into bucket order; each key then ranks itself against its own bucket
+// only (a handful of LDS.64 instead of n / 2 LDS.128).  Threads are assigned to keys in bucket order, so a warp's lanes
+// loop over the same one or two buckets.  Depth ties share a bucket and are ordered by the index half of the key, as
+// before; if every key has the same depth the kernel degenerates to the all-pairs count.
+#ifndef MOBGS_RANK_SORT_BUCKETS
+#define MOBGS_RANK_SORT_BUCKETS 1
+#endif
+constexpr int kBuckets = 64;
+__global__ void __launch_bounds__(kSortThreads) tile_bucket_sort_kernel(MobgsTileSort a) {
+  __shared__ __align__(16) uint64_t buf[kRankSortMax];
+  __shared__ int hist[kBuckets], start[kBuckets + 1];
+  __shared__ uint32_t wmin[kSortWarps], wmax[kSortWarps];
+  const int seg = blockIdx.x;
+  const int beg = a.tile_offsets[seg];
+  int n = a.tile_offsets[seg + 1] - beg;
+  if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
+  if (n <= 0 || n > kRankSortMax) return;
+  const uint64_t* gkeys = a.keys + beg;
+  if (n == 1) {
+    if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(gkeys[0] & 0xffffffffu);
+    return;
+  }
+  constexpr int kPer = (kRankSortMax + kSortThreads - 1) / kSortThreads;   // keys per thread (3)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t key[kPer];
+  uint32_t lo = 0xffffffffu, hi = 0u;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + j * kSortThreads;
+    key[j] = i < n ? gkeys[i] : 0ull;
+    if (i < n) { const uint32_t d = (uint32_t)(key[j] >> 32); lo = min(lo, d); hi = max(hi, d); }
+  }
+  if (threadIdx.x < kBuckets) hist[threadIdx.x] = 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { wmin[warp] = lo; wmax[warp] = hi; }
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) { lo = min(lo, wmin[w]); hi = max(hi, wmax[w]); }
+  const uint32_t range = hi - lo;
+  const int shift = range < (uint32_t)kBuckets ? 0 : (32 - __clz(range)) - 6;   // (range >> shift) < kBuckets = 2^6
+  int slot[kPer], bkt[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + j * kSortThreads;
+    bkt[j] = (int)(((uint32_t)(key[j] >> 32) - lo) >> shift);
+    slot[j] = i < n ? atomicAdd(&hist[bkt[j]], 1) : 0;
+  }
+  __syncthreads();
+  if (warp == 0) {          // exclusive scan over the 64 buckets, two per lane
+    const int c0 = hist[2 * lane], c1 = hist[2 * lane + 1];
+    int s = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+    start[2 * lane] = s - c0 - c1;
+    start[2 * lane + 1] = s - c1;
+    if (lane == 31) start[kBuckets] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = threadIdx.x + j * kSortThreads;
+    if (i < n) buf[start[bkt[j]] + slot[j]] = key[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += kSortThreads) {
+    const uint64_t k = buf[i];
+    const int b = (int)(((uint32_t)(k >> 32) - lo) >> shift);
+    const int b0 = start[b], b1 = start[b + 1];
+    int rank = b0;
+    for (int q = b0; q < b1; ++q) rank += buf[q] < k;
+    a.sorted_ids[beg + rank] = (int)(k & 0xffffffffu);
+  }
+}
+
 // Large segments (n > kRankSortMax, rare): LSD radix sort, one CTA per segment at a time.  The grid is a
 // few CTAs per SM; each scans 256 segment sizes at once and sorts the large ones it finds.
 __device__ void radix_sort_segment(const MobgsTileSort& a, int seg, uint64_t* bufA, uint64_t* bufB,
@@ -467,7 +548,11 @@ extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
   }
   const size_t smem = 2 * sizeof(uint64_t) * kSortSmemCap + sizeof(int) * kSortWarps * 256;
   cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#if MOBGS_RANK_SORT_BUCKETS
+  tile_bucket_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);
+#else
   tile_rank_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);
+#endif
   static int sort_ctas = 0;           // a few CTAs per SM (the radix buffers allow 3)
   if (!sort_ctas) {
     int dev = 0, sms = 148;

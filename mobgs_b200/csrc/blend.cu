@@ -128,6 +128,13 @@ __device__ __forceinline__ int build_unit_lists(const unsigned* smask, unsigned 
   return mine;
 }
 
+// Gaussian index of list entry `idx`, clamped to [0, N): when a speculative list capacity overflows, the attempt's lists
+// hold unwritten entries (the caller discards it and redoes the chain with the exact size), and this kernel — already
+// enqueued on them — must still dereference valid records.
+__device__ __forceinline__ int list_gid(const int32_t* sorted_ids, int idx, int N) {
+  return (int)min((unsigned)sorted_ids[idx], (unsigned)(N - 1));
+}
+
 // first / one-past-last entry of the tile lists walked by CTA (list k, tile): lists may share a binning
 __device__ __forceinline__ int tile_segment(const MobgsLists& l, int k, int tiles, int tile) {
   return l.tile_list[k] * tiles + tile;
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
     if (tid == 0) mbar_expect_tx(&sbar, (uint32_t)bn * kRecBytes);
     float2 mref = make_float2(0.f, 0.f);
     if (idx < end) {
-      const int g = a.sorted_ids[idx];
+      const int g = list_gid(a.sorted_ids, idx, a.N);
       bulk_g2s(&srec[tid][0], recs + (size_t)g * 4, kRecBytes, &sbar);
       if (FLOW) mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
     }
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
     }
 #else
     if (idx < end) {
-      const int g = a.sorted_ids[idx];
+      const int g = list_gid(a.sorted_ids, idx, a.N);
       const float4* r = recs + (size_t)g * 4;
       const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
       srec[tid][0] = q0; srec[tid][1] = q1;
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     constexpr uint32_t kRecBytes = D > 6 ? 64 : (D > 2 ? 48 : 32);
     if (tid == 0) mbar_expect_tx(&sbar, (uint32_t)bn * kRecBytes);
     if (tid < bn) {
-      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      const int g = list_gid(a.sorted_ids, hi - tid, a.N);   // slot t holds list entry hi - t
       sid[tid] = g;
       bulk_g2s(&srec[tid][0], recs + (size_t)g * 4, kRecBytes, &sbar);
     }
@@ -634,7 +641,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
     if (tid < bn) smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
 #else
     if (tid < bn) {
-      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      const int g = list_gid(a.sorted_ids, hi - tid, a.N);   // slot t holds list entry hi - t
       sid[tid] = g;
       const float4* r = recs + (size_t)g * 4;
       const float4 q0 = __ldg(r), q1 = __ldg(r + 1);
@@ -793,7 +800,21 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 #ifndef MOBGS_BWD_DIRECT_RED
 #define MOBGS_BWD_DIRECT_RED 1
 #endif
+// 1: Phase A without the per-iteration "is this unit's list exhausted" test: the unit lists are pre-filled with the index
+// of a dummy record (opacity 0 -> alpha = 0 -> the pair is invalid by the ordinary alpha test), the "blended by this pixel"
+// test is one compare against a per-batch constant, and v_sigma is selected straight from opac * vis (6 of 54
+// instructions per iteration).
+#ifndef MOBGS_BWD_LEAN_A
+#define MOBGS_BWD_LEAN_A 1
+#endif
+// 1: Phase B sums the six moments of v_sigma about the unit's first pixel — sums of vs, c vs, r vs, c^2 vs, c r vs with
+// the compile-time pixel offsets c in 0..3, r in 0..1 (27 instructions per lane and block) — and shifts them to the
+// Gaussian's mean once per (unit, Gaussian); 0: accumulates them about the mean pixel by pixel (64 instructions).
+#ifndef MOBGS_BWD_UNIT_MOMENTS
+#define MOBGS_BWD_UNIT_MOMENTS 1
+#endif
 constexpr int kBwdBatch = MOBGS_BWD_DIRECT_RED ? 192 : 128;   // list entries staged per batch (shared-memory budget)
+constexpr int kDummySlot = kBwdBatch;          // staged row of the dummy record (MOBGS_BWD_LEAN_A)
 constexpr int kRecRow = 20;                    // floats between staged records (16 used): the rows of 8 different
                                                // entries start 4 banks apart for the per-entry reads of Phase B
 constexpr int kListRow = kBwdBatch + 8;        // bytes between unit lists: 8-byte loads of a warp's two units differ in bank
@@ -806,7 +827,7 @@ constexpr int kVUnit = 2 * kVHalf + 8;         // second unit of the warp: +16 b
 constexpr int kVWarp = 2 * kVUnit;             //   groups of a warp read four different 16-byte bank groups
 constexpr int kAccRow = 17;                    // accumulator row stride: row t starts at bank 17 t
 constexpr int kAccFloats = MOBGS_BWD_DIRECT_RED ? 0 : kBwdBatch * kAccRow;
-constexpr int kTrScratch = kBwdBatch * kRecRow + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
+constexpr int kTrScratch = (kBwdBatch + 1) * kRecRow + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
 static_assert(kTrScratch >= 27 * kProPad, "prologue scratch must fit the aliased buffers");
 constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 112 + 112) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
 
@@ -821,8 +842,8 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   static_assert(kUL == 16, "transposing backward is written for 4x4-pixel units");
   static_assert(!FLOW || (D == 10 && MOBGS_BWD_DIRECT_RED), "fused flow channels need the D = 10 layout and direct reductions");
   extern __shared__ __align__(128) float smem[];
-  float* srec = smem;                                            // [kBwdBatch][kRecRow]   (TMA destination)
-  float* sacc = srec + kBwdBatch * kRecRow;                      // [kBwdBatch][kAccRow]
+  float* srec = smem;                                            // [kBwdBatch + 1][kRecRow]   (TMA destination + dummy row)
+  float* sacc = srec + (kBwdBatch + 1) * kRecRow;                // [kBwdBatch][kAccRow]
   float* sF = sacc + kAccFloats;                                 // [8 warps][F | VS][kBlk][kFRow]
   float* sV = smem + kTrScratch;                                 // [8 warps][kVWarp]
   float* sdec = sV + 8 * kVWarp;                                 // [112] decoder weights | camera pose
@@ -910,6 +931,9 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
 #pragma unroll
   for (int w = 0; w < kBlendThreads / 32; ++w) tile_last = max(tile_last, warp_max[w]);
   if (tile_last < beg) return;
+#if MOBGS_BWD_LEAN_A
+  if (tid < kRecRow) srec[kDummySlot * kRecRow + tid] = 0.f;      // dummy record: opacity 0 (visible after the batch barriers)
+#endif
 
   float* Fm = sF + warp * (2 * kBlk * kFRow);                     // F  [kBlk][kFRow]: fac     of (entry, pixel of the warp)
   float* VSm = Fm + kBlk * kFRow;                                 // VS [kBlk][kFRow]: v_sigma
@@ -928,12 +952,17 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     if (tid == 0) mbar_expect_tx(sbar, (uint32_t)bn * kRecBytes);
     float2 mref = make_float2(0.f, 0.f);
     if (tid < bn) {
-      const int g = a.sorted_ids[hi - tid];   // slot t holds list entry hi - t
+      const int g = list_gid(a.sorted_ids, hi - tid, a.N);   // slot t holds list entry hi - t
       sid[tid] = g;
       bulk_g2s(srec + tid * kRecRow, recs + (size_t)g * 4, kRecBytes, sbar);
       if (FLOW) mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
     }
     for (int i = tid; i < kAccFloats; i += kBlendThreads) sacc[i] = 0.f;
+#if MOBGS_BWD_LEAN_A
+    // every list byte names the dummy record until build_unit_lists overwrites it
+    for (int i = tid; i < 16 * kListRow / 4; i += kBlendThreads) reinterpret_cast<uint32_t*>(swl)[i] = 0x01010101u * (uint32_t)kDummySlot;
+    const int tmin = hi - last;            // pixel blended list entry hi - t  <=>  t >= tmin  (last = -1 outside the image)
+#endif
     mbar_wait(sbar, bar_phase);
     bar_phase ^= 1;
     if (tid < bn) {
@@ -953,8 +982,12 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
 #pragma unroll
       for (int i = 0; i < kBlk; ++i) {
         if (i >= nb) break;
+#if MOBGS_BWD_LEAN_A
+        const int t = (int)(((i < 4 ? tl.x : tl.y) >> (8 * (i & 3))) & 0xffu);   // past the unit's count: the dummy record
+#else
         const bool act = base + i < cnt;
         const int t = act ? (int)(((i < 4 ? tl.x : tl.y) >> (8 * (i & 3))) & 0xffu) : 0;
+#endif
         const float4* r = reinterpret_cast<const float4*>(srec + t * kRecRow);
         const float4 r0 = r[0], r1 = r[1];
         float4 r2 = make_float4(0, 0, 0, 0), r3 = make_float4(0, 0, 0, 0);
@@ -963,8 +996,13 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         const float dx = r0.x - px, dy = r0.y - py;
         const float pw = pair_exponent(r0, r1, dx, dy);          // = -sigma log2(e)
         const float vis = ex2_approx(pw);
-        const float alpha = fminf(kAlphaMax, r0.z * vis);
+        const float ou = r0.z * vis;
+        const float alpha = fminf(kAlphaMax, ou);
+#if MOBGS_BWD_LEAN_A
+        const bool valid = t >= tmin && pw <= 0.f && alpha >= kAlphaMin;
+#else
         const bool valid = act && inside && hi - t <= last && pw <= 0.f && alpha >= kAlphaMin;
+#endif
         // lanes whose pixel does not blend this Gaussian run the same arithmetic with alpha = 0, which
         // leaves T and S unchanged and makes both stored terms exactly zero
         const float al = valid ? alpha : 0.f;
@@ -980,8 +1018,12 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         }
         const float v_alpha = d * T + (tf_term - S) * ra;
         S += d * fac;
+#if MOBGS_BWD_LEAN_A
+        const float v_sigma = (valid && ou <= kAlphaMax) ? -ou * v_alpha : 0.f;   // (invalid lanes may hold ou = inf: selected away)
+#else
         const float ov = r0.z * (valid ? vis : 0.f);             // (sigma < 0 lanes may hold vis = inf)
         const float v_sigma = ov <= kAlphaMax ? -ov * v_alpha : 0.f;
+#endif
         Fm[i * kFRow + lane] = fac;
         VSm[i * kFRow + lane] = v_sigma;
       }
@@ -1002,13 +1044,32 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
         const float4 s0 = *reinterpret_cast<const float4*>(sr), s1 = *reinterpret_cast<const float4*>(sr + 4);
         const float fv[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
         const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#if MOBGS_BWD_UNIT_MOMENTS
+        {
+          // this lane's pixels are (c, r), c = 0..3, r = 0..1, at distance (X - c, Y - r) from the mean
+          const float X = mean.x - ubx, Y = mean.y - uby;
+          const float R0 = (sv[0] + sv[1]) + (sv[2] + sv[3]), R1 = (sv[4] + sv[5]) + (sv[6] + sv[7]);   // sum vs per row
+          const float C0 = fmaf(3.f, sv[3], fmaf(2.f, sv[2], sv[1])), C1 = fmaf(3.f, sv[7], fmaf(2.f, sv[6], sv[5]));   // sum c vs
+          const float Q0 = fmaf(9.f, sv[3], fmaf(4.f, sv[2], sv[1])), Q1 = fmaf(9.f, sv[7], fmaf(4.f, sv[6], sv[5]));   // sum c^2 vs
+          const float S0 = R0 + R1, Sc = C0 + C1, Scc = Q0 + Q1;      // (sum r vs = sum r^2 vs = R1, sum c r vs = C1)
+          const float m = X * S0, n = Y * S0;
+          acc[0] = m - Sc;                                  // sum vs dx
+          acc[1] = n - R1;                                  // sum vs dy
+          acc[2] = S0;
+          acc[3] = fmaf(X, fmaf(-2.f, Sc, m), Scc);         // sum vs dx^2  = X (X S0 - 2 Sc) + Scc
+          acc[4] = fmaf(X, acc[1], fmaf(-Y, Sc, C1));       // sum vs dx dy = X (Y S0 - Sr) - Y Sc + Scr
+          acc[5] = fmaf(Y, fmaf(-2.f, R1, n), R1);          // sum vs dy^2  = Y (Y S0 - 2 Sr) + Srr
+        }
+#else
         float dxs[4], dys[2];
 #pragma unroll
         for (int c = 0; c < 4; ++c) dxs[c] = mean.x - (ubx + (float)c);
         dys[0] = mean.y - uby;
         dys[1] = mean.y - (uby + 1.f);
+#endif
 #pragma unroll
         for (int pp = 0; pp < 8; ++pp) {
+#if !MOBGS_BWD_UNIT_MOMENTS
           const float dx = dxs[pp & 3], dy = dys[pp >> 2];
           const float vs = sv[pp], sx = vs * dx, sy = vs * dy;
           acc[0] += sx;
@@ -1017,6 +1078,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
           acc[3] += sx * dx;
           acc[4] += sx * dy;
           acc[5] += sy * dy;
+#endif
           const float4* vp = reinterpret_cast<const float4*>(vrow + pp * kVPix);
           const float4 v0 = vp[0];
           acc[6] += fv[pp] * v0.x;
