@@ -155,7 +155,7 @@ typedef struct {
   const float* t_spline;
   const float* t_poly;
   const int32_t* radii;     /* [K,N] */
-  const float* v_records;   /* [K,N,16] */
+  float* v_records;         /* [K,N,16]; read (and, with zero_v_records, zeroed behind the read) */
   float* v_xyz; float* v_rotation_s; float* v_scaling_s; float* v_opacity_s; float* v_features_dc_s;
   float* v_control_xyz; float* v_rotation_d; float* v_omega; float* v_scaling_d; float* v_opacity_d;
   float* v_features_dc_d; float* v_features_t; float* v_offset;
@@ -165,6 +165,10 @@ typedef struct {
    * a private block passes block - g0 * row_floats.  Used to split the backward into chunks whose gradient
    * all-reduce (NCCL, side stream) overlaps the next chunk's kernel. */
   int32_t g_lo, g_hi;
+  /* != 0: the gradient records of the Gaussian range are overwritten with zeros behind the reads (whole warps zero
+   * their 2 KB chunks with coalesced stores), so the [K,N,16] buffer returns to the all-zero state mobgs_blend_bwd
+   * needs and a caller that keeps it across steps never issues the 448 MB allocation + memset. */
+  int32_t zero_v_records;
 } MobgsSynthBwd;
 int mobgs_synth_project_bwd(const MobgsSynthBwd* a, void* stream);
 

@@ -106,7 +106,8 @@ class SynthBwd(C.Structure):
                 ("v_control_xyz", C.c_void_p), ("v_rotation_d", C.c_void_p), ("v_omega", C.c_void_p),
                 ("v_scaling_d", C.c_void_p), ("v_opacity_d", C.c_void_p),
                 ("v_features_dc_d", C.c_void_p), ("v_features_t", C.c_void_p),
-                ("v_offset", C.c_void_p), ("v_viewmats", C.c_void_p), ("g_lo", C.c_int32), ("g_hi", C.c_int32)]
+                ("v_offset", C.c_void_p), ("v_viewmats", C.c_void_p), ("g_lo", C.c_int32), ("g_hi", C.c_int32),
+                ("zero_v_records", C.c_int32)]
 
 
 class Pack(C.Structure):

@@ -13,6 +13,9 @@ from __future__ import annotations
 
 from typing import Optional, Tuple
 
+import os
+import weakref
+
 import torch
 
 from . import _lib as L
@@ -41,6 +44,51 @@ GRAD_SINK = None
 # caller installs one that hands out a persistent NVLS symmetric-memory buffer (mobgs_b200.dist.SymmetricGradients), so
 # that the gradient all-reduce is a multimem (in-switch) reduction on the very buffer the backward kernel wrote.
 FLAT_ALLOCATOR = None
+
+# Gradient-record buffers [record sets, N, 16] are kept across steps: the blend backward scatters into an all-zero buffer
+# and the projection backward — its only reader — zeroes the whole buffer behind its reads (MobgsSynthBwd.zero_v_records:
+# each warp clears the 2 KB chunk it has just consumed, coalesced), so the buffer comes back clean and the per-step 448 MB
+# allocation + memset (1 M Gaussians, K = 7) disappears.  Only buffers handed out by `_take_grad_records` and still alive
+# when they reach `_SynthProject.backward` are recycled; anything else (a user-supplied gradient, an autograd-accumulated
+# sum in a fresh tensor) is read without being touched.
+_GRAD_REC_POOL = {}      # (record sets, N, device index) -> clean buffer not in use
+_GRAD_REC_OUT = {}       # data_ptr -> (key, weakref to the tensor handed out)
+_GRAD_REC_USES = {}      # key -> number of reuses
+RECYCLE_GRAD_RECORDS = os.environ.get("MOBGS_RECYCLE_GRAD_RECORDS", "1") != "0"
+
+
+def _take_grad_records(Kr, N, dev):
+    """an all-zero [Kr,N,16] gradient-record buffer (recycled when possible)"""
+    key = (int(Kr), int(N), dev.index)
+    t = _GRAD_REC_POOL.pop(key, None) if RECYCLE_GRAD_RECORDS else None
+    if t is not None:
+        _GRAD_REC_USES[key] = _GRAD_REC_USES.get(key, 0) + 1
+    if t is None:
+        t = torch.zeros(Kr, N, L.REC, device=dev)
+    if RECYCLE_GRAD_RECORDS:
+        if len(_GRAD_REC_OUT) > 16:
+            for ptr in [p for p, (_k, r) in _GRAD_REC_OUT.items() if r() is None]:
+                del _GRAD_REC_OUT[ptr]
+        _GRAD_REC_OUT[t.data_ptr()] = (key, weakref.ref(t))
+    return t
+
+
+def _recyclable(g_rec) -> bool:
+    """True if g_rec is a buffer of `_take_grad_records` (still the same live allocation): the projection backward may
+    zero it behind its reads; `_recycle` then returns it to the pool."""
+    ent = _GRAD_REC_OUT.get(g_rec.data_ptr())
+    if ent is None:
+        return False
+    key, ref = ent
+    orig = ref()
+    return (orig is not None and orig.data_ptr() == g_rec.data_ptr() and tuple(g_rec.shape) == (key[0], key[1], L.REC)
+            and g_rec.is_contiguous() and g_rec.device.index == key[2])
+
+
+def _recycle(g_rec):
+    key, _ = _GRAD_REC_OUT.pop(g_rec.data_ptr())
+    _GRAD_REC_POOL[key] = g_rec
+
 
 STATIC_KEYS = ("xyz", "rotation", "scaling", "opacity", "features_dc")
 DYNAMIC_KEYS = ("control_xyz", "rotation", "omega", "scaling", "opacity", "features_dc", "features_t",
@@ -97,6 +145,7 @@ class _SynthProject(torch.autograd.Function):
         K = viewmats.shape[0]
         dev = viewmats.device
         g_rec = _f32c(g_rec)
+        recycle = _recyclable(g_rec)          # our own buffer: zero it behind the reads and keep it for the next step
         # All Gaussian-parameter gradients are views into ONE zeroed flat buffer (segments padded to 16 B):
         # autograd adopts the views as `.grad`, so a data-parallel caller all-reduces the buffer in place
         # (dist.FlatGradients) instead of packing / unpacking 12 tensors.  control_xyz needs the zeros
@@ -109,8 +158,10 @@ class _SynthProject(torch.autograd.Function):
             # gradient buffer, no parameter-gradient stores
             if v_view is not None:
                 a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
-                               _p(t_poly), _p(radii), _p(g_rec), *([None] * 13), _p(v_view))
+                               _p(t_poly), _p(radii), _p(g_rec), *([None] * 13), _p(v_view), 0, 0, int(recycle))
                 L.call("mobgs_synth_project_bwd", a, _stream())
+                if recycle:
+                    _recycle(g_rec)
             return (v_view,) + (None,) * 21
         outs = list(st) + list(dy[:7])
         starts, tot = [], 0
@@ -123,21 +174,27 @@ class _SynthProject(torch.autograd.Function):
         sink = GRAD_SINK
         if sink is not None and off is None and sink.n_chunks > 1:
             if sink.n_chunks == 2:
-                _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, flat, starts, views, v_view)
+                _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, flat, starts, views, v_view,
+                                int(recycle))
             else:
-                _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view)
+                _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view,
+                                  int(recycle))
+            if recycle:
+                _recycle(g_rec)
             sink.reduced_storage = flat.untyped_storage().data_ptr()
             return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, None)
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
                        _p(t_poly), _p(radii), _p(g_rec),
                        _p(v_st[0]), _p(v_st[1]), _p(v_st[2]), _p(v_st[3]), _p(v_st[4]),
                        _p(v_dy[0]), _p(v_dy[1]), _p(v_dy[2]), _p(v_dy[3]), _p(v_dy[4]), _p(v_dy[5]),
-                       _p(v_dy[6]), _p(v_off), _p(v_view))
+                       _p(v_dy[6]), _p(v_off), _p(v_view), 0, 0, int(recycle))
         L.call("mobgs_synth_project_bwd", a, _stream())
+        if recycle:
+            _recycle(g_rec)
         return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, v_off)
 
 
-def _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, flat, starts, views, v_view):
+def _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, flat, starts, views, v_view, zero_rec=0):
     """GradSink with two ranges that need no repacking: the flat gradient buffer holds the 5 static tensors, then
     the 7 dynamic ones, so "all dynamic Gaussians" and "all static Gaussians" are each one contiguous slice of it.
     The dynamic range runs first; its all-reduce (59 % of the bytes at 700 k / 300 k) overlaps the static range's
@@ -153,7 +210,7 @@ def _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_
             continue
         ptr = [_p(v) for v in views]
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, None), _p(t_spline), _p(t_poly),
-                       _p(radii), _p(g_rec), *ptr[:5], *ptr[5:12], None, _p(v_view), lo, hi)
+                       _p(radii), _p(g_rec), *ptr[:5], *ptr[5:12], None, _p(v_view), lo, hi, zero_rec)
         L.call("mobgs_synth_project_bwd", a, stream)
         ev = torch.cuda.Event()
         ev.record(main)
@@ -169,7 +226,7 @@ def _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_
     flat.record_stream(sink.comm_stream)
 
 
-def _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view):
+def _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, outs, views, v_view, zero_rec=0):
     """see GradSink.  outs = the 12 parameter tensors (5 static, 7 dynamic), views = their gradient tensors."""
     dev = g_rec.device
     Ns, Nd = st[0].shape[0], dy[0].shape[0]
@@ -200,7 +257,7 @@ def _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, 
             ptr[t] = base_ptr + 4 * (o - lo * row[t])          # "row g of the full tensor" addressing
         g_lo, g_hi = (lo, hi) if kind == "s" else (Ns + lo, Ns + hi)
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, None), _p(t_spline), _p(t_poly),
-                       _p(radii), _p(g_rec), *ptr[:5], *ptr[5:12], None, _p(v_view), g_lo, g_hi)
+                       _p(radii), _p(g_rec), *ptr[:5], *ptr[5:12], None, _p(v_view), g_lo, g_hi, zero_rec)
         L.call("mobgs_synth_project_bwd", a, stream)
         ev = torch.cuda.Event()
         ev.record(main)
@@ -273,7 +330,7 @@ class _BlendRecords(torch.autograd.Function):
         dev = records.device
         g_c = _f32c(g_c) if g_c is not None else torch.zeros(K, height, width, D, device=dev)
         g_a = _f32c(g_a) if g_a is not None else None
-        v_rec = torch.zeros(Kr, N, L.REC, device=dev)
+        v_rec = _take_grad_records(Kr, N, dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
         a = L.BlendBwd(K, N, D, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
@@ -418,7 +475,7 @@ class _BlendDecode(torch.autograd.Function):
         g_depth = _f32c(g_depth) if g_depth is not None else None
         g_alpha = _f32c(g_alpha) if g_alpha is not None else None
         g_mean = _f32c(g_mean) if (g_mean is not None and g_mean.numel() > 0) else None
-        v_rec = torch.zeros(Kr, N, L.REC, device=dev)
+        v_rec = _take_grad_records(Kr, N, dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
         v_rays = v_pose = None
         if ctx.needs_input_grad[5]:
@@ -589,7 +646,7 @@ class _FlowRender(torch.autograd.Function):
         K, M, N, width, height, ray_intr = ctx.meta
         dev = records.device
         st = _stream()
-        v_rec = torch.zeros(K + 1, N, L.REC, device=dev)
+        v_rec = _take_grad_records(K + 1, N, dev)
         v_rays = v_pose = None
         if ctx.needs_input_grad[4]:
             if ray_intr is None:

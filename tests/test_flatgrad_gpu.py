@@ -82,3 +82,60 @@ def test_chunked_backward_with_gradient_sink_equals_plain_backward():
             # the order of which varies); what the split changes must stay at that rounding level
             assert (a - b).abs().max() <= 1e-5 * a.abs().max(), (tuple(p.shape), float((a - b).abs().max()))
         assert (v_plain - v_chunked).abs().max() <= 1e-5 * v_plain.abs().max()
+
+
+def test_recycled_gradient_records_give_identical_gradients():
+    """The gradient-record buffer is kept across steps and zeroed behind the projection backward's reads
+    (MobgsSynthBwd.zero_v_records): repeated steps — with a different view in between, so that the set of visible
+    Gaussians changes — must give bit-identical gradients with recycling on and off, and a caller-supplied gradient
+    tensor must never be modified."""
+    import torch
+    from mobgs_b200 import fused
+    from mobgs_b200.cameras import ray_pose_from_w2c
+    from mobgs_b200.scene import make_camera, subframe_w2c, synthetic_scene
+    from mobgs_b200.subframes import render_subframes
+    K, W, H = 3, 96, 64
+    sc, dc, intr = synthetic_scene(300, 200, W, H, seed=9, device="cuda")
+    params = [p for pc in (sc, dc) for p in pc.parameters() if p.requires_grad]
+    Kmat = make_camera(intr, subframe_w2c(0, K)).K.cuda()
+    t = torch.full((K,), 0.5).cuda()
+    bg = torch.zeros(3, device="cuda")
+    views = [torch.stack([subframe_w2c(k, K) for k in range(K)]).cuda(),
+             torch.stack([subframe_w2c(k, K) @ subframe_w2c(2, 3) for k in range(K)]).cuda()]
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(0)).cuda()
+
+    def run(view):
+        for p in params:
+            p.grad = None
+        rp = ray_pose_from_w2c(view, intr.fx, intr.fy, intr.cx, intr.cy, rigid=True)
+        out = render_subframes(sc, dc, view, Kmat, t, t, rp, bg, W, H)
+        ((out["render"] - tgt).abs().mean() + out["depth"].mean() * 0.1).backward()
+        return [None if p.grad is None else p.grad.clone() for p in params]
+
+    old = fused.RECYCLE_GRAD_RECORDS
+    try:
+        fused.RECYCLE_GRAD_RECORDS = False
+        ref = [run(views[i % 2]) for i in range(4)]
+        fused.RECYCLE_GRAD_RECORDS = True
+        fused._GRAD_REC_POOL.clear(); fused._GRAD_REC_OUT.clear()
+        got = [run(views[i % 2]) for i in range(4)]
+        assert len(fused._GRAD_REC_POOL) == 1, "the buffer must be back in the pool after a step"
+        pooled = next(iter(fused._GRAD_REC_POOL.values()))
+        assert float(pooled.abs().max()) == 0.0, "the recycled buffer must be all zero between steps"
+    finally:
+        fused.RECYCLE_GRAD_RECORDS = old
+    for step, (a, b) in enumerate(zip(got, ref)):
+        for x, y, p in zip(a, b, params):
+            assert (x is None) == (y is None)
+            if x is not None and x.numel():
+                # atomics make the scatter order nondeterministic: compare to rounding, not bit for bit
+                assert float((x - y).abs().max()) <= 1e-5 * (float(y.abs().max()) + 1e-12), (step, tuple(p.shape))
+    # a gradient tensor supplied by the caller is read-only
+    rec, radii, depths, _ = fused.synth_project(
+        (sc._xyz, sc._rotation, sc._scaling, sc._opacity, sc._features_dc),
+        (dc.control_xyz, dc._rotation, dc._omega, dc._scaling, dc._opacity, dc._features_dc, dc._features_t, dc._trbf_center),
+        dc.current_control_num, views[0], Kmat[None].expand(K, -1, -1), t, t, W, H)
+    g = torch.rand_like(rec)
+    g0 = g.clone()
+    rec.backward(g)
+    assert torch.equal(g, g0)
