@@ -15,7 +15,6 @@ namespace mobgs {
 
 constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
-constexpr int kSortSmemCap = 4096;   // keys per segment sorted entirely in shared memory
 constexpr int kRankSortMax = 768;    // segments up to this size use the O(n^2 / 256) rank sort
 
 struct TileRect { int x0, y0, x1, y1; };
@@ -264,59 +263,6 @@ __global__ void __launch_bounds__(256) tile_emit_kernel(const __grid_constant__ 
 // ------------------------------------------------------------------------------------------
 // one CTA sorts one (sub-frame, tile) segment
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void radix_pass(const uint64_t* src, uint64_t* dst, int n, int shift,
-                                           int (*warp_hist)[256], int* digit_base) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int chunk = (((n + kSortWarps - 1) / kSortWarps) + 31) & ~31;
-  const int beg = min(n, warp * chunk), end = min(n, beg + chunk);
-  int* hist = warp_hist[warp];
-  for (int d = lane; d < 256; d += 32) hist[d] = 0;
-  __syncwarp();
-  for (int i = beg; i < end; i += 32) {
-    const int idx = i + lane;
-    const bool valid = idx < end;
-    const int digit = valid ? (int)((src[idx] >> shift) & 0xff) : 256;
-    const unsigned peers = __match_any_sync(0xffffffffu, digit);
-    if (valid && lane == (__ffs(peers) - 1)) hist[digit] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-  {
-    // thread d owns digit d: exclusive scan over warps, then over digits
-    const int d = threadIdx.x;
-    int tot = 0;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) { const int c = warp_hist[w][d]; warp_hist[w][d] = tot; tot += c; }
-    int s = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-    if (lane == 31) digit_base[warp] = s;
-    __syncthreads();
-    int prev = 0;
-    for (int w = 0; w < warp; ++w) prev += digit_base[w];
-    const int base = prev + s - tot;
-#pragma unroll
-    for (int w = 0; w < kSortWarps; ++w) warp_hist[w][d] += base;
-  }
-  __syncthreads();
-  for (int i = beg; i < end; i += 32) {
-    const int idx = i + lane;
-    const bool valid = idx < end;
-    uint64_t key = 0;
-    int digit = 256;
-    if (valid) { key = src[idx]; digit = (int)((key >> shift) & 0xff); }
-    const unsigned peers = __match_any_sync(0xffffffffu, digit);
-    if (valid) {
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      dst[hist[digit] + rank] = key;
-    }
-    __syncwarp();
-    if (valid && lane == (__ffs(peers) - 1)) hist[digit] += __popc(peers);
-    __syncwarp();
-  }
-  __syncthreads();
-}
-
 // Small segments (n <= kRankSortMax, the common case): all-pairs rank sort out of 6 KB of static shared
 // memory — keys are unique (they embed the Gaussian index), so rank = #{keys smaller} is the final
 // position.  A kernel of its own so that its occupancy is not capped by the radix path's 72 KB buffers.
@@ -358,20 +304,14 @@ __global__ void __launch_bounds__(kSortThreads) tile_rank_sort_kernel(MobgsTileS
 #define MOBGS_RANK_SORT_BUCKETS 1
 #endif
 constexpr int kBuckets = 64;
-__global__ void __launch_bounds__(kSortThreads) tile_bucket_sort_kernel(MobgsTileSort a) {
-  __shared__ __align__(16) uint64_t buf[kRankSortMax];
-  __shared__ int hist[kBuckets], start[kBuckets + 1];
-  __shared__ uint32_t wmin[kSortWarps], wmax[kSortWarps];
-  const int seg = blockIdx.x;
-  const int beg = a.tile_offsets[seg];
-  int n = a.tile_offsets[seg + 1] - beg;
-  if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
-  if (n <= 0 || n > kRankSortMax) return;
-  const uint64_t* gkeys = a.keys + beg;
-  if (n == 1) {
-    if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(gkeys[0] & 0xffffffffu);
-    return;
-  }
+struct SmallSortSmem {
+  uint64_t buf[kRankSortMax];
+  int hist[kBuckets], start[kBuckets + 1];
+  uint32_t wmin[kSortWarps], wmax[kSortWarps];
+};
+
+// sorts gkeys[0, n), 2 <= n <= kRankSortMax, and writes the Gaussian indices to out[0, n); called by all threads of the CTA
+__device__ __forceinline__ void small_sort(SmallSortSmem& sm, const uint64_t* gkeys, int n, int32_t* out) {
   constexpr int kPer = (kRankSortMax + kSortThreads - 1) / kSortThreads;   // keys per thread (3)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t key[kPer];
@@ -382,16 +322,16 @@ __global__ void __launch_bounds__(kSortThreads) tile_bucket_sort_kernel(MobgsTil
     key[j] = i < n ? gkeys[i] : 0ull;
     if (i < n) { const uint32_t d = (uint32_t)(key[j] >> 32); lo = min(lo, d); hi = max(hi, d); }
   }
-  if (threadIdx.x < kBuckets) hist[threadIdx.x] = 0;
+  if (threadIdx.x < kBuckets) sm.hist[threadIdx.x] = 0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
     hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
   }
-  if (lane == 0) { wmin[warp] = lo; wmax[warp] = hi; }
+  if (lane == 0) { sm.wmin[warp] = lo; sm.wmax[warp] = hi; }
   __syncthreads();
 #pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) { lo = min(lo, wmin[w]); hi = max(hi, wmax[w]); }
+  for (int w = 0; w < kSortWarps; ++w) { lo = min(lo, sm.wmin[w]); hi = max(hi, sm.wmax[w]); }
   const uint32_t range = hi - lo;
   const int shift = range < (uint32_t)kBuckets ? 0 : (32 - __clz(range)) - 6;   // (range >> shift) < kBuckets = 2^6
   int slot[kPer], bkt[kPer];
@@ -399,99 +339,224 @@ __global__ void __launch_bounds__(kSortThreads) tile_bucket_sort_kernel(MobgsTil
   for (int j = 0; j < kPer; ++j) {
     const int i = threadIdx.x + j * kSortThreads;
     bkt[j] = (int)(((uint32_t)(key[j] >> 32) - lo) >> shift);
-    slot[j] = i < n ? atomicAdd(&hist[bkt[j]], 1) : 0;
+    slot[j] = i < n ? atomicAdd(&sm.hist[bkt[j]], 1) : 0;
   }
   __syncthreads();
   if (warp == 0) {          // exclusive scan over the 64 buckets, two per lane
-    const int c0 = hist[2 * lane], c1 = hist[2 * lane + 1];
+    const int c0 = sm.hist[2 * lane], c1 = sm.hist[2 * lane + 1];
     int s = c0 + c1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-    start[2 * lane] = s - c0 - c1;
-    start[2 * lane + 1] = s - c1;
-    if (lane == 31) start[kBuckets] = s;
+    sm.start[2 * lane] = s - c0 - c1;
+    sm.start[2 * lane + 1] = s - c1;
+    if (lane == 31) sm.start[kBuckets] = s;
   }
   __syncthreads();
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
     const int i = threadIdx.x + j * kSortThreads;
-    if (i < n) buf[start[bkt[j]] + slot[j]] = key[j];
+    if (i < n) sm.buf[sm.start[bkt[j]] + slot[j]] = key[j];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += kSortThreads) {
-    const uint64_t k = buf[i];
+    const uint64_t k = sm.buf[i];
     const int b = (int)(((uint32_t)(k >> 32) - lo) >> shift);
-    const int b0 = start[b], b1 = start[b + 1];
+    const int b0 = sm.start[b], b1 = sm.start[b + 1];
     int rank = b0;
-    for (int q = b0; q < b1; ++q) rank += buf[q] < k;
-    a.sorted_ids[beg + rank] = (int)(k & 0xffffffffu);
+    for (int q = b0; q < b1; ++q) rank += sm.buf[q] < k;
+    out[rank] = (int)(k & 0xffffffffu);
   }
+  __syncthreads();          // the buffers may be reused by the caller's next call
 }
 
-// Large segments (n > kRankSortMax, rare): LSD radix sort, one CTA per segment at a time.  The grid is a
-// few CTAs per SM; each scans 256 segment sizes at once and sorts the large ones it finds.
-__device__ void radix_sort_segment(const MobgsTileSort& a, int seg, uint64_t* bufA, uint64_t* bufB,
-                                   int (*warp_hist)[256], int* digit_base, unsigned long long* red_or,
-                                   unsigned long long* red_and) {
+__global__ void __launch_bounds__(kSortThreads) tile_bucket_sort_kernel(MobgsTileSort a) {
+  __shared__ __align__(16) SmallSortSmem sm;
+  const int seg = blockIdx.x;
   const int beg = a.tile_offsets[seg];
   int n = a.tile_offsets[seg + 1] - beg;
   if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
-  uint64_t* gkeys = a.keys + beg;
-  const bool in_smem = n <= kSortSmemCap;
-  uint64_t* src = in_smem ? bufA : gkeys;
-  uint64_t* dst = in_smem ? bufB : a.keys_tmp + beg;
-
-  unsigned long long vor = 0ull, vand = ~0ull;
-  for (int i = threadIdx.x; i < n; i += kSortThreads) {
-    const uint64_t key = gkeys[i];
-    if (in_smem) bufA[i] = key;
-    vor |= key; vand &= key;
+  if (n <= 0 || n > kRankSortMax) return;
+  if (n == 1) {
+    if (threadIdx.x == 0) a.sorted_ids[beg] = (int)(a.keys[beg] & 0xffffffffu);
+    return;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
-    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
-  }
-  if ((threadIdx.x & 31) == 0) { red_or[threadIdx.x >> 5] = vor; red_and[threadIdx.x >> 5] = vand; }
-  __syncthreads();
-  vor = 0ull; vand = ~0ull;
-#pragma unroll
-  for (int w = 0; w < kSortWarps; ++w) { vor |= red_or[w]; vand &= red_and[w]; }
-  const unsigned long long diff = vor ^ vand;
-
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = 8 * pass;
-    if (((diff >> shift) & 0xffull) == 0ull) continue;   // all keys share this digit
-    radix_pass(src, dst, n, shift, warp_hist, digit_base);
-    uint64_t* t = src; src = dst; dst = t;
-  }
-  for (int i = threadIdx.x; i < n; i += kSortThreads) a.sorted_ids[beg + i] = (int)(src[i] & 0xffffffffu);
+  small_sort(sm, a.keys + beg, n, a.sorted_ids + beg);
 }
 
-__global__ void __launch_bounds__(kSortThreads) tile_sort_kernel(MobgsTileSort a, int nt) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* bufA = reinterpret_cast<uint64_t*>(smem_raw);
-  uint64_t* bufB = bufA + kSortSmemCap;
-  int (*warp_hist)[256] = reinterpret_cast<int (*)[256]>(bufB + kSortSmemCap);
-  __shared__ int digit_base[kSortWarps];
-  __shared__ unsigned long long red_or[kSortWarps], red_and[kSortWarps];
-  __shared__ int big[kSortThreads];
-  __shared__ int nbig;
-  for (int c0 = blockIdx.x * kSortThreads; c0 < nt; c0 += gridDim.x * kSortThreads) {
-    if (threadIdx.x == 0) nbig = 0;
+// Large segments (n > kRankSortMax): MSD partition on the 64-bit key + small sorts.  A range is split into 256 (n <= 4096)
+// or 2048 buckets of (key - min) >> shift — monotone in the key, so the buckets are already in final order — by three
+// streaming passes (min / max, histogram, scatter into the other key buffer).  Keys in buckets of at most kDirectMax
+// entries then rank themselves inside their bucket straight from the partitioned array (a short loop of cached loads,
+// threads in bucket order); buckets up to kRankSortMax take the shared-memory small sort; larger ones (skewed depth
+// distributions) are pushed on a small stack and partitioned again with their own, narrower key range — keys are unique,
+// so every level strictly narrows the range and the recursion ends.  Persistent CTAs take segments from an atomic
+// counter.  (This replaced an LSD radix sort — 5-7 histogram / scatter passes per segment, ping-ponging through global
+// memory above 4096 keys — that took 39 ms on the heavy-footprint workload's 242 M entries.)
+constexpr int kMsdBucketsMax = 2048;
+constexpr int kDirectMax = 64;        // bucket sizes ranked directly from the partitioned array
+constexpr int kMsdStack = 256;        // pending ranges per CTA
+constexpr int kMsdListMax = 512;      // buckets of one partition that need their own sort
+
+struct MsdSmem {
+  SmallSortSmem small;
+  int hist[kMsdBucketsMax];
+  int start[kMsdBucketsMax + 1];
+  unsigned long long rmin[kSortWarps], rmax[kSortWarps];
+  int warp_tot[kSortWarps];
+  int stk_off[kMsdStack], stk_len[kMsdStack], stk_lvl[kMsdStack];
+  int big_list[kMsdListMax];
+  int stk_n, big_n, seg;
+};
+
+// all-pairs rank straight from global memory: O(m^2 / threads); only when the range stack is full
+__device__ __forceinline__ void slow_sort(const uint64_t* keys, int m, int32_t* out) {
+  for (int i = threadIdx.x; i < m; i += kSortThreads) {
+    const uint64_t k = keys[i];
+    int rank = 0;
+    for (int q = 0; q < m; ++q) rank += keys[q] < k;
+    out[rank] = (int)(k & 0xffffffffu);
+  }
+}
+
+// One partition step of the range [off, off + len) of a segment whose keys currently live in A (B = the other buffer;
+// both already offset to the segment's begin).  Called by all threads of the CTA.
+__device__ void msd_partition(MsdSmem& sm, const uint64_t* A, uint64_t* B, int32_t* out, int off, int len, int lvl) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nb_bits = len > 4096 ? 11 : 8, nb = 1 << nb_bits;
+  // 1. key range
+  unsigned long long lo = ~0ull, hi = 0ull;
+  for (int i = threadIdx.x; i < len; i += kSortThreads) { const unsigned long long k = A[off + i]; lo = min(lo, k); hi = max(hi, k); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { sm.rmin[warp] = lo; sm.rmax[warp] = hi; }
+  for (int b = threadIdx.x; b < nb; b += kSortThreads) sm.hist[b] = 0;
+  if (threadIdx.x == 0) sm.big_n = 0;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < kSortWarps; ++w) { lo = min(lo, sm.rmin[w]); hi = max(hi, sm.rmax[w]); }
+  const unsigned long long range = hi - lo;
+  if (range == 0ull) {
+    // cannot happen with real keys (they embed the Gaussian index, so they are unique); the unwritten keys of an
+    // overflowed speculative attempt can all be equal, and that attempt's lists only have to be harmless
+    for (int i = threadIdx.x; i < len; i += kSortThreads) out[off + i] = (int)(A[off + i] & 0xffffffffu);
     __syncthreads();
-    const int seg = c0 + threadIdx.x;
-    if (seg < nt) {
+    return;
+  }
+  const int bits = 64 - __clzll((long long)range);
+  const int shift = bits > nb_bits ? bits - nb_bits : 0;          // (range >> shift) < nb
+  // 2. histogram
+  for (int i = threadIdx.x; i < len; i += kSortThreads) atomicAdd(&sm.hist[(int)((A[off + i] - lo) >> shift)], 1);
+  __syncthreads();
+  // 3. exclusive scan over nb buckets (nb / 256 consecutive buckets per thread); large buckets go on big_list
+  {
+    const int per = nb / kSortThreads;                             // 1 or 8
+    const int b0 = threadIdx.x * per;
+    int sum = 0;
+    for (int j = 0; j < per; ++j) sum += sm.hist[b0 + j];
+    int sc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+    if (lane == 31) sm.warp_tot[warp] = sc;
+    __syncthreads();
+    int base = sc - sum;
+    for (int w = 0; w < warp; ++w) base += sm.warp_tot[w];
+    for (int j = 0; j < per; ++j) {
+      const int c = sm.hist[b0 + j];
+      sm.start[b0 + j] = base;
+      sm.hist[b0 + j] = 0;                                          // becomes the scatter cursor
+      if (c > kDirectMax) {
+        const int slot = atomicAdd(&sm.big_n, 1);
+        if (slot < kMsdListMax) sm.big_list[slot] = b0 + j;
+      }
+      base += c;
+    }
+    if (threadIdx.x == kSortThreads - 1) sm.start[nb] = base;
+  }
+  __syncthreads();
+  // 4. scatter into bucket order
+  for (int i = threadIdx.x; i < len; i += kSortThreads) {
+    const unsigned long long k = A[off + i];
+    const int b = (int)((k - lo) >> shift);
+    B[off + sm.start[b] + atomicAdd(&sm.hist[b], 1)] = k;
+  }
+  __syncthreads();
+  // 5. small buckets: every key ranks itself inside its bucket
+  for (int i = threadIdx.x; i < len; i += kSortThreads) {
+    const unsigned long long k = B[off + i];
+    const int b = (int)((k - lo) >> shift);
+    const int b0 = sm.start[b], b1 = sm.start[b + 1];
+    if (b1 - b0 > kDirectMax) continue;
+    int rank = b0;
+    for (int q = b0; q < b1; ++q) rank += B[off + q] < k;
+    out[off + rank] = (int)(k & 0xffffffffu);
+  }
+  // 6. the others: shared-memory small sort, or another partition level
+  const int big_n = sm.big_n;
+  const bool listed = big_n <= kMsdListMax;
+  const int n_iter = listed ? big_n : nb;                          // list overflow: look at every bucket
+  for (int it = 0; it < n_iter; ++it) {
+    const int b = listed ? sm.big_list[it] : it;
+    const int b0 = sm.start[b], m = sm.start[b + 1] - b0;
+    if (m <= kDirectMax) continue;
+    if (m <= kRankSortMax) {
+      small_sort(sm.small, B + off + b0, m, out + off + b0);
+    } else {
+      __syncthreads();
+      const int top = sm.stk_n;
+      __syncthreads();
+      if (top < kMsdStack) {
+        if (threadIdx.x == 0) { sm.stk_off[top] = off + b0; sm.stk_len[top] = m; sm.stk_lvl[top] = lvl + 1; sm.stk_n = top + 1; }
+      } else {
+        slow_sort(B + off + b0, m, out + off + b0);
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+}
+
+constexpr int kMsdChunk = 32;         // segments claimed per atomic: one warp looks at their sizes
+__global__ void __launch_bounds__(kSortThreads) tile_msd_sort_kernel(MobgsTileSort a, int nt) {
+  __shared__ __align__(16) MsdSmem sm;
+  __shared__ int chunk_big[kMsdChunk];
+  __shared__ int chunk_n;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) { sm.seg = atomicAdd(a.tile_cursor, kMsdChunk); chunk_n = 0; }    // counter zeroed by the launcher
+    __syncthreads();
+    const int c0 = sm.seg;
+    if (c0 >= nt) return;
+    if (threadIdx.x < kMsdChunk && c0 + threadIdx.x < nt) {
+      const int seg = c0 + threadIdx.x;
       const int beg = a.tile_offsets[seg];
       int n = a.tile_offsets[seg + 1] - beg;
       if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
-      if (n > kRankSortMax) big[atomicAdd(&nbig, 1)] = seg;
+      if (n > kRankSortMax) chunk_big[atomicAdd(&chunk_n, 1)] = seg;      // the others are tile_bucket_sort_kernel's
     }
     __syncthreads();
-    const int nb = nbig;
-    for (int b = 0; b < nb; ++b) {
-      radix_sort_segment(a, big[b], bufA, bufB, warp_hist, digit_base, red_or, red_and);
+    const int nbig = chunk_n;
+    for (int bi = 0; bi < nbig; ++bi) {
+      const int seg = chunk_big[bi];
+      const int beg = a.tile_offsets[seg];
+      int n = a.tile_offsets[seg + 1] - beg;
+      if ((int64_t)beg + n > a.capacity) n = (int)max((int64_t)0, a.capacity - beg);
       __syncthreads();
+      if (threadIdx.x == 0) { sm.stk_n = 1; sm.stk_off[0] = 0; sm.stk_len[0] = n; sm.stk_lvl[0] = 0; }
+      for (;;) {
+        __syncthreads();
+        const int top = sm.stk_n;
+        if (top == 0) break;
+        const int off = sm.stk_off[top - 1], len = sm.stk_len[top - 1], lvl = sm.stk_lvl[top - 1];
+        __syncthreads();
+        if (threadIdx.x == 0) sm.stk_n = top - 1;
+        __syncthreads();
+        uint64_t* A = ((lvl & 1) ? a.keys_tmp : a.keys) + beg;
+        uint64_t* B = ((lvl & 1) ? a.keys : a.keys_tmp) + beg;
+        msd_partition(sm, A, B, a.sorted_ids + beg, off, len, lvl);
+      }
     }
   }
 }
@@ -529,7 +594,7 @@ extern "C" int mobgs_tile_count(const MobgsTileCount* a, void* stream) {
 extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
   MOBGS_REQUIRE(a, "NULL args");
   MOBGS_REQUIRE(a->K >= 1 && a->K <= MOBGS_MAX_K && a->N >= 0 && a->width > 0 && a->height > 0, "bad extents");
-  MOBGS_REQUIRE(a->tile_offsets && (a->tile_cursor || a->entries), "NULL workspace");
+  MOBGS_REQUIRE(a->tile_offsets && a->tile_cursor, "NULL workspace");
   if (a->N == 0 || a->capacity == 0) return MOBGS_OK;
   MOBGS_REQUIRE(a->keys && a->keys_tmp && a->sorted_ids, "NULL pointer");
   cudaStream_t s = (cudaStream_t)stream;
@@ -546,20 +611,19 @@ extern "C" int mobgs_tile_emit_sort(const MobgsTileSort* a, void* stream) {
     const size_t total = (size_t)a->K * a->N;
     tile_emit_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(*a, tiles_x, tiles_y);
   }
-  const size_t smem = 2 * sizeof(uint64_t) * kSortSmemCap + sizeof(int) * kSortWarps * 256;
-  cudaFuncSetAttribute(tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #if MOBGS_RANK_SORT_BUCKETS
   tile_bucket_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);
 #else
   tile_rank_sort_kernel<<<nt, kSortThreads, 0, s>>>(*a);
 #endif
-  static int sort_ctas = 0;           // a few CTAs per SM (the radix buffers allow 3)
+  static int sort_ctas = 0;           // persistent CTAs for the large segments
   if (!sort_ctas) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    sort_ctas = 3 * sms;
+    sort_ctas = 4 * sms;
   }
-  tile_sort_kernel<<<min(sort_ctas, (nt + kSortThreads - 1) / kSortThreads), kSortThreads, smem, s>>>(*a, nt);
+  cudaMemsetAsync(a->tile_cursor, 0, sizeof(int), s);     // (the emit pass is done with it) segment counter of the MSD sort
+  tile_msd_sort_kernel<<<min(sort_ctas, nt), kSortThreads, 0, s>>>(*a, nt);
   return check_launch("tile_emit_sort");
 }

@@ -220,6 +220,42 @@ def test_speculative_list_capacity_overflow_is_redone_exactly():
     assert all(v > 7 for v in ops._CAP_CACHE.values())
 
 
+@pytest.mark.parametrize("n,dist", [(900, "uniform"), (5000, "uniform"), (40000, "uniform"), (40000, "clustered"),
+                                    (6000, "ties"), (300000, "clustered")])
+def test_large_segments_sort_exactly(n, dist):
+    """Segments above 768 entries take the MSD partition sort (256 / 2048 buckets, direct in-bucket ranking, small sorts,
+    recursion for skewed buckets): every tile's list must be exactly the (depth, index) order — for uniform depths,
+    for depths concentrated in a few narrow clusters (buckets that must be partitioned again), and for thousands of
+    exactly equal depths (the index half of the key decides)."""
+    from mobgs_b200 import ops
+    W, H = 32, 32                                  # 4 tiles, every Gaussian reaches all of them
+    g = torch.Generator().manual_seed(n)
+    if dist == "uniform":
+        dep = 1 + 9 * torch.rand(n, generator=g)
+    elif dist == "clustered":
+        centre = torch.tensor([2.0, 2.00001, 7.5])[torch.randint(0, 3, (n,), generator=g)]
+        dep = centre * (1 + 1e-6 * torch.randn(n, generator=g))
+        dep[: n // 10] = 1 + 9 * torch.rand(n // 10, generator=g)
+    else:
+        dep = 1 + 9 * torch.rand(n, generator=g)
+        dep[: 4000] = 3.25                         # one bucket of 4000 identical depths
+        dep[4000:5000] = dep[5000:6000]
+    rec = torch.zeros(1, n, 16)
+    rec[0, :, 0] = 16 + 8 * torch.rand(n, generator=g)
+    rec[0, :, 1] = 16 + 8 * torch.rand(n, generator=g)
+    rec[0, :, 2] = 0.9
+    rec[0, :, 3] = rec[0, :, 5] = 1e-4              # conic: a footprint of hundreds of pixels
+    radii = torch.full((1, n), 300, dtype=torch.int32)
+    lists = ops.build_tile_lists(rec.cuda(), radii.cuda(), dep[None].cuda().contiguous(), W, H, tight=True)
+    off = lists.tile_offsets.cpu().numpy()
+    assert list(off) == [0, n, 2 * n, 3 * n, 4 * n]
+    d = dep.numpy()
+    want = np.lexsort((np.arange(n), d)).astype(np.int32)
+    ids = lists.sorted_ids.cpu().numpy()
+    for t in range(4):
+        assert np.array_equal(ids[off[t]:off[t + 1]], want), (dist, t)
+
+
 @pytest.mark.parametrize("tight", [False, True])
 @pytest.mark.parametrize("n,W,H,big", [(3000, 150, 100, False), (400, 272, 208, True), (1, 48, 48, False), (5000, 64, 48, False)])
 def test_recorded_entries_give_identical_lists(n, W, H, big, tight):

@@ -1,0 +1,7 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/o_pytest.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/o_pytest.log
+for w in c4_1M_1080p_K7 c4L_1M_1080p_K7 sb_150k_512x288_K9; do
+timeout 300 python bench.py --steps 20 --warmup 5 --no-extras --no-cpu-baseline --workload $w 2> gpurun_out/o_$w.err | tee gpurun_out/o_$w.json | python tools/show_bench.py | sed -n 1,2p
+done
