@@ -813,6 +813,11 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_k
 #ifndef MOBGS_BWD_UNIT_MOMENTS
 #define MOBGS_BWD_UNIT_MOMENTS 1
 #endif
+// 1: L2 prefetch of the list tail's records before the prologue (see blend_bwd_tr_kernel).  Measured 0.5 % SLOWER
+// (2.972 vs 2.957 ms): the staging latency is already covered by the other three CTAs of the SM; kept as a switch.
+#ifndef MOBGS_BWD_PREFETCH
+#define MOBGS_BWD_PREFETCH 0
+#endif
 constexpr int kBwdBatch = MOBGS_BWD_DIRECT_RED ? 192 : 128;   // list entries staged per batch (shared-memory budget)
 constexpr int kDummySlot = kBwdBatch;          // staged row of the dummy record (MOBGS_BWD_LEAN_A)
 constexpr int kRecRow = 20;                    // floats between staged records (16 used): the rows of 8 different
@@ -875,6 +880,19 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   float* v_recs = a.v_records + (size_t)a.lists.rec_k[k] * a.N * kRecFloats;
   const float4* recs_ref = FLOW ? reinterpret_cast<const float4*>(a.records) + (size_t)a.flow_ref * a.N * 4 : nullptr;
   float* v_recs_ref = FLOW ? a.v_records + (size_t)a.flow_ref * a.N * kRecFloats : nullptr;
+#if MOBGS_BWD_PREFETCH
+  // The records of the first batch are staged only after the per-pixel prologue (they alias its scratch).  Pull the
+  // list tail's records towards L2 now, so that the staging copies hit L2 instead of waiting on DRAM: the tail is
+  // where the walk starts whenever some pixel of the tile blended the whole list (the usual case).
+  {
+    const int endl = min(a.tile_offsets[tile_segment(a.lists, k, tiles, tile) + 1], (int)min(a.list_capacity, (int64_t)0x7fffffff));
+    const int pf = endl - 1 - tid;
+    if (tid < kBwdBatch && pf >= beg) {
+      const int g = list_gid(a.sorted_ids, pf, a.N);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(recs + (size_t)g * 4));
+    }
+  }
+#endif
 
   float T_final, v_a, bg_dot = 0.f;
   float v_c[D];
