@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
       for (int c = 0; c < 10; ++c) v[c] = pix[c % D];
       if (POSE) {                  // the ray of this pixel from 12 pose floats: no [.,6,H,W] image is read
         const RayIntr in = {a.dec_ppx, a.dec_ppy, a.dec_sfx, a.dec_sfy};
-        pixel_ray(sdec + (POSE ? 96 : 0), in, ix, iy, rays);
+        pixel_ray<true>(sdec + (POSE ? 96 : 0), in, ix, iy, rays);
       } else {
         const int rk = a.dec_rays_per_k == 2 ? a.lists.rec_k[k] : (a.dec_rays_per_k ? k : 0);
         const float* rp = a.dec_rays + (size_t)rk * 6 * P + pp;
@@ -457,7 +457,7 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
         depth_acc = t4.y;
         if (POSE) {
           float r6[6];
-          pixel_ray(sdec + (POSE ? 96 : 0), rin, ix, iy, r6);
+          pixel_ray<true>(sdec + (POSE ? 96 : 0), rin, ix, iy, r6);
 #pragma unroll
           for (int i = 0; i < 6; ++i) x[6 + i] = r6[i];
         } else {
@@ -522,7 +522,7 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
       // pose gradient (what mobgs_camera_rays_bwd reduces from a [.,6,H,W] image): 12 sums over the tile's pixels,
       // warp shuffles -> CTA accumulator swg[96..107] -> one atomicAdd per CTA and value (after the barrier below)
       float v12[12];
-      pixel_ray_vjp(sdec + (POSE ? 96 : 0), rin, ix, iy, gray, v12);
+      pixel_ray_vjp<true>(sdec + (POSE ? 96 : 0), rin, ix, iy, gray, v12);
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
         const float sum = warp_sum(v12[i]);

@@ -21,10 +21,20 @@ __device__ __forceinline__ RayCam load_ray_cam(const float* rot, const float* ce
   return m;
 }
 
+// FAST = false: IEEE sqrt / divisions, the arithmetic of camera_rays.cu (pinned to the reference's torch ops);
+// FAST = true (the in-register rays of the blend kernels): one MUFU.RSQ per normalisation and a multiplication by the
+// reciprocal scale factors — 2^-22 relative error per component, ~20 instead of ~60 instructions per pixel.
+template <bool FAST = false>
 __device__ __forceinline__ void ray_local_dir(const RayIntr& in, int x, int y, float (&l)[3]) {
-  const float lx = ((float)x + 0.5f - in.ppx) / in.sfx, ly = ((float)y + 0.5f - in.ppy) / in.sfy;
-  const float n = sqrtf(lx * lx + ly * ly + 1.f);
-  l[0] = lx / n; l[1] = ly / n; l[2] = 1.f / n;
+  if (FAST) {
+    const float lx = ((float)x + 0.5f - in.ppx) * __frcp_rn(in.sfx), ly = ((float)y + 0.5f - in.ppy) * __frcp_rn(in.sfy);
+    const float rn = rsqrtf(lx * lx + ly * ly + 1.f);
+    l[0] = lx * rn; l[1] = ly * rn; l[2] = rn;
+  } else {
+    const float lx = ((float)x + 0.5f - in.ppx) / in.sfx, ly = ((float)y + 0.5f - in.ppy) / in.sfy;
+    const float n = sqrtf(lx * lx + ly * ly + 1.f);
+    l[0] = lx / n; l[1] = ly / n; l[2] = 1.f / n;
+  }
 }
 
 // world direction before normalisation
@@ -35,22 +45,27 @@ __device__ __forceinline__ void ray_rotate(const float* r, const float (&l)[3], 
 }
 
 // pose = R (9, row-major) | c (3); rays[6] = [c | d]
+template <bool FAST = false>
 __device__ __forceinline__ void pixel_ray(const float* pose, const RayIntr& in, int x, int y, float (&rays)[6]) {
   float l[3], w[3];
-  ray_local_dir(in, x, y, l);
+  ray_local_dir<FAST>(in, x, y, l);
   ray_rotate(pose, l, w);
-  const float n = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const float n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const float inv_n = FAST ? rsqrtf(n2) : 1.f / sqrtf(n2);
   rays[0] = pose[9]; rays[1] = pose[10]; rays[2] = pose[11];
-  rays[3] = w[0] / n; rays[4] = w[1] / n; rays[5] = w[2] / n;
+  if (FAST) { rays[3] = w[0] * inv_n; rays[4] = w[1] * inv_n; rays[5] = w[2] * inv_n; }
+  else { const float n = sqrtf(n2); rays[3] = w[0] / n; rays[4] = w[1] / n; rays[5] = w[2] / n; }
 }
 
 // VJP of pixel_ray: g[6] = d loss / d rays -> the 12 pose-gradient terms of this pixel (v[0..8] = d R, v[9..11] = d c)
+template <bool FAST = false>
 __device__ __forceinline__ void pixel_ray_vjp(const float* pose, const RayIntr& in, int x, int y, const float (&g)[6],
                                               float (&v)[12]) {
   float l[3], w[3];
-  ray_local_dir(in, x, y, l);
+  ray_local_dir<FAST>(in, x, y, l);
   ray_rotate(pose, l, w);
-  const float inv_n = 1.f / sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const float n2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const float inv_n = FAST ? rsqrtf(n2) : 1.f / sqrtf(n2);
   const float dx = w[0] * inv_n, dy = w[1] * inv_n, dz = w[2] * inv_n;
   const float dot = dx * g[3] + dy * g[4] + dz * g[5];
   const float vx = (g[3] - dx * dot) * inv_n, vy = (g[4] - dy * dot) * inv_n, vz = (g[5] - dz * dot) * inv_n;   // d/dw of w/|w|
