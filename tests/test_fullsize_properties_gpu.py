@@ -54,6 +54,38 @@ def test_tile_lists_sorted_and_counted_at_full_size(scene):
             assert lists.n_isect < n_aabb       # pruning removed something, never added
 
 
+def test_recorded_entries_binning_equals_two_pass_at_full_size(scene):
+    """The steady-state binning (counting pass records its intersections, streaming scatter) against the two-pass
+    count / emit kernels on the 1 M / 1080p scene: identical offsets and identical (depth, index)-sorted lists; and
+    with the heavy-footprint scales, where most segments take the MSD partition sort instead of the bucket sort."""
+    from mobgs_b200 import ops
+    rec, radii, depths, _ = _project(scene)
+    keep = lambda tl: tl.sorted_ids.clone()
+    for variant in ("benchmark footprint", "large footprint"):
+        if variant == "large footprint":
+            rec = rec.clone()
+            rec[..., 3:6] *= 1.0 / 64.0               # conics / 64 = footprints x 8: thousands of entries per tile
+            radii = torch.where(radii > 0, radii * 8, radii)
+        ops._CAP_CACHE.clear()
+        ref, ref_ids = ops.build_tile_lists(rec, radii, depths, W, H, tight=True, consume=keep)        # two-pass
+        got, got_ids = ops.build_tile_lists(rec, radii, depths, W, H, tight=True, consume=keep)        # recorded entries
+        assert got.n_isect == ref.n_isect
+        assert torch.equal(got.tile_offsets, ref.tile_offsets)
+        assert torch.equal(got_ids[: ref.n_isect], ref_ids[: ref.n_isect]), variant
+        per_tile = (ref.tile_offsets[1:] - ref.tile_offsets[:-1])
+        if variant == "large footprint":
+            assert int(per_tile.max()) > 4096, "the large-segment sort was not exercised"
+        # sortedness by (depth, index) inside every segment
+        off = ref.tile_offsets.long()
+        ids = ref_ids[: ref.n_isect].long()
+        tiles = math.ceil(W / 16) * math.ceil(H / 16)
+        seg = torch.repeat_interleave(torch.arange(off.numel() - 1, device="cuda"), off[1:] - off[:-1])
+        d = depths.reshape(-1)[(seg // tiles) * (NS + ND) + ids]
+        same = seg[1:] == seg[:-1]
+        ok = (d[1:] > d[:-1]) | ((d[1:] == d[:-1]) & (ids[1:] > ids[:-1]))
+        assert bool((ok | ~same).all()), variant
+
+
 def test_exact_pruning_and_k_batching_do_not_change_the_image(scene):
     from mobgs_b200 import fused
     rec, radii, depths, _ = _project(scene)
