@@ -95,6 +95,23 @@ typedef struct {
 } MobgsProjectBwd;
 int mobgs_project_bwd(const MobgsProjectBwd* a, void* stream);
 
+/* A launch of the binning / blend kernels renders K *lists*.  List k takes its Gaussians from
+ * record set rec_k[k] (a sub-frame of the projection launch) restricted to the index range
+ * [g_begin[k], g_end[k]).  Identity (rec_k[k] = k, full range) is the plain K-sub-frame render;
+ * {(0, 0..N), (0, Ns..N), (0, 0..Ns)} renders the combined / dynamic-only / static-only images
+ * of render() (gaussian_renderer/__init__.py:143,201,236) from ONE projection in ONE launch. */
+#define MOBGS_MAX_K 32
+typedef struct {
+  int32_t rec_k[MOBGS_MAX_K];
+  int32_t g_begin[MOBGS_MAX_K];
+  int32_t g_end[MOBGS_MAX_K];
+  /* Blend kernels only: list k walks the tile lists that binning produced for its list
+   * tile_list[k] (identity = k).  Lists with the same geometry and index range but different
+   * colour payloads (the mid-time flow renders of get_flow, gaussian_renderer/__init__.py:456)
+   * are binned and sorted ONCE and share the result.  The binning entry points ignore it. */
+  int32_t tile_list[MOBGS_MAX_K];
+} MobgsLists;
+
 /* ------------------------------------------------------------------------------------------
  * Fused MoBGS attribute synthesis + projection for K latent sub-frames (SURVEY.md §8 a1+a2+a4):
  *   static set  : GaussianModel getters scene/gaussian_model.py:209-257 (xyz, exp(scaling),
@@ -139,6 +156,17 @@ typedef struct {
   int32_t* radii;          /* [K,N] */
   float* depths;           /* [K,N] */
   float* means3d;          /* [K,N,3] or NULL */
+  /* Optional fused counting pass (bin_tile_counts != NULL): what mobgs_tile_count does for the bin_n_lists lists
+   * `bin_lists` over this launch's record sets — per-tile counters and, with bin_entries, the recorded
+   * (segment, slot, index, depth) entries — done here, while the projected Gaussian is still in registers, instead of
+   * by a second kernel that re-reads records / radii / depths.  bin_tile_counts [bin_n_lists * T] and
+   * bin_entry_cursor [1] are zeroed inside; afterwards call mobgs_tile_count with counts_ready = 1 (prefix sum only). */
+  int32_t bin_n_lists, bin_tight;
+  MobgsLists bin_lists;
+  int32_t* bin_tile_counts;
+  void* bin_entries;
+  int64_t bin_entry_capacity;
+  int32_t* bin_entry_cursor;
 } MobgsSynthFwd;
 int mobgs_synth_project_fwd(const MobgsSynthFwd* a, void* stream);
 
@@ -187,22 +215,6 @@ typedef struct {
 } MobgsPack;
 int mobgs_pack_records(const MobgsPack* a, void* stream);
 
-/* A launch of the binning / blend kernels renders K *lists*.  List k takes its Gaussians from
- * record set rec_k[k] (a sub-frame of the projection launch) restricted to the index range
- * [g_begin[k], g_end[k]).  Identity (rec_k[k] = k, full range) is the plain K-sub-frame render;
- * {(0, 0..N), (0, Ns..N), (0, 0..Ns)} renders the combined / dynamic-only / static-only images
- * of render() (gaussian_renderer/__init__.py:143,201,236) from ONE projection in ONE launch. */
-#define MOBGS_MAX_K 32
-typedef struct {
-  int32_t rec_k[MOBGS_MAX_K];
-  int32_t g_begin[MOBGS_MAX_K];
-  int32_t g_end[MOBGS_MAX_K];
-  /* Blend kernels only: list k walks the tile lists that binning produced for its list
-   * tile_list[k] (identity = k).  Lists with the same geometry and index range but different
-   * colour payloads (the mid-time flow renders of get_flow, gaussian_renderer/__init__.py:456)
-   * are binned and sorted ONCE and share the result.  The binning entry points ignore it. */
-  int32_t tile_list[MOBGS_MAX_K];
-} MobgsLists;
 
 /* ------------------------------------------------------------------------------------------
  * Tile binning + per-tile depth sort (gsplat isect_tiles + radix sort + isect_offset_encode,
@@ -233,6 +245,9 @@ typedef struct {
   void* entries;
   int64_t entry_capacity;
   int32_t* entry_cursor;
+  /* != 0: tile_counts (and the entries) were already produced by mobgs_synth_project_fwd's fused counting pass
+   * (MobgsSynthFwd.bin_tile_counts): only the prefix sum runs. */
+  int32_t counts_ready;
 } MobgsTileCount;
 int mobgs_tile_count(const MobgsTileCount* a, void* stream);
 

@@ -91,10 +91,30 @@ class DynamicParams(C.Structure):
                 ("features_t", C.c_void_p), ("trbf_center", C.c_void_p), ("offset", C.c_void_p)]
 
 
+class Lists(C.Structure):
+    _fields_ = [("rec_k", C.c_int32 * MAX_K), ("g_begin", C.c_int32 * MAX_K), ("g_end", C.c_int32 * MAX_K),
+                ("tile_list", C.c_int32 * MAX_K)]
+
+
+def make_lists(specs, tile_list=None):
+    """specs: [(record_set, g_begin, g_end)] per list; tile_list[k] = index of the binned tile lists list k
+    walks (default identity)."""
+    if len(specs) > MAX_K:
+        raise RuntimeError(f"at most {MAX_K} lists per launch, got {len(specs)}")
+    l = Lists()
+    for i, (rk, g0, g1) in enumerate(specs):
+        l.rec_k[i], l.g_begin[i], l.g_end[i] = int(rk), int(g0), int(g1)
+        l.tile_list[i] = i if tile_list is None else int(tile_list[i])
+    return l
+
+
 class SynthFwd(C.Structure):
     _fields_ = [("cams", Cameras), ("st", StaticParams), ("dy", DynamicParams),
                 ("t_spline", C.c_void_p), ("t_poly", C.c_void_p), ("records", C.c_void_p),
-                ("radii", C.c_void_p), ("depths", C.c_void_p), ("means3d", C.c_void_p)]
+                ("radii", C.c_void_p), ("depths", C.c_void_p), ("means3d", C.c_void_p),
+                ("bin_n_lists", C.c_int32), ("bin_tight", C.c_int32), ("bin_lists", Lists),
+                ("bin_tile_counts", C.c_void_p), ("bin_entries", C.c_void_p), ("bin_entry_capacity", C.c_int64),
+                ("bin_entry_cursor", C.c_void_p)]
 
 
 class SynthBwd(C.Structure):
@@ -116,30 +136,13 @@ class Pack(C.Structure):
                 ("colors_per_cam", C.c_int32), ("depths", C.c_void_p), ("records", C.c_void_p)]
 
 
-class Lists(C.Structure):
-    _fields_ = [("rec_k", C.c_int32 * MAX_K), ("g_begin", C.c_int32 * MAX_K), ("g_end", C.c_int32 * MAX_K),
-                ("tile_list", C.c_int32 * MAX_K)]
-
-
-def make_lists(specs, tile_list=None):
-    """specs: [(record_set, g_begin, g_end)] per list; tile_list[k] = index of the binned tile lists list k
-    walks (default identity)."""
-    if len(specs) > MAX_K:
-        raise RuntimeError(f"at most {MAX_K} lists per launch, got {len(specs)}")
-    l = Lists()
-    for i, (rk, g0, g1) in enumerate(specs):
-        l.rec_k[i], l.g_begin[i], l.g_end[i] = int(rk), int(g0), int(g1)
-        l.tile_list[i] = i if tile_list is None else int(tile_list[i])
-    return l
-
-
 class TileCount(C.Structure):
     _fields_ = [("K", C.c_int32), ("N", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
                 ("records", C.c_void_p), ("radii", C.c_void_p), ("tight", C.c_int32),
                 ("lists", Lists),
                 ("tile_counts", C.c_void_p), ("tile_offsets", C.c_void_p),
                 ("depths", C.c_void_p), ("entries", C.c_void_p), ("entry_capacity", C.c_int64),
-                ("entry_cursor", C.c_void_p)]
+                ("entry_cursor", C.c_void_p), ("counts_ready", C.c_int32)]
 
 
 class TileSort(C.Structure):

@@ -6,6 +6,7 @@
 // except the 12-float view-matrix gradient (one warp-reduced atomicAdd per warp and sub-frame).
 // HBM-bound; see DESIGN.md for the byte model.
 #include "common.cuh"
+#include "tile_bin.cuh"
 
 namespace mobgs {
 
@@ -184,7 +185,19 @@ __device__ __forceinline__ void load_dyn(const MobgsDynamicParams& d, int j, Dyn
   r.n_ctrl = n;
 }
 
-__global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSynthFwd a) {
+// Fused counting pass (MobgsSynthFwd.bin_tile_counts): the lists that read record set k take this Gaussian while its
+// projection is still in registers.  The loop over the lists is warp-uniform (k and the list table are); a lane whose
+// Gaussian is outside the list's range or culled takes part with live = false (bin_count_record reserves per warp).
+__device__ __forceinline__ void synth_bin(const MobgsSynthFwd& a, const BinTarget& bt, int k, int g, const ProjOut& o, float opac) {
+  const GaussGeom geo = {o.mx, o.my, opac, o.ca, o.cb, o.cc};
+  for (int l = 0; l < a.bin_n_lists; ++l) {
+    if (a.bin_lists.rec_k[l] != k) continue;
+    const bool live = o.radius > 0 && g >= a.bin_lists.g_begin[l] && g < a.bin_lists.g_end[l];
+    bin_count_record(bt, l, g, live, geo, o.radius, o.depth);
+  }
+}
+
+__global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(const __grid_constant__ MobgsSynthFwd a) {
   __shared__ CamSmem sm;
   load_cams(sm, a.cams, a.t_spline, a.t_poly);
   const int N = a.st.Ns + a.dy.Nd;
@@ -192,6 +205,10 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSy
   if (g >= N) return;
   const ProjCfg cfg = make_cfg(a.cams);
   const int K = a.cams.K;
+  const bool binning = a.bin_tile_counts != nullptr;
+  const int tiles_x = (a.cams.width + kTile - 1) / kTile, tiles_y = (a.cams.height + kTile - 1) / kTile;
+  const BinTarget bt = {a.bin_tile_counts, a.bin_entries, a.bin_entry_capacity, a.bin_entry_cursor,
+                        a.cams.width, a.cams.height, tiles_x, tiles_y, a.bin_tight};
   if (g < a.st.Ns) {
     float p[3], q[4], s[3], col[10];
 #pragma unroll
@@ -211,6 +228,7 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSy
       a.radii[i] = o.radius;
       a.depths[i] = o.depth;
       if (a.means3d) { a.means3d[3 * i] = p[0]; a.means3d[3 * i + 1] = p[1]; a.means3d[3 * i + 2] = p[2]; }
+      if (binning) synth_bin(a, bt, k, g, o, opac);
     }
   } else {
     const int j = g - a.st.Ns;
@@ -244,6 +262,7 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(MobgsSy
       a.radii[i] = o.radius;
       a.depths[i] = o.depth;
       if (a.means3d) { a.means3d[3 * i] = p[0]; a.means3d[3 * i + 1] = p[1]; a.means3d[3 * i + 2] = p[2]; }
+      if (binning) synth_bin(a, bt, k, g, o, r.opac);
     }
   }
 }
@@ -473,6 +492,13 @@ extern "C" int mobgs_synth_project_fwd(const MobgsSynthFwd* a, void* stream) {
   if (N == 0) return MOBGS_OK;
   MOBGS_REQUIRE(a->records && a->radii && a->depths, "outputs must not be NULL");
   MOBGS_REQUIRE(a->dy.Nd == 0 || (a->t_spline && a->t_poly), "t_spline / t_poly must not be NULL");
+  if (a->bin_tile_counts) {
+    MOBGS_REQUIRE(a->bin_n_lists >= 1 && a->bin_n_lists <= MOBGS_MAX_K, "bin_n_lists=%d out of range", a->bin_n_lists);
+    MOBGS_REQUIRE(!a->bin_entries || (a->bin_entry_cursor && a->bin_entry_capacity >= 0), "bin_entries need a cursor and a capacity");
+    const int tiles = ((a->cams.width + kTile - 1) / kTile) * ((a->cams.height + kTile - 1) / kTile);
+    cudaMemsetAsync(a->bin_tile_counts, 0, sizeof(int) * (size_t)a->bin_n_lists * tiles, (cudaStream_t)stream);
+    if (a->bin_entry_cursor) cudaMemsetAsync(a->bin_entry_cursor, 0, sizeof(int), (cudaStream_t)stream);
+  }
   const int grid = (N + kProjThreads - 1) / kProjThreads;
   synth_project_fwd_kernel<<<grid, kProjThreads, 0, (cudaStream_t)stream>>>(*a);
   return check_launch("synth_project_fwd");

@@ -110,7 +110,7 @@ class _SynthProject(torch.autograd.Function):
     @staticmethod
     def forward(ctx, viewmats, Ks, t_spline, t_poly, control_num, width, height, want_means3d,
                 s_xyz, s_rot, s_sc, s_op, s_fdc,
-                d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf, d_off):
+                d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf, d_off, binning=None):
         st = [_f32c(t) for t in (s_xyz, s_rot, s_sc, s_op, s_fdc)]
         dy = [_f32c(t) for t in (d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf)]
         viewmats, Ks = _f32c(viewmats), _f32c(Ks)
@@ -126,8 +126,15 @@ class _SynthProject(torch.autograd.Function):
         depths = torch.empty(K, N, device=dev)
         means3d = torch.empty(K, N, 3, device=dev) if want_means3d else None
         cams = _cams(viewmats, Ks, width, height)
+        # fused counting pass (ops.BinPlan): the lists the blend will walk are counted / recorded by this launch
+        bin_args = ()
+        if binning is not None and (binning.width, binning.height) == (width, height):
+            prep = binning.prepare(N, dev)
+            if prep is not None:
+                lists, counts, entries, cursor = prep
+                bin_args = (len(binning.specs), int(binning.tight), lists, _p(counts), _p(entries), entries.shape[0], _p(cursor))
         a = L.SynthFwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
-                       _p(t_poly), _p(records), _p(radii), _p(depths), _p(means3d))
+                       _p(t_poly), _p(records), _p(radii), _p(depths), _p(means3d), *bin_args)
         L.call("mobgs_synth_project_fwd", a, _stream())
         ctx.save_for_backward(viewmats, Ks, t_spline, t_poly, control_num, radii, off, *st, *dy)
         ctx.size = (width, height)
@@ -162,7 +169,7 @@ class _SynthProject(torch.autograd.Function):
                 L.call("mobgs_synth_project_bwd", a, _stream())
                 if recycle:
                     _recycle(g_rec)
-            return (v_view,) + (None,) * 21
+            return (v_view,) + (None,) * 22
         outs = list(st) + list(dy[:7])
         starts, tot = [], 0
         for t in outs:
@@ -182,7 +189,7 @@ class _SynthProject(torch.autograd.Function):
             if recycle:
                 _recycle(g_rec)
             sink.reduced_storage = flat.untyped_storage().data_ptr()
-            return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, None)
+            return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, None, None)
         a = L.SynthBwd(cams, _static_struct(st), _dynamic_struct(dy, control_num, off), _p(t_spline),
                        _p(t_poly), _p(radii), _p(g_rec),
                        _p(v_st[0]), _p(v_st[1]), _p(v_st[2]), _p(v_st[3]), _p(v_st[4]),
@@ -191,7 +198,7 @@ class _SynthProject(torch.autograd.Function):
         L.call("mobgs_synth_project_bwd", a, _stream())
         if recycle:
             _recycle(g_rec)
-        return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, v_off)
+        return (v_view, None, None, None, None, None, None, None, *v_st, *v_dy[:7], None, v_off, None)
 
 
 def _split_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, g_rec, flat, starts, views, v_view, zero_rec=0):
@@ -287,13 +294,14 @@ def _chunked_backward(sink, cams, st, dy, control_num, t_spline, t_poly, radii, 
 
 
 def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_spline, t_poly,
-                  width, height, offset=None, want_means3d=False):
+                  width, height, offset=None, want_means3d=False, binning=None):
     """static_params: (xyz[Ns,3], rotation[Ns,4], scaling[Ns,3], opacity[Ns(,1)], features_dc[Ns,6]);
     dynamic_params: (control_xyz[Nd,P,3], rotation, omega, scaling, opacity, features_dc,
     features_t[Nd,3], trbf_center[Nd(,1)]); control_num int64 [Nd(,1)].
+    binning: optional ops.BinPlan — the tile-counting pass of the lists it names is fused into this launch.
     -> records [K,N,16], radii i32 [K,N], depths [K,N], means3d [K,N,3] or empty."""
     return _SynthProject.apply(viewmats, Ks, t_spline, t_poly, control_num, int(width), int(height),
-                               bool(want_means3d), *static_params, *dynamic_params, offset)
+                               bool(want_means3d), *static_params, *dynamic_params, offset, binning)
 
 
 class _BlendRecords(torch.autograd.Function):
@@ -410,7 +418,7 @@ class _BlendDecode(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
-                vsp_list, want_mean, mean_K=0, flow_ref=-1, ray_intr=None):
+                vsp_list, want_mean, mean_K=0, flow_ref=-1, ray_intr=None, plan=None):
         records = _f32c(records)
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
@@ -446,7 +454,7 @@ class _BlendDecode(torch.autograd.Function):
             return img10, alpha, last, rgb, depth, flow
 
         lists, (img10, alpha, last, rgb, depth, flow) = build_tile_lists(records, radii, depths, width, height, tight,
-                                                                         specs, consume=blend)
+                                                                         specs, consume=blend, plan=plan)
         if want_mean:
             mean = torch.empty(3, height, width, device=dev)
             L.subframe_mean(_p(rgb), _p(mean), mK, 3 * height * width, _stream())
@@ -494,12 +502,12 @@ class _BlendDecode(torch.autograd.Function):
             v_rays = v_pose.sum(1)
         v_w = v_wp.sum(0)
         return (v_rec, None, None, None, v_vsp, v_rays, v_w[:72].reshape(6, 12), v_w[72:].reshape(3, 6),
-                None, None, None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None, None)
 
 
 def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, height, specs=None, tight=True,
                  vsp: Optional[torch.Tensor] = None, vsp_k: int = 0, want_mean: bool = False, mean_K: int = 0,
-                 flow_ref: Optional[int] = None):
+                 flow_ref: Optional[int] = None, plan=None):
     """-> (rgb [K,3,H,W], expected depth [K,H,W], alpha [K,H,W], mean [3,H,W] or empty[, flow [K,H,W,2]]).
     rays: [1,6,H,W] shared, [K,6,H,W] per list, or [record sets,6,H,W] per projection — or a
     mobgs_b200.cameras.RayPose (same leading-axis conventions, 12 pose floats per camera): the kernels then generate
@@ -515,7 +523,7 @@ def blend_decode(records, radii, depths, backgrounds, rays, w1, w2, width, heigh
         rays, ray_intr = rays.pose, tuple(float(v) for v in rays.intr)
     out = _BlendDecode.apply(records, radii, depths, backgrounds, vsp, rays, w1, w2, int(width), int(height),
                              specs, bool(tight), int(vsp_k), bool(want_mean), int(mean_K),
-                             -1 if flow_ref is None else int(flow_ref), ray_intr)
+                             -1 if flow_ref is None else int(flow_ref), ray_intr, plan)
     return out if flow_ref is not None else out[:4]
 
 

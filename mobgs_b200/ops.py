@@ -126,7 +126,49 @@ SPECULATIVE_LISTS = os.environ.get("MOBGS_SPECULATIVE_LISTS", "1") != "0"
 RECORD_ENTRIES = os.environ.get("MOBGS_RECORD_ENTRIES", "1") != "0"
 
 
-def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None, tile_list=None):
+class BinPlan:
+    """Counting pass fused into the projection (MobgsSynthFwd.bin_tile_counts): created by the caller that knows which
+    lists the blend will walk BEFORE it projects, handed to `fused.synth_project(..., binning=plan)` — which lets the
+    projection kernel count and record the tile intersections while each projected Gaussian is still in registers — and
+    then to `build_tile_lists(..., plan=plan)`, which only runs the prefix sum, the scatter and the sorts.  Speculative
+    like the lists themselves: it needs the entry capacity guessed from the previous launch of the same shape, so the
+    first call of a shape (and an overflow redo) take the stand-alone counting kernels."""
+
+    def __init__(self, specs, width, height, tight=True):
+        self.specs = tuple(tuple(int(v) for v in s) for s in specs)
+        self.width, self.height, self.tight = int(width), int(height), bool(tight)
+        self.counts = self.entries = self.cursor = None
+        self.N = None
+
+    def key(self, N, dev):
+        return (len(self.specs), int(N), self.width, self.height, self.specs, self.tight, dev.index)
+
+    def prepare(self, N, dev):
+        """-> (lists struct, counts, entries, cursor) for the projection launch, or None (no capacity guess yet)"""
+        if not (SPECULATIVE_LISTS and RECORD_ENTRIES and FUSED_COUNT) or len(self.specs) > L.MAX_K:
+            return None
+        guess = _CAP_CACHE.get(self.key(N, dev))
+        if guess is None:
+            return None
+        # The projection kernel owns one Gaussian per thread for all K sub-frames, so its slot atomics are issued one
+        # after the other: fine at ~1.4 tiles per (list, Gaussian) (150 k / 512x288 / K = 9: count 0.19 -> +0.11 ms on the
+        # projection, step 1.41 -> 1.31 ms; 1 M / 1080p: neutral), hopeless at 35 (heavy-footprint run: 6.8 -> 22 ms).
+        if guess > FUSED_COUNT_MAX_TILES * len(self.specs) * max(int(N), 1) + 4096:
+            return None
+        tiles = math.ceil(self.width / L.TILE) * math.ceil(self.height / L.TILE)
+        self.counts = torch.empty(len(self.specs) * tiles, dtype=torch.int32, device=dev)
+        self.entries = torch.empty(max(int(guess), 1), 4, dtype=torch.int32, device=dev)
+        self.cursor = torch.empty(1, dtype=torch.int32, device=dev)
+        self.N = int(N)
+        return L.make_lists(self.specs), self.counts, self.entries, self.cursor
+
+
+# 0: never fuse the counting pass into the projection (ablation)
+FUSED_COUNT = os.environ.get("MOBGS_FUSED_COUNT", "1") != "0"
+FUSED_COUNT_MAX_TILES = 2.5      # average tile entries per (list, Gaussian) above which the stand-alone pass is used
+
+
+def build_tile_lists(records, radii, depths, width, height, tight=True, specs=None, consume=None, tile_list=None, plan=None):
     """mobgs_tile_count -> mobgs_tile_emit_sort (-> consume(lists)).
 
     specs: [(record_set, g_begin, g_end)] per list; default = one full-range list per record set.
@@ -135,7 +177,9 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     of a group is the position of its first member among the distinct values).  Default: every list its own.
     consume: optional callable(lists) that enqueues the kernels using the lists (blend); when given,
     returns (lists, consume(lists)) and sizes the lists speculatively (see above); otherwise reads I
-    back synchronously and returns lists."""
+    back synchronously and returns lists.
+    plan: a BinPlan that the projection launch has already filled (counts + recorded entries): only the prefix sum,
+    the scatter and the sorts run here."""
     Kr, N = radii.shape
     if specs is None:
         specs = tuple((k, 0, N) for k in range(Kr))
@@ -165,11 +209,17 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     # Speculative calls also let the counting pass RECORD the intersections it finds (MobgsTileCount.entries), which turns
     # the emit pass into a streaming scatter; the exact-size (first / overflow) calls use the two-pass kernels.
     entries = cursor = None
-    if speculative and RECORD_ENTRIES:
+    precounted = (plan is not None and plan.counts is not None and speculative and tile_list is None and plan.N == N
+                  and plan.specs == tuple(bin_specs) and plan.tight == bool(tight)
+                  and (plan.width, plan.height) == (width, height))
+    if precounted:
+        counts, entries, cursor = plan.counts, plan.entries, plan.cursor
+        plan.counts = plan.entries = plan.cursor = None          # consumed
+    elif speculative and RECORD_ENTRIES:
         entries = torch.empty(max(int(guess), 1), 4, dtype=torch.int32, device=dev)
         cursor = torch.empty(1, dtype=torch.int32, device=dev)
     a = L.TileCount(K, N, width, height, _p(records), _p(radii), int(tight), lists, _p(counts), _p(offsets),
-                    _p(depths), _p(entries), 0 if entries is None else entries.shape[0], _p(cursor))
+                    _p(depths), _p(entries), 0 if entries is None else entries.shape[0], _p(cursor), int(precounted))
     L.call("mobgs_tile_count", a, _stream())
 
     def emit_sort(cap, use_entries=False):

@@ -17,6 +17,7 @@ import os
 
 from . import fused
 from .gaussian_renderer import _bg10, _dynamic_params, _static_params
+from .ops import BinPlan
 
 # ablation only (tools/ablation.sh): MOBGS_ABL_AABB_TILES=1 lists every tile of gsplat's 3-sigma
 # square instead of pruning the provably empty ones
@@ -41,15 +42,17 @@ def render_subframes(stat_pc, dyn_pc, viewmats: torch.Tensor, Ks: torch.Tensor, 
     if Ks.dim() == 2:
         Ks = Ks[None].expand(K, -1, -1)
     ck = K // 2 if center_k is None else center_k
+    N = stat_pc.get_xyz.shape[0] + dyn_pc.get_xyz.shape[0]
+    plan = BinPlan([(k, 0, N) for k in range(K)], width, height, tight)      # the K lists are counted by the projection launch
     records, radii, depths, _ = fused.synth_project(
         _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
-        viewmats, Ks, t_spline, t_poly, width, height, offset=offset)
+        viewmats, Ks, t_spline, t_poly, width, height, offset=offset, binning=plan)
     vsp = records[ck:ck + 1, :, 0:2].detach().clone().requires_grad_(True)
     bg10 = _bg10(bg_color, dev).expand(K, -1)
     dec = dyn_pc.rgbdecoder
     rgb, depth, alpha, mean = fused.blend_decode(
         records, radii, depths, bg10, rays, dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6),
-        width, height, tight=tight, vsp=vsp, vsp_k=ck, want_mean=True)
+        width, height, tight=tight, vsp=vsp, vsp_k=ck, want_mean=True, plan=plan)
     return {"render": mean, "subframes": rgb, "depth": depth, "alpha": alpha, "radii": radii,
             "viewspace_points": vsp, "visibility_filter": radii[ck] > 0}
 
@@ -99,16 +102,17 @@ def render_blurry_view(viewpoint_cam, warped_cams, exposure_time, stat_pc, dyn_p
     if rays is None:       # `rays` [K,6,H,W]: the K cameras' cam_ray already stacked (mobgs_b200.cameras.camera_rays builds them
         rays = torch.cat([c.cam_ray for c in cams]).to(dev)     # in one launch), saving the concatenation and its backward
 
+    specs = [(k, 0, N) for k in range(K)] + [(half, Ns, N), (half, 0, Ns)]
+    plan = BinPlan(specs, W, H, tight)          # all K + 2 lists are counted by the projection launch
     records, radii, depths, _ = fused.synth_project(
         _static_params(stat_pc), _dynamic_params(dyn_pc), dyn_pc.current_control_num,
-        viewmats, Ks, t_spline, t_poly, W, H)
+        viewmats, Ks, t_spline, t_poly, W, H, binning=plan)
     vsp = records[half:half + 1, :, 0:2].detach().clone().requires_grad_(True)
-    specs = [(k, 0, N) for k in range(K)] + [(half, Ns, N), (half, 0, Ns)]
     bg10 = _bg10(bg_color, dev).expand(K + 2, -1)
     dec = dyn_pc.rgbdecoder
     rgb, depth, alpha, mean = fused.blend_decode(
         records, radii, depths, bg10, rays, dec.mlp1.weight.reshape(6, 12), dec.mlp2.weight.reshape(3, 6),
-        W, H, specs=specs, tight=tight, vsp=vsp, vsp_k=half, want_mean=True, mean_K=K)
+        W, H, specs=specs, tight=tight, vsp=vsp, vsp_k=half, want_mean=True, mean_K=K, plan=plan)
     bg0 = bg_color[0].to(alpha)
     center = rgb[half]
     return {"render": mean, "subframes": rgb[:K], "depths": depth[:K], "render_center": center,

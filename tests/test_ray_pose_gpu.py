@@ -118,3 +118,66 @@ def test_ray_pose_without_pose_gradient_and_slicing():
     _same(full["subframes"], ref["subframes"], "pose vs materialised rays", rtol=1e-6)
     rigid = ray_pose_from_w2c(view, intr.fx, intr.fy, intr.cx, intr.cy, rigid=True)
     _same(rigid.pose, rp.pose, "closed-form rigid inverse vs torch.inverse", rtol=1e-5)
+
+
+def test_counting_pass_fused_into_projection_gives_identical_results():
+    """ops.BinPlan: the projection launch counts and records the tile intersections of the lists the blend will walk
+    (MobgsSynthFwd.bin_tile_counts); the lists — and therefore images and gradients — must be exactly those of the
+    stand-alone counting kernels.  Covers K plain lists (render_subframes) and K + 2 lists with index ranges over shared
+    record sets (render_blurry_view), and checks that the fused path was really taken."""
+    from mobgs_b200 import ops
+    from mobgs_b200.cameras import ray_pose_from_w2c
+    from mobgs_b200.subframes import render_blurry_view, render_subframes
+    K, W, H = 5, 112, 80
+    sc, dc, intr = synthetic_scene(500, 300, W, H, seed=8, device="cuda")
+    params = [p for pc in (sc, dc) for p in pc.parameters() if p.requires_grad]
+    view = torch.stack([subframe_w2c(k, K) for k in range(K)]).cuda()
+    rp = ray_pose_from_w2c(view, intr.fx, intr.fy, intr.cx, intr.cy, rigid=True)
+    Kmat = make_camera(intr, subframe_w2c(0, K)).K.cuda()
+    t = (0.5 + torch.linspace(-1, 1, K) * 0.4 / 23).cuda()
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    cams = [make_camera(intr, subframe_w2c(k, K, device="cuda"), time=0.55) for k in range(K)]
+    expo = (torch.linspace(-1, 1, K) * 0.4).cuda()
+    tgt = torch.rand(3, H, W, generator=torch.Generator().manual_seed(1)).cuda()
+
+    def run(kind):
+        for p in params:
+            p.grad = None
+        if kind == "subframes":
+            out = render_subframes(sc, dc, view, Kmat, t.clamp(0, 1), t, rp, bg, W, H)
+            keys = ("render", "depth", "alpha")
+        else:
+            out = render_blurry_view(cams[K // 2], cams, expo, sc, dc, None, bg, rays=rp)
+            keys = ("render", "depth", "d_alpha", "s_alpha", "s_render", "d_render")
+        (out["render"] - tgt).abs().mean().backward()
+        return [out[k].detach().clone() for k in keys], [None if p.grad is None else p.grad.clone() for p in params]
+
+    taken = []
+    orig = ops.BinPlan.prepare
+
+    def spy(self, N, dev):
+        r = orig(self, N, dev)
+        taken.append(r is not None)
+        return r
+
+    old = ops.FUSED_COUNT
+    try:
+        for kind in ("subframes", "blurry"):
+            ops._CAP_CACHE.clear()
+            ops.FUSED_COUNT = False
+            run(kind)                                   # first call of the shape: sets the capacity guess
+            ref_out, ref_g = run(kind)                  # stand-alone counting kernel (recorded entries)
+            ops.FUSED_COUNT = True
+            ops.BinPlan.prepare = spy
+            got_out, got_g = run(kind)
+            ops.BinPlan.prepare = orig
+            assert taken and taken[-1], "the fused counting pass was not taken"
+            for a, b in zip(got_out, ref_out):
+                assert torch.equal(a, b), kind
+            for a, b, p in zip(got_g, ref_g, params):
+                assert (a is None) == (b is None)
+                if a is not None and a.numel():
+                    assert float((a - b).abs().max()) <= 1e-5 * (float(b.abs().max()) + 1e-12), (kind, tuple(p.shape))
+    finally:
+        ops.FUSED_COUNT = old
+        ops.BinPlan.prepare = orig
