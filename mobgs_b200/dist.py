@@ -155,6 +155,7 @@ class SymmetricGradients:
         self.buf = None
         self.storage_ptr = None
         self.free = False
+        self.slice_ok = None
 
     def begin_step(self):
         """Call once per optimiser step, before the backward: the NEXT flat gradient buffer the backward asks for is
@@ -203,6 +204,20 @@ class SymmetricGradients:
         fused.FLAT_ALLOCATOR = None
         _SYMMETRIC = None
 
+    def all_reduce_slice(self, part: torch.Tensor) -> bool:
+        """in-place sum over ranks of a contiguous, 16-byte aligned slice of the symmetric buffer (same order on every
+        rank); False if `part` is not such a slice or the op refuses views"""
+        if (self.buf is None or self.slice_ok is False or part.untyped_storage().data_ptr() != self.storage_ptr
+                or not part.is_contiguous() or (part.storage_offset() * 4) % 16 or (part.numel() * 4) % 16):
+            return False
+        try:
+            torch.ops.symm_mem.multimem_all_reduce_(part, "sum", self.group.group_name)
+            self.slice_ok = True
+            return True
+        except Exception:  # noqa: BLE001   (every rank fails alike: same op, same arguments)
+            self.slice_ok = False
+            return False
+
     def all_reduce(self, alias: torch.Tensor) -> bool:
         """in-place sum over ranks if `alias` is (a view over) the symmetric buffer"""
         if self.buf is None or alias.untyped_storage().data_ptr() != self.storage_ptr:
@@ -228,6 +243,10 @@ def overlap_gradient_allreduce(enable: bool = True, n_chunks: int = 2, group=Non
 
     def reduce(t):
         if not multi:
+            return None
+        # a slice of the NVLS symmetric gradient buffer: in-switch (multimem) reduction of just that slice, on the
+        # side stream the caller has made current; anything else: NCCL
+        if _SYMMETRIC is not None and _SYMMETRIC.all_reduce_slice(t):
             return None
         return dist.all_reduce(t, group=group, async_op=True)
 
