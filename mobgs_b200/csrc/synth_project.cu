@@ -270,7 +270,10 @@ __global__ void __launch_bounds__(kProjThreads) synth_project_fwd_kernel(const _
 #ifndef MOBGS_CTRL_RED
 #define MOBGS_CTRL_RED 1
 #endif
-__global__ void __launch_bounds__(kProjThreads) synth_project_bwd_kernel(MobgsSynthBwd a) {
+#ifndef MOBGS_SYNTH_BWD_MIN_CTAS
+#define MOBGS_SYNTH_BWD_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(kProjThreads, MOBGS_SYNTH_BWD_MIN_CTAS) synth_project_bwd_kernel(const __grid_constant__ MobgsSynthBwd a) {
   __shared__ CamSmem sm;
   load_cams(sm, a.cams, a.t_spline, a.t_poly);
   const int N = a.st.Ns + a.dy.Nd;
