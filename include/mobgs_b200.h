@@ -312,6 +312,10 @@ typedef struct {
    * ray = [c | normalise(R l)].  The camera of list k is chosen by dec_rays_per_k as for dec_rays. */
   const float* dec_pose;
   float dec_ppx, dec_ppy, dec_sfx, dec_sfy;
+  /* Optional out [list_capacity] (16-lane-unit builds): the per-entry unit mask the kernel computes while staging — which
+   * of the tile's sixteen 4x4-pixel units the Gaussian can reach with alpha >= 1/255 — kept for mobgs_blend_bwd, which
+   * would otherwise recompute it for every entry it stages. */
+  uint16_t* list_masks;
 } MobgsBlendFwd;
 int mobgs_blend_fwd(const MobgsBlendFwd* a, void* stream);
 
@@ -355,6 +359,8 @@ typedef struct {
   const float* dec_pose;
   float dec_ppx, dec_ppy, dec_sfx, dec_sfy;
   float* v_pose_partial;
+  /* Optional in: MobgsBlendFwd.list_masks of the forward over the same lists (NULL = recompute). */
+  const uint16_t* list_masks;
 } MobgsBlendBwd;
 
 #define MOBGS_DEC_SLOTS 1024

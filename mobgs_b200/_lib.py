@@ -165,7 +165,7 @@ class BlendFwd(C.Structure):
                 ("dec_w2", C.c_void_p), ("out_rgb", C.c_void_p), ("out_depth", C.c_void_p),
                 ("flow_ref", C.c_int32), ("out_flow", C.c_void_p),
                 ("dec_pose", C.c_void_p), ("dec_ppx", C.c_float), ("dec_ppy", C.c_float), ("dec_sfx", C.c_float),
-                ("dec_sfy", C.c_float)]
+                ("dec_sfy", C.c_float), ("list_masks", C.c_void_p)]
 
 
 class BlendBwd(C.Structure):
@@ -181,7 +181,7 @@ class BlendBwd(C.Structure):
                 ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p),
                 ("flow_ref", C.c_int32), ("g_flow", C.c_void_p),
                 ("dec_pose", C.c_void_p), ("dec_ppx", C.c_float), ("dec_ppy", C.c_float), ("dec_sfx", C.c_float),
-                ("dec_sfy", C.c_float), ("v_pose_partial", C.c_void_p)]
+                ("dec_sfy", C.c_float), ("v_pose_partial", C.c_void_p), ("list_masks", C.c_void_p)]
 
 
 class DecodeFwd(C.Structure):

@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
     bar_phase ^= 1;
     if (idx < end) {
       smask[tid] = unit_mask(srec[tid][0], srec[tid][1], (float)(tx * kTile), (float)(ty * kTile));
+      if (kUnits <= 16 && a.list_masks) a.list_masks[idx] = (uint16_t)smask[tid];       // kept for the backward
       if (FLOW) sflow[tid] = make_float2(mref.x - srec[tid][0].x, mref.y - srec[tid][0].y);
       rescale_conic(reinterpret_cast<float*>(&srec[tid][0]));
     }
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(kBlendThreads, FLOW ? MOBGS_FWD_MIN_CTAS - 1 :
       if (D > 2) srec[tid][2] = __ldg(r + 2);
       if (D > 6) srec[tid][3] = __ldg(r + 3);
       smask[tid] = unit_mask(q0, q1, (float)(tx * kTile), (float)(ty * kTile));
+      if (kUnits <= 16 && a.list_masks) a.list_masks[idx] = (uint16_t)smask[tid];
       if (FLOW) {
         const float2 mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
         sflow[tid] = make_float2(mref.x - q0.x, mref.y - q0.y);
@@ -969,11 +971,14 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     __syncthreads();   // previous batch fully flushed
     if (tid == 0) mbar_expect_tx(sbar, (uint32_t)bn * kRecBytes);
     float2 mref = make_float2(0.f, 0.f);
+    const bool have_masks = kUnits <= 16 && a.list_masks != nullptr;     // the forward's unit masks of these lists
+    unsigned fwd_mask = 0u;
     if (tid < bn) {
       const int g = list_gid(a.sorted_ids, hi - tid, a.N);   // slot t holds list entry hi - t
       sid[tid] = g;
       bulk_g2s(srec + tid * kRecRow, recs + (size_t)g * 4, kRecBytes, sbar);
       if (FLOW) mref = __ldg(reinterpret_cast<const float2*>(recs_ref + (size_t)g * 4));
+      if (have_masks) fwd_mask = a.list_masks[hi - tid];
     }
     for (int i = tid; i < kAccFloats; i += kBlendThreads) sacc[i] = 0.f;
 #if MOBGS_BWD_LEAN_A
@@ -985,7 +990,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
     bar_phase ^= 1;
     if (tid < bn) {
       const float4* r = reinterpret_cast<const float4*>(srec + tid * kRecRow);
-      smask[tid] = unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
+      smask[tid] = have_masks ? fwd_mask : unit_mask(r[0], r[1], (float)(tx * kTile), (float)(ty * kTile));
       if (FLOW) *reinterpret_cast<float2*>(srec + tid * kRecRow + 16) = make_float2(mref.x - r[0].x, mref.y - r[0].y);
       rescale_conic(srec + tid * kRecRow);
     }

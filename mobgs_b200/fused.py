@@ -90,6 +90,11 @@ def _recycle(g_rec):
     _GRAD_REC_POOL[key] = g_rec
 
 
+# argument tails of L.BlendFwd / L.BlendBwd for launches without the fused decoder, up to (not including) list_masks
+_NO_DEC_FWD = (None, 0, None, None, None, None, 0, None, None, 0.0, 0.0, 0.0, 0.0)
+_NO_DEC_BWD = (None, 0, None, None, None, None, None, None, None, 0, None, None, 0, None, None, 0.0, 0.0, 0.0, 0.0, None)
+
+
 STATIC_KEYS = ("xyz", "rotation", "scaling", "opacity", "features_dc")
 DYNAMIC_KEYS = ("control_xyz", "rotation", "omega", "scaling", "opacity", "features_dc", "features_t",
                 "trbf_center")
@@ -317,14 +322,15 @@ class _BlendRecords(torch.autograd.Function):
             out_c = torch.empty(K, height, width, D, device=dev)
             out_a = torch.empty(K, height, width, device=dev)
             last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
+            masks = torch.empty(lists.capacity, dtype=torch.int16, device=dev)       # unit masks, kept for the backward
             a = L.BlendFwd(K, N, D, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
-                           _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last))
+                           _p(lists.sorted_ids), _p(bg), _p(out_c), _p(out_a), _p(last), *_NO_DEC_FWD, _p(masks))
             L.call("mobgs_blend_fwd", a, _stream())
-            return out_c, out_a, last
+            return out_c, out_a, last, masks
 
-        lists, (out_c, out_a, last) = build_tile_lists(records, radii, depths, width, height, tight, specs, consume=blend,
-                                                       tile_list=tile_list)
-        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last)
+        lists, (out_c, out_a, last, masks) = build_tile_lists(records, radii, depths, width, height, tight, specs,
+                                                              consume=blend, tile_list=tile_list)
+        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, out_a, last, masks)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
         ctx.meta = (K, Kr, N, D, width, height, vsp_list, vsp is not None)
         ctx.n_isect = lists.n_isect
@@ -333,7 +339,7 @@ class _BlendRecords(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_c, g_a, _g_last):
-        records, offsets, sorted_ids, bg, out_a, last = ctx.saved_tensors
+        records, offsets, sorted_ids, bg, out_a, last, masks = ctx.saved_tensors
         K, Kr, N, D, width, height, vsp_list, has_vsp = ctx.meta
         dev = records.device
         g_c = _f32c(g_c) if g_c is not None else torch.zeros(K, height, width, D, device=dev)
@@ -341,7 +347,8 @@ class _BlendRecords(torch.autograd.Function):
         v_rec = _take_grad_records(Kr, N, dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
         a = L.BlendBwd(K, N, D, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
-                       _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp))
+                       _p(bg), _p(out_a), _p(last), _p(g_c), _p(g_a), _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
+                       *_NO_DEC_BWD, _p(masks))
         L.call("mobgs_blend_bwd", a, _stream())
         return v_rec, None, None, None, v_vsp, None, None, None, None, None, None, None
 
@@ -445,23 +452,24 @@ class _BlendDecode(torch.autograd.Function):
             rgb = torch.empty(K, 3, height, width, device=dev)
             depth = torch.empty(K, height, width, device=dev)
             flow = torch.empty(K, height, width, 2, device=dev) if flow_ref >= 0 else None
+            masks = torch.empty(lists.capacity, dtype=torch.int16, device=dev)       # unit masks, kept for the backward
             a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
                            _p(lists.sorted_ids), _p(bg), _p(img10), _p(alpha), _p(last),
                            _p(rays) if ray_intr is None else None, per_k, _p(w1), _p(w2), _p(rgb), _p(depth),
                            max(flow_ref, 0), _p(flow), *((None, 0.0, 0.0, 0.0, 0.0) if ray_intr is None else
-                                                         (_p(rays), *ray_intr)))
+                                                         (_p(rays), *ray_intr)), _p(masks))
             L.call("mobgs_blend_fwd", a, _stream())
-            return img10, alpha, last, rgb, depth, flow
+            return img10, alpha, last, rgb, depth, flow, masks
 
-        lists, (img10, alpha, last, rgb, depth, flow) = build_tile_lists(records, radii, depths, width, height, tight,
-                                                                         specs, consume=blend, plan=plan)
+        lists, (img10, alpha, last, rgb, depth, flow, masks) = build_tile_lists(records, radii, depths, width, height, tight,
+                                                                                specs, consume=blend, plan=plan)
         if want_mean:
             mean = torch.empty(3, height, width, device=dev)
             L.subframe_mean(_p(rgb), _p(mean), mK, 3 * height * width, _stream())
         else:
             mean = torch.empty(0, device=dev)
             ctx.mark_non_differentiable(mean)
-        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2)
+        ctx.save_for_backward(records, lists.tile_offsets, lists.sorted_ids, bg, img10, alpha, last, rays, w1, w2, masks)
         ctx.lists, ctx.capacity = lists.lists, lists.capacity
         ctx.meta = (K, Kr, N, width, height, vsp_list, vsp is not None, per_k, mK, flow_ref, ray_intr)
         ctx.n_isect = lists.n_isect
@@ -472,7 +480,7 @@ class _BlendDecode(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rgb, g_depth, g_alpha, g_mean, g_flow):
-        records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2 = ctx.saved_tensors
+        records, offsets, sorted_ids, bg, img10, alpha, last, rays, w1, w2, masks = ctx.saved_tensors
         K, Kr, N, width, height, vsp_list, has_vsp, per_k, mK, flow_ref, ray_intr = ctx.meta
         if flow_ref >= 0:
             g_flow = _f32c(g_flow) if g_flow is not None else torch.zeros(K, height, width, 2, device=records.device)
@@ -496,7 +504,8 @@ class _BlendDecode(torch.autograd.Function):
                        _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
                        _p(rays) if ray_intr is None else None, per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth),
                        _p(g_alpha), _p(g_mean), mK, _p(v_rays), _p(v_wp), max(flow_ref, 0), _p(g_flow),
-                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))))
+                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))),
+                       _p(masks))
         L.call("mobgs_blend_bwd", a, _stream())
         if v_pose is not None:
             v_rays = v_pose.sum(1)
@@ -606,14 +615,15 @@ class _FlowRender(torch.autograd.Function):
             last = torch.empty(K, height, width, dtype=torch.int32, device=dev)
             rgb = torch.empty(K, 3, height, width, device=dev)
             flow = torch.empty(K, height, width, 2, device=dev)
+            masks = torch.empty(lists.capacity, dtype=torch.int16, device=dev)
             a = L.BlendFwd(K, N, 10, width, height, lists.lists, lists.capacity, _p(records), _p(lists.tile_offsets),
                            _p(lists.sorted_ids), _p(bg10), _p(img10), _p(alpha), _p(last),
                            _p(rays) if ray_intr is None else None, 0, _p(w1), _p(w2), _p(rgb), None, 0, _p(flow),
-                           *((None, 0.0, 0.0, 0.0, 0.0) if ray_intr is None else (_p(rays), *ray_intr)))
+                           *((None, 0.0, 0.0, 0.0, 0.0) if ray_intr is None else (_p(rays), *ray_intr)), _p(masks))
             L.call("mobgs_blend_fwd", a, st)
-            return img10, alpha, last, rgb, flow
+            return img10, alpha, last, rgb, flow, masks
 
-        le, (img10, alpha_e, last_e, rgb, flow) = build_tile_lists(
+        le, (img10, alpha_e, last_e, rgb, flow, masks_e) = build_tile_lists(
             records, radii, depths, width, height, tight, tuple((k + 1, 0, N) for k in range(K)), consume=exp_walk)
 
         def plain_walk(recs, D):
@@ -622,26 +632,27 @@ class _FlowRender(torch.autograd.Function):
                 out_c = torch.empty(Kl, height, width, D, device=dev)
                 out_a = torch.empty(Kl, height, width, device=dev)
                 last = torch.empty(Kl, height, width, dtype=torch.int32, device=dev)
+                masks = torch.empty(lists.capacity, dtype=torch.int16, device=dev)
                 a = L.BlendFwd(Kl, N, D, width, height, lists.lists, lists.capacity, _p(recs), _p(lists.tile_offsets),
-                               _p(lists.sorted_ids), None, _p(out_c), _p(out_a), _p(last))
+                               _p(lists.sorted_ids), None, _p(out_c), _p(out_a), _p(last), *_NO_DEC_FWD, _p(masks))
                 L.call("mobgs_blend_fwd", a, st)
-                return out_c, out_a, last
+                return out_c, out_a, last, masks
             return walk
 
-        ld, (_junk, alpha_d, last_d) = build_tile_lists(
+        ld, (_junk, alpha_d, last_d, masks_d) = build_tile_lists(
             records, radii, depths, width, height, tight, tuple((k + 1, Ns, N) for k in range(K)), consume=plain_walk(records, 1))
 
         M = (2 * K + 9) // 10
         frec = torch.empty(M, N, L.REC, device=dev)
         L.call("mobgs_midflow_records_fwd", L.FlowRecFwd(K, N, _p(records), _p(frec)), st)
         radii_m, depths_m = radii[0:1].expand(M, -1).contiguous(), depths[0:1].expand(M, -1).contiguous()
-        lm, (mid, alpha_m, last_m) = build_tile_lists(
+        lm, (mid, alpha_m, last_m, masks_m) = build_tile_lists(
             frec, radii_m, depths_m, width, height, tight, tuple((m, 0, N) for m in range(M)),
             consume=plain_walk(frec, 10), tile_list=(0,) * M)
 
         ctx.save_for_backward(records, bg10, rays, w1, w2, img10, alpha_e, last_e, le.tile_offsets, le.sorted_ids,
                               alpha_d, last_d, ld.tile_offsets, ld.sorted_ids, frec, alpha_m, last_m, lm.tile_offsets,
-                              lm.sorted_ids)
+                              lm.sorted_ids, masks_e, masks_d, masks_m)
         ctx.lists = (le.lists, le.capacity, ld.lists, ld.capacity, lm.lists, lm.capacity)
         ctx.meta = (K, M, N, width, height, ray_intr)
         return rgb, flow, alpha_d, mid
@@ -649,7 +660,7 @@ class _FlowRender(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_flow, g_alpha_d, g_mid):
         (records, bg10, rays, w1, w2, img10, alpha_e, last_e, off_e, ids_e, alpha_d, last_d, off_d, ids_d, frec, alpha_m,
-         last_m, off_m, ids_m) = ctx.saved_tensors
+         last_m, off_m, ids_m, masks_e, masks_d, masks_m) = ctx.saved_tensors
         le, cap_e, ld, cap_d, lm, cap_m = ctx.lists
         K, M, N, width, height, ray_intr = ctx.meta
         dev = records.device
@@ -667,19 +678,20 @@ class _FlowRender(torch.autograd.Function):
         a = L.BlendBwd(K, N, 10, width, height, le, cap_e, _p(records), _p(off_e), _p(ids_e), _p(bg10), _p(alpha_e),
                        _p(last_e), None, None, _p(v_rec), -1, None, _p(rays) if ray_intr is None else None, 0, _p(w1),
                        _p(w2), _p(img10), _p(g_rgb), None, None, None, 0, _p(v_rays), _p(v_wp), 0, _p(g_flow),
-                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))))
+                       *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))),
+                       _p(masks_e))
         L.call("mobgs_blend_bwd", a, st)
         if v_pose is not None:
             v_rays = v_pose.sum(1)
         if g_alpha_d is not None:
             zeros = torch.zeros(K, height, width, 1, device=dev)
             a = L.BlendBwd(K, N, 1, width, height, ld, cap_d, _p(records), _p(off_d), _p(ids_d), None, _p(alpha_d),
-                           _p(last_d), _p(zeros), _p(_f32c(g_alpha_d)), _p(v_rec), -1, None)
+                           _p(last_d), _p(zeros), _p(_f32c(g_alpha_d)), _p(v_rec), -1, None, *_NO_DEC_BWD, _p(masks_d))
             L.call("mobgs_blend_bwd", a, st)
         if g_mid is not None:
             v_frec = torch.zeros(M, N, L.REC, device=dev)
             a = L.BlendBwd(M, N, 10, width, height, lm, cap_m, _p(frec), _p(off_m), _p(ids_m), None, _p(alpha_m),
-                           _p(last_m), _p(_f32c(g_mid)), None, _p(v_frec), -1, None)
+                           _p(last_m), _p(_f32c(g_mid)), None, _p(v_frec), -1, None, *_NO_DEC_BWD, _p(masks_m))
             L.call("mobgs_blend_bwd", a, st)
             L.call("mobgs_midflow_records_bwd", L.FlowRecBwd(K, N, _p(v_frec), _p(v_rec), 1), st)
         v_w = v_wp.sum(0)
