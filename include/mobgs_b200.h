@@ -361,6 +361,13 @@ typedef struct {
   float* v_pose_partial;
   /* Optional in: MobgsBlendFwd.list_masks of the forward over the same lists (NULL = recompute). */
   const uint16_t* list_masks;
+  /* != 0 (fused-prologue launches): the caller expects most tiles to receive no gradient at all — train.py's SECOND
+   * backward pass over a blurry view (loss.backward() at :680 after photo_loss.backward(retain_graph=True) at :629)
+   * reaches only the centre render's depth / alpha / image, i.e. 2 of its K + 2 lists.  Every CTA then first tests
+   * its pixels' g_mean / g_rgb / g_depth / g_alpha / g_flow and leaves before the decoder prologue when all are zero
+   * (the VJP is linear in them, so the result is unchanged).  With per-list v_rays (dec_rays_per_k == 1) the caller
+   * must then zero v_rays itself. */
+  int32_t sparse_grads;
 } MobgsBlendBwd;
 
 #define MOBGS_DEC_SLOTS 1024
@@ -753,6 +760,22 @@ int mobgs_reg_loss_fwd(const MobgsRegLoss* a, void* stream);
  * neighbours, the point itself excluded (scene/gaussian_model.py:420, :514).  Tiled brute force, O(N^2):
  * for the initialisation point clouds. */
 int mobgs_knn3_mean_dist2(const float* points, float* out, int32_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * main_utils.get_normals (main_utils.py:95-141; called once per view and step at train.py:590 on the centre render's
+ * depth): camera-space normals from a depth map.  With the local view direction of pixel (u, v)
+ *   y = (v + pixel_offset - ppy) / sfy,  x = (u + pixel_offset - ppx - y skew) / sfx,  c(u, v) = (x, y, 1) z(u, v)
+ * (dycheck_geometry Camera.get_pixels / principal_point / scale_factor / skew; pixel_offset = 0.5 when use_center),
+ *   n = normalise((c(u+1,v) - c(u-1,v)) x (c(u,v-1) - c(u,v+1)))   (F.normalize, eps 1e-12)
+ * for interior pixels and 0 on the one-pixel border.  z [B,H,W] -> normals [B,3,H,W].  Forward only: the reference
+ * never uses the result in a loss (train.py:615). */
+typedef struct {
+  int32_t B, width, height;
+  const float* z;
+  float ppx, ppy, sfx, sfy, skew, pixel_offset;
+  float* normals;
+} MobgsNormals;
+int mobgs_depth_normals(const MobgsNormals* a, void* stream);
 
 #ifdef __cplusplus
 }

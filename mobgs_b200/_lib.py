@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "hexplane_mlp_bwd.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "hexplane_mlp_bwd.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu", "normals.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -181,7 +181,8 @@ class BlendBwd(C.Structure):
                 ("mean_K", C.c_int32), ("v_rays", C.c_void_p), ("v_w_partial", C.c_void_p),
                 ("flow_ref", C.c_int32), ("g_flow", C.c_void_p),
                 ("dec_pose", C.c_void_p), ("dec_ppx", C.c_float), ("dec_ppy", C.c_float), ("dec_sfx", C.c_float),
-                ("dec_sfy", C.c_float), ("v_pose_partial", C.c_void_p), ("list_masks", C.c_void_p)]
+                ("dec_sfy", C.c_float), ("v_pose_partial", C.c_void_p), ("list_masks", C.c_void_p),
+                ("sparse_grads", C.c_int32)]
 
 
 class DecodeFwd(C.Structure):
@@ -290,6 +291,12 @@ class RegLoss(C.Structure):
                 ("alpha", C.c_void_p), ("sums", C.c_void_p), ("g_depth", C.c_void_p), ("g_alpha", C.c_void_p)]
 
 
+class Normals(C.Structure):
+    _fields_ = [("B", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("z", C.c_void_p),
+                ("ppx", C.c_float), ("ppy", C.c_float), ("sfx", C.c_float), ("sfy", C.c_float), ("skew", C.c_float),
+                ("pixel_offset", C.c_float), ("normals", C.c_void_p)]
+
+
 COMPACT_MAX_TENSORS = 64
 
 
@@ -309,7 +316,7 @@ class CopySegments(C.Structure):
                 ("chunk_begin", C.c_int32 * (COPY_MAX_SEGMENTS + 1))]
 
 
-EXTRA_STRUCTS = {"MobgsHexMlpBwd": HexMlpBwd, "MobgsHexWgrad": HexWgrad, "MobgsCopySegments": CopySegments, "MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd}
+EXTRA_STRUCTS = {"MobgsHexMlpBwd": HexMlpBwd, "MobgsHexWgrad": HexWgrad, "MobgsCopySegments": CopySegments, "MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd, "MobgsNormals": Normals}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -348,6 +355,7 @@ ENTRY_POINTS = {
     "mobgs_compact_rows": CompactRows,
     "mobgs_compact_chunk_words": "int",
     "mobgs_copy_segments": CopySegments,
+    "mobgs_depth_normals": Normals,
 }
 
 _lib = None

@@ -896,6 +896,28 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   }
 #endif
 
+  if (DEC && a.sparse_grads) {
+    // MobgsBlendBwd.sparse_grads: most tiles of this launch receive no gradient.  Test the upstream gradients of the
+    // tile's pixels before anything else — a tile without any leaves here, before the decoder prologue (img10 reads, ray
+    // generation, decoder recompute, 27 scratch rows, the weight-gradient dot products) that the exit below comes after.
+    bool nz = false;
+    if (inside) {
+      const size_t P = (size_t)a.width * a.height, pp = (size_t)iy * a.width + ix, p = (size_t)k * P + pp;
+      const int meanK = a.mean_K > 0 ? a.mean_K : a.K;
+      if (a.g_mean && k < meanK) nz = __ldg(a.g_mean + pp) != 0.f || __ldg(a.g_mean + P + pp) != 0.f || __ldg(a.g_mean + 2 * P + pp) != 0.f;
+      if (a.g_rgb) {
+        const float* gr = a.g_rgb + (size_t)k * 3 * P + pp;
+        nz = nz || __ldg(gr) != 0.f || __ldg(gr + P) != 0.f || __ldg(gr + 2 * P) != 0.f;
+      }
+      if (a.g_depth) nz = nz || __ldg(a.g_depth + p) != 0.f;
+      if (a.g_alpha) nz = nz || __ldg(a.g_alpha + p) != 0.f;
+      if (FLOW) {
+        const float2 gf = __ldg(reinterpret_cast<const float2*>(a.g_flow + p * 2));
+        nz = nz || gf.x != 0.f || gf.y != 0.f;
+      }
+    }
+    if (!__syncthreads_or(nz)) return;
+  }
   float T_final, v_a, bg_dot = 0.f;
   float v_c[D];
   int last;

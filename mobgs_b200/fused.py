@@ -116,6 +116,9 @@ class _SynthProject(torch.autograd.Function):
     def forward(ctx, viewmats, Ks, t_spline, t_poly, control_num, width, height, want_means3d,
                 s_xyz, s_rot, s_sc, s_op, s_fdc,
                 d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf, d_off, binning=None):
+        # gradients of outputs nobody used arrive as None instead of freshly zero-filled tensors (radii / depths / means3d
+        # are K*N each: 56 MB of fills per backward at 1 M Gaussians, K = 7)
+        ctx.set_materialize_grads(False)
         st = [_f32c(t) for t in (s_xyz, s_rot, s_sc, s_op, s_fdc)]
         dy = [_f32c(t) for t in (d_ctrl, d_rot, d_om, d_sc, d_op, d_fdc, d_ft, d_trbf)]
         viewmats, Ks = _f32c(viewmats), _f32c(Ks)
@@ -156,6 +159,8 @@ class _SynthProject(torch.autograd.Function):
         width, height = ctx.size
         K = viewmats.shape[0]
         dev = viewmats.device
+        if g_rec is None:                     # (only radii / depths were used downstream: nothing to propagate)
+            return (None,) * 23
         g_rec = _f32c(g_rec)
         recycle = _recyclable(g_rec)          # our own buffer: zero it behind the reads and keep it for the next step
         # All Gaussian-parameter gradients are views into ONE zeroed flat buffer (segments padded to 16 B):
@@ -312,6 +317,7 @@ def synth_project(static_params, dynamic_params, control_num, viewmats, Ks, t_sp
 class _BlendRecords(torch.autograd.Function):
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, D, width, height, specs, tight, vsp_list, tile_list=None):
+        ctx.set_materialize_grads(False)
         records = _f32c(records)
         Kr, N = radii.shape
         dev = records.device
@@ -426,6 +432,10 @@ class _BlendDecode(torch.autograd.Function):
     @staticmethod
     def forward(ctx, records, radii, depths, backgrounds, vsp, rays, w1, w2, width, height, specs, tight,
                 vsp_list, want_mean, mean_K=0, flow_ref=-1, ray_intr=None, plan=None):
+        # Unused outputs' gradients arrive as None, not as zero-filled tensors: a step whose loss reads only the blur mean
+        # would otherwise allocate, fill and then READ (in the backward prologue) zeros for rgb [K,3,H,W], depth and
+        # alpha — 290 MB each way at 1080p, K = 7.
+        ctx.set_materialize_grads(False)
         records = _f32c(records)
         rays, w1, w2 = _f32c(rays), _f32c(w1), _f32c(w2)
         Kr, N = radii.shape
@@ -494,18 +504,22 @@ class _BlendDecode(torch.autograd.Function):
         v_rec = _take_grad_records(Kr, N, dev)
         v_vsp = torch.zeros(1, N, 2, device=dev) if has_vsp else None
         v_rays = v_pose = None
+        # No gradient through the blur mean: this is a pass that reaches few of the lists (train.py's second backward,
+        # :680, touches the centre render's depth / alphas / image only) — tiles test their upstream gradients first and
+        # leave before the decoder prologue (MobgsBlendBwd.sparse_grads).
+        sparse = g_mean is None and K > 1
         if ctx.needs_input_grad[5]:
             if ray_intr is not None:
                 v_pose = torch.zeros(rays.shape[0], L.POSE_SLOTS, 12, device=dev)
             else:
-                v_rays = torch.empty_like(rays) if per_k == 1 else torch.zeros_like(rays)
+                v_rays = torch.empty_like(rays) if (per_k == 1 and not sparse) else torch.zeros_like(rays)
         v_wp = torch.zeros(L.DEC_SLOTS, 90, device=dev)
         a = L.BlendBwd(K, N, 10, width, height, ctx.lists, ctx.capacity, _p(records), _p(offsets), _p(sorted_ids),
                        _p(bg), _p(alpha), _p(last), None, None, _p(v_rec), vsp_list if has_vsp else -1, _p(v_vsp),
                        _p(rays) if ray_intr is None else None, per_k, _p(w1), _p(w2), _p(img10), _p(g_rgb), _p(g_depth),
                        _p(g_alpha), _p(g_mean), mK, _p(v_rays), _p(v_wp), max(flow_ref, 0), _p(g_flow),
                        *((None, 0.0, 0.0, 0.0, 0.0, None) if ray_intr is None else (_p(rays), *ray_intr, _p(v_pose))),
-                       _p(masks))
+                       _p(masks), int(sparse))
         L.call("mobgs_blend_bwd", a, _stream())
         if v_pose is not None:
             v_rays = v_pose.sum(1)
@@ -601,6 +615,7 @@ class _FlowRender(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, records, radii, depths, bg10, rays, w1, w2, width, height, Ns, tight, ray_intr=None):
+        ctx.set_materialize_grads(False)
         records = _f32c(records)
         rays, w1, w2, bg10 = _f32c(rays), _f32c(w1), _f32c(w2), _f32c(bg10)
         Kr, N = radii.shape
