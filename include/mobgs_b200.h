@@ -521,6 +521,40 @@ typedef struct {
 int mobgs_hexplane_wgrad(const MobgsHexWgrad* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a11: device-side packing of the operands MobgsHexMlpFwd / MobgsHexMlpBwd describe above (tiled {hi,lo} weights,
+ * zero-padded biases, channels-last planes) — one table-driven launch instead of ~200 torch ops per optimiser step.
+ * Every job reads a logical [rows x cols] matrix m[r][c] = src[r*row_stride + c*col_stride] (zero outside
+ * valid_rows x valid_cols: padding; strides express the transposes of the backward's W^T operands) and writes
+ *   MOBGS_PACK_TILED:     dst[(k4*rows + r)*4 + q] = hi(m[r][4 k4 + q]) followed, rows*cols floats later, by the lo
+ *                         block (hi = fp32 bits & 0xffffe000 — the tf32 part —, lo = m - hi); cols % 4 == 0
+ *   MOBGS_PACK_PLAIN:     dst[r*cols + c] = m[r][c]
+ *   MOBGS_PACK_TRANSPOSE: dst[c*rows + r] = m[r][c]          ([32][H*W] plane -> channels-last [H*W][32])
+ * jobs / chunk_begin live in DEVICE memory (they change only when a parameter tensor is re-allocated);
+ * chunk_begin[j] = first chunk of job j when every job's rows*cols elements are cut into
+ * mobgs_pack_chunk_elems()-element chunks, chunk_begin[n_jobs] = n_chunks. */
+#define MOBGS_PACK_MAX_JOBS 96
+#define MOBGS_PACK_TILED 0
+#define MOBGS_PACK_PLAIN 1
+#define MOBGS_PACK_TRANSPOSE 2
+typedef struct {
+  const float* src;
+  int64_t row_stride, col_stride;
+  int32_t rows, cols;
+  int32_t valid_rows, valid_cols;
+  float* dst;
+  int32_t kind;
+  int32_t reserved_;
+} MobgsPackJob;
+typedef struct {
+  int32_t n_jobs;
+  int32_t n_chunks;
+  const MobgsPackJob* jobs;       /* [n_jobs] device */
+  const int32_t* chunk_begin;     /* [n_jobs + 1] device */
+} MobgsPackOperands;
+int mobgs_pack_operands(const MobgsPackOperands* a, void* stream);
+int mobgs_pack_chunk_elems(void);
+
+/* ------------------------------------------------------------------------------------------
  * Flow records for get_flow() (gaussian_renderer/__init__.py:435-471), K exposure offsets at once.
  * records [K+1,N,16]: set 0 = geometry at the mid time, sets 1..K = geometry at the K exposure
  * times (same camera).  For every k two record sets are written to flow_records [2K,N,16]:

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.path.join(_HERE, "libmobgs_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "hexplane_mlp_bwd.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu", "normals.cu"]
+SOURCES = ["capi.cu", "synth_project.cu", "bin_sort.cu", "blend.cu", "decode.cu", "hexplane_mlp.cu", "hexplane_mlp_bwd.cu", "flow_records.cu", "hexplane_grid.cu", "adam.cu", "photo_loss.cu", "camera_rays.cu", "flow_warp_loss.cu", "reg_loss.cu", "knn.cu", "compact.cu", "normals.cu", "hexplane_pack.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-extended-lambda", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared",
@@ -297,6 +297,20 @@ class Normals(C.Structure):
                 ("pixel_offset", C.c_float), ("normals", C.c_void_p)]
 
 
+PACK_MAX_JOBS = 96
+PACK_TILED, PACK_PLAIN, PACK_TRANSPOSE = 0, 1, 2
+
+
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("row_stride", C.c_int64), ("col_stride", C.c_int64), ("rows", C.c_int32),
+                ("cols", C.c_int32), ("valid_rows", C.c_int32), ("valid_cols", C.c_int32), ("dst", C.c_void_p),
+                ("kind", C.c_int32), ("reserved_", C.c_int32)]
+
+
+class PackOperands(C.Structure):
+    _fields_ = [("n_jobs", C.c_int32), ("n_chunks", C.c_int32), ("jobs", C.c_void_p), ("chunk_begin", C.c_void_p)]
+
+
 COMPACT_MAX_TENSORS = 64
 
 
@@ -316,7 +330,7 @@ class CopySegments(C.Structure):
                 ("chunk_begin", C.c_int32 * (COPY_MAX_SEGMENTS + 1))]
 
 
-EXTRA_STRUCTS = {"MobgsHexMlpBwd": HexMlpBwd, "MobgsHexWgrad": HexWgrad, "MobgsCopySegments": CopySegments, "MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd, "MobgsNormals": Normals}
+EXTRA_STRUCTS = {"MobgsHexMlpBwd": HexMlpBwd, "MobgsHexWgrad": HexWgrad, "MobgsCopySegments": CopySegments, "MobgsCompactRows": CompactRows, "MobgsRegLoss": RegLoss, "MobgsFlowWarp": FlowWarp, "MobgsCameraRays": CameraRays, "MobgsAdam": Adam, "MobgsPhotoLossFwd": PhotoLossFwd, "MobgsPhotoLossBwd": PhotoLossBwd, "MobgsNormals": Normals, "MobgsPackJob": PackJob, "MobgsPackOperands": PackOperands}
 
 # name -> argument struct (None = no-arg string getter).  tests/test_abi.py checks that every
 # function declared in include/mobgs_b200.h appears here and resolves in the .so.
@@ -356,6 +370,8 @@ ENTRY_POINTS = {
     "mobgs_compact_chunk_words": "int",
     "mobgs_copy_segments": CopySegments,
     "mobgs_depth_normals": Normals,
+    "mobgs_pack_operands": PackOperands,
+    "mobgs_pack_chunk_elems": "int",
 }
 
 _lib = None

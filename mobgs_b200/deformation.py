@@ -30,51 +30,106 @@ PLANE_FEATURES = 32
 HEAD_OUT = (7, 3, 4)
 
 
-def _tile(w: torch.Tensor) -> torch.Tensor:
-    """[rows, K] row-major -> {hi, lo} x [K/4][rows][4] (the kernel's shared-memory operand layout)."""
-    rows, K = w.shape
-    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)     # keep 10 mantissa bits (TF32)
-    lo = w - hi
-    t = lambda m: m.reshape(rows, K // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)  # noqa: E731
-    return torch.cat([t(hi), t(lo)])
+class _OperandPack:
+    """Device-side packing plan for one set of parameter tensors (csrc/hexplane_pack.cu, MobgsPackOperands): the
+    kernels' operand layouts — weights tiled {tf32 hi, fp32 lo} x [K/4][rows][4], biases zero-padded, W^T tiles for
+    the data-gradient GEMMs, planes channels-last [H,W,32] — are all produced by ONE launch per parameter change
+    (once per optimiser step in training, never during inference).  The job table is built once and lives on the
+    device; it is rebuilt only when a parameter tensor is replaced or re-allocated.
 
+      w0:   feature_out[0].weight [128, 32*levels] as 2 row halves x {hi,lo} x [K/4][64][4]
+      wa:   per head, Linear(128,128) as 2 row halves;  wb: per head, last Linear zero-padded to 16 rows
+      w0_t: W0^T rows [0,64) then [64,K0);  wa_t: per head Wa^T in two 64-row halves;
+      wb_t: per head (Wb padded to 16 outputs)^T in two 64-row halves (K = 16)
+      heads: [(Wa[128,128], ba[128], Wb[n,128], bb[n])] * 3 in pos / scales / rotations order."""
 
-def pack_weights(w0, b0, heads):
-    """heads: [(Wa[128,128], ba[128], Wb[n,128], bb[n])] * 3 in pos/scales/rotations order."""
-    dev = w0.device
-    w0_t = torch.cat([_tile(w0[h * 64:(h + 1) * 64].float()) for h in range(2)])
-    wa_t = torch.cat([_tile(Wa[h * 64:(h + 1) * 64].float()) for Wa, _, _, _ in heads for h in range(2)])
-    wb_list, bb_list = [], []
-    for _, _, Wb, bb in heads:
-        pad = torch.zeros(16, NET_WIDTH, device=dev)
-        pad[:Wb.shape[0]] = Wb.float()
-        wb_list.append(_tile(pad))
-        pb = torch.zeros(16, device=dev)
-        pb[:bb.shape[0]] = bb.float()
-        bb_list.append(pb)
-    ba = torch.stack([ba.float() for _, ba, _, _ in heads]).contiguous()
-    return (w0_t.contiguous(), b0.float().contiguous(), wa_t.contiguous(), ba,
-            torch.cat(wb_list).contiguous(), torch.cat(bb_list).contiguous())
+    def __init__(self, planes, w0, b0, heads):
+        W = NET_WIDTH
+        dev = w0.device
+        levels = len(planes)
+        K0 = PLANE_FEATURES * levels
+        self.flat = [p for level in planes for p in level] + [w0, b0] + [t for h in heads for t in h]
+        for t in self.flat:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise NotImplementedError("deformation parameters must be contiguous fp32 CUDA tensors")
+        self.ptrs = [t.data_ptr() for t in self.flat]
+        self.shapes = [tuple(t.shape) for t in self.flat]
+        self.versions = None
+        e = lambda n: torch.empty(n, device=dev)  # noqa: E731
+        self.w0, self.b0, self.wa, self.ba = e(2 * 2 * 64 * K0), e(W), e(3 * 2 * 2 * 64 * W), e(3 * W).view(3, W)
+        self.wb, self.bb = e(3 * 2 * 16 * W), e(3 * 16)
+        self.w0_t, self.wa_t, self.wb_t = e(2 * K0 * W), e(3 * 2 * 2 * 64 * W), e(3 * 2 * 2 * 64 * 16)
+        self.cl = []
+        jobs = []
 
+        def job(kind, src, src_off, rs, cs, rows, cols, dst, dst_off, vr=None, vc=None):
+            jobs.append((kind, src.data_ptr() + 4 * src_off, rs, cs, rows, cols, rows if vr is None else vr,
+                         cols if vc is None else vc, dst.data_ptr() + 4 * dst_off))
 
-def pack_weights_t(w0, heads):
-    """Transposed weights for the data-gradient GEMMs of mobgs_hexplane_mlp_bwd, tiled like the forward's:
-    W0^T rows [0,64) then [64,K0); per head Wa^T in two 64-row halves; per head (Wb padded to 16 outputs)^T in
-    two 64-row halves (K = 16)."""
-    dev = w0.device
-    w0t = w0.float().t().contiguous()                          # [K0, 128]
-    K0 = w0t.shape[0]
-    parts = [_tile(w0t[:min(64, K0)])]
-    if K0 > 64:
-        parts.append(_tile(w0t[64:]))
-    wa_t = torch.cat([_tile(Wa.float().t().contiguous()[h * 64:(h + 1) * 64]) for Wa, _, _, _ in heads for h in range(2)])
-    wb_parts = []
-    for _, _, Wb, _ in heads:
-        pad = torch.zeros(16, NET_WIDTH, device=dev)
-        pad[:Wb.shape[0]] = Wb.float()
-        padt = pad.t().contiguous()                            # [128, 16]
-        wb_parts += [_tile(padt[h * 64:(h + 1) * 64]) for h in range(2)]
-    return torch.cat(parts).contiguous(), wa_t.contiguous(), torch.cat(wb_parts).contiguous()
+        for grids in planes:
+            assert len(grids) == 6
+            for g in grids:
+                if g.shape[0] != 1 or g.shape[1] != PLANE_FEATURES:
+                    raise NotImplementedError(f"plane shape {tuple(g.shape)} not covered")
+                H, Wd = g.shape[2], g.shape[3]
+                cl = torch.empty(H, Wd, PLANE_FEATURES, device=dev)               # channels-last [H,W,32]
+                self.cl.append(cl)
+                job(L.PACK_TRANSPOSE, g, 0, H * Wd, 1, PLANE_FEATURES, H * Wd, cl, 0)
+        for h in range(2):
+            job(L.PACK_TILED, w0, h * 64 * K0, K0, 1, 64, K0, self.w0, h * 2 * 64 * K0)
+        job(L.PACK_PLAIN, b0, 0, W, 1, 1, W, self.b0, 0)
+        r0 = min(64, K0)
+        job(L.PACK_TILED, w0, 0, 1, K0, r0, W, self.w0_t, 0)                        # W0^T rows [0, 64)
+        if K0 > 64:
+            job(L.PACK_TILED, w0, 64, 1, K0, K0 - 64, W, self.w0_t, 2 * r0 * W)       # W0^T rows [64, K0)
+        for i, (Wa, ba, Wb, bb) in enumerate(heads):
+            n_out = Wb.shape[0]
+            if tuple(Wa.shape) != (W, W) or Wb.shape[1] != W or n_out > 16:
+                raise NotImplementedError(f"head {i}: Linear shapes {tuple(Wa.shape)}, {tuple(Wb.shape)} not covered")
+            for h in range(2):
+                job(L.PACK_TILED, Wa, h * 64 * W, W, 1, 64, W, self.wa, (i * 2 + h) * 2 * 64 * W)
+                job(L.PACK_TILED, Wa, h * 64, 1, W, 64, W, self.wa_t, (i * 2 + h) * 2 * 64 * W)       # Wa^T half
+                job(L.PACK_TILED, Wb, h * 64, 1, W, 64, 16, self.wb_t, (i * 2 + h) * 2 * 64 * 16, vc=n_out)
+            job(L.PACK_TILED, Wb, 0, W, 1, 16, W, self.wb, i * 2 * 16 * W, vr=n_out)
+            job(L.PACK_PLAIN, ba, 0, W, 1, 1, W, self.ba, i * W)
+            job(L.PACK_PLAIN, bb, 0, 16, 1, 1, 16, self.bb, i * 16, vc=n_out)
+        if len(jobs) > L.PACK_MAX_JOBS:
+            raise NotImplementedError(f"{len(jobs)} packing jobs exceed MOBGS_PACK_MAX_JOBS")
+        chunk = L.load().mobgs_pack_chunk_elems()
+        table = (L.PackJob * len(jobs))()
+        begin, tot = [], 0
+        for t, (kind, src, rs, cs, rows, cols, vr, vc, dst) in zip(table, jobs):
+            t.src, t.row_stride, t.col_stride, t.rows, t.cols = src, rs, cs, rows, cols
+            t.valid_rows, t.valid_cols, t.dst, t.kind = vr, vc, dst, kind
+            begin.append(tot)
+            tot += (rows * cols + chunk - 1) // chunk
+        begin.append(tot)
+        self.jobs_dev = torch.frombuffer(bytearray(bytes(table)), dtype=torch.uint8).to(dev)
+        self.begin_dev = torch.tensor(begin, dtype=torch.int32).to(dev)
+        self.args = L.PackOperands(len(jobs), tot, self.jobs_dev.data_ptr(), self.begin_dev.data_ptr())
+
+    def matches(self, flat):
+        # same storage = same address while the plan keeps the original tensor objects (hence their storage) alive:
+        # autograd hands the backward fresh Python objects for the saved parameters, so identity is not required
+        return (len(flat) == len(self.flat)
+                and all(t.data_ptr() == p and tuple(t.shape) == s for t, p, s in zip(flat, self.ptrs, self.shapes))
+                and all(t.data_ptr() == p for t, p in zip(self.flat, self.ptrs)))
+
+    def refresh(self):
+        """repack if any parameter changed since the last launch (autograd version counters; FusedAdam bumps them)"""
+        versions = [t._version for t in self.flat]
+        if versions != self.versions:
+            L.call("mobgs_pack_operands", self.args, _stream())
+            self.versions = versions
+        return self
+
+    @property
+    def packed(self):
+        return self.w0, self.b0, self.wa, self.ba, self.wb, self.bb
+
+    @property
+    def packed_t(self):
+        return self.w0_t, self.wa_t, self.wb_t
 
 
 class _FusedDeform(torch.autograd.Function):
@@ -119,13 +174,12 @@ class _FusedDeform(torch.autograd.Function):
         for i in range(6):
             a.aabb[i] = ab[i]
         a.levels, a.net_width, a.plane_features = nl, W, PLANE_FEATURES
-        cl, packed = _packed_operands(planes, w0, b0, heads)
-        for i, t in enumerate(cl):
+        pack = _operand_pack(planes, w0, b0, heads)
+        for i, t in enumerate(pack.cl):
             a.planes[i] = t.data_ptr()
             a.plane_h[i], a.plane_w[i] = t.shape[0], t.shape[1]
-        a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in packed)
-        packed_t = _packed_transposed(w0, heads)
-        a.w0_t, a.wa_t, a.wb_t = (_p(t) for t in packed_t)
+        a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in pack.packed)
+        a.w0_t, a.wa_t, a.wb_t = (_p(t) for t in pack.packed_t)
         gs = [None if g is None else _f32c(g) for g in (g_pts, g_scales, g_rots)]
         a.g_out_pts, a.g_out_scales, a.g_out_rots = (_p(g) for g in gs)
         g_p_direct = torch.empty(N, 3, device=dev)
@@ -229,9 +283,8 @@ def fused_forward_raw(pts, scales, rots, times, aabb, planes: Sequence[Sequence[
     return _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads)
 
 
-# Packed operands (tiled hi/lo weights, channels-last planes) are rebuilt only when a parameter
-# changed (tensor identity + autograd version counter), i.e. once per optimiser step in training
-# and never during inference.
+# Packed operands (tiled hi/lo weights, channels-last planes) are refreshed only when a parameter changed (autograd
+# version counter), i.e. once per optimiser step in training and never during inference — by one launch (_OperandPack).
 _PACK_CACHE = {}
 
 
@@ -245,37 +298,17 @@ def _aabb_host(aabb):
     return vals
 
 
-def _packed_operands(planes, w0, b0, heads):
+def _operand_pack(planes, w0, b0, heads) -> _OperandPack:
+    """the packing plan of these parameter tensors, refreshed.  Identity is checked on addresses while the plan keeps
+    the tensor OBJECTS alive (an address can be recycled by the allocator; one whose owner is still referenced
+    cannot), staleness on the autograd version counters, which FusedAdam bumps after its raw-pointer update
+    (optim._launch)."""
     flat = [p for level in planes for p in level] + [w0, b0] + [t for h in heads for t in h]
-    # identity is checked on the tensor OBJECTS the cache keeps alive (an address can be recycled by the
-    # allocator; an object that is still referenced cannot), plus the autograd version counter, which
-    # FusedAdam bumps after its raw-pointer update (optim._launch)
-    key = [(t, t._version) for t in flat]
-    hit = _PACK_CACHE.get("last")
-    if hit is not None and len(hit[0]) == len(key) and all(a is b and va == vb for (a, va), (b, vb) in zip(hit[0], key)):
-        return hit[1], hit[2]
-    cl = []
-    for grids in planes:
-        assert len(grids) == 6
-        for g in grids:
-            if g.shape[0] != 1 or g.shape[1] != PLANE_FEATURES:
-                raise NotImplementedError(f"plane shape {tuple(g.shape)} not covered")
-            cl.append(g.detach()[0].permute(1, 2, 0).contiguous().float())     # channels-last [H,W,32]
-    packed = pack_weights(w0.detach(), b0.detach(), [tuple(t.detach() for t in h) for h in heads])
-    _PACK_CACHE["last"] = (key, cl, packed)
-    return cl, packed
-
-
-def _packed_transposed(w0, heads):
-    """cached like _packed_operands (tensor objects + version counters)"""
-    flat = [w0] + [t for h in heads for t in (h[0], h[2])]
-    key = [(t, t._version) for t in flat]
-    hit = _PACK_CACHE.get("last_t")
-    if hit is not None and len(hit[0]) == len(key) and all(a is b and va == vb for (a, va), (b, vb) in zip(hit[0], key)):
-        return hit[1]
-    packed = pack_weights_t(w0.detach(), [tuple(t.detach() for t in h) for h in heads])
-    _PACK_CACHE["last_t"] = (key, packed)
-    return packed
+    plan = _PACK_CACHE.get("plan")
+    if plan is None or not plan.matches(flat):
+        plan = _OperandPack(planes, w0, b0, heads)
+        _PACK_CACHE["plan"] = plan
+    return plan.refresh()
 
 
 def _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads):
@@ -292,11 +325,11 @@ def _fused_forward_nograd(pts, scales, rots, times, aabb, planes, w0, b0, heads)
     for i in range(6):
         a.aabb[i] = ab[i]
     a.levels, a.net_width, a.plane_features = levels, NET_WIDTH, PLANE_FEATURES
-    cl, packed = _packed_operands(planes, w0, b0, heads)
-    for i, t in enumerate(cl):
+    pack = _operand_pack(planes, w0, b0, heads)
+    for i, t in enumerate(pack.cl):
         a.planes[i] = t.data_ptr()
         a.plane_h[i], a.plane_w[i] = t.shape[0], t.shape[1]
-    a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in packed)
+    a.w0, a.b0, a.wa, a.ba, a.wb, a.bb = (_p(t) for t in pack.packed)
     out_pts = torch.empty(N, 3, device=pts.device)
     out_scales = torch.empty(N, 3, device=pts.device)
     out_rots = torch.empty(N, 4, device=pts.device)

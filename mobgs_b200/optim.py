@@ -75,7 +75,7 @@ def _launch(items):
             a.chunk_begin[len(part)] = chunks
             _lib.call("mobgs_adam_step", a, stream)
     # The kernel wrote the parameters and the Adam moments through raw pointers: tell autograd (saved-tensor
-    # checks) and every version-keyed cache (deformation._packed_operands) that they changed, as an
+    # checks) and every version-keyed cache (deformation._operand_pack) that they changed, as an
     # in-place torch op would have.
     torch.autograd.graph.increment_version([t for it in items for t in it[0:1] + it[2:4]])
 

@@ -222,3 +222,80 @@ def test_tcgen05_backward_matches_oracle_autograd(n, base_res):
                 assert int(rows.sum()) <= 2, (k, float(err.max()), int(bad.sum()), int(rows.sum()))
             checked += 1
     assert checked >= 30
+
+
+# ---- the torch formulation of the operand layouts (what the kernels' headers specify), as the checker of the
+# ---- device-side packing launch (mobgs_pack_operands)
+def _tile_ref(w):
+    """[rows, K] row-major -> {hi, lo} x [K/4][rows][4]"""
+    rows, K = w.shape
+    hi = (w.contiguous().view(torch.int32) & -8192).view(torch.float32)     # keep the 10 mantissa bits of tf32
+    lo = w - hi
+    t = lambda m: m.reshape(rows, K // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)  # noqa: E731
+    return torch.cat([t(hi), t(lo)])
+
+
+def _pad16(m):
+    out = torch.zeros(16, *m.shape[1:], device=m.device)
+    out[:m.shape[0]] = m
+    return out
+
+
+@pytest.mark.parametrize("base_res,levels", [(16, 3), (32, 2), (8, 1)])
+def test_device_operand_pack_is_bit_exact(base_res, levels):
+    from mobgs_b200 import deformation as D
+    args = _hexplane_args(base_res)
+    args.multires = [1, 2, 4][:levels]
+    torch.manual_seed(base_res + levels)
+    net = D.HexPlaneMLP(args).cuda()
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.requires_grad:
+                p.copy_(torch.randn_like(p))
+    d = net.deformation_net
+    heads = [(s[1].weight, s[1].bias, s[3].weight, s[3].bias) for s in (d.pos_deform, d.scales_deform, d.rotations_deform)]
+    planes = [[p for p in level] for level in d.grid.grids]
+    w0, b0 = d.feature_out[0].weight, d.feature_out[0].bias
+    D._PACK_CACHE.clear()
+    pack = D._operand_pack(planes, w0, b0, heads)
+
+    def check():
+        K0 = w0.shape[1]
+        want = {"w0": torch.cat([_tile_ref(w0.detach()[h * 64:(h + 1) * 64]) for h in range(2)]),
+                "b0": b0.detach(),
+                "wa": torch.cat([_tile_ref(Wa.detach()[h * 64:(h + 1) * 64]) for Wa, _, _, _ in heads for h in range(2)]),
+                "ba": torch.stack([ba.detach() for _, ba, _, _ in heads]),
+                "wb": torch.cat([_tile_ref(_pad16(Wb.detach())) for _, _, Wb, _ in heads]),
+                "bb": torch.cat([_pad16(bb.detach()) for _, _, _, bb in heads])}
+        w0t = w0.detach().t().contiguous()
+        want["w0_t"] = torch.cat([_tile_ref(w0t[:min(64, K0)])] + ([_tile_ref(w0t[64:])] if K0 > 64 else []))
+        want["wa_t"] = torch.cat([_tile_ref(Wa.detach().t().contiguous()[h * 64:(h + 1) * 64])
+                                  for Wa, _, _, _ in heads for h in range(2)])
+        want["wb_t"] = torch.cat([_tile_ref(_pad16(Wb.detach()).t().contiguous()[h * 64:(h + 1) * 64])
+                                  for _, _, Wb, _ in heads for h in range(2)])
+        for name, w in want.items():
+            got = getattr(pack, name)
+            assert got.numel() == w.numel(), (name, got.shape, w.shape)
+            assert torch.equal(got.reshape(-1).view(torch.int32), w.reshape(-1).view(torch.int32)), name
+        flat = [p for level in planes for p in level]
+        assert len(pack.cl) == len(flat)
+        for cl, g in zip(pack.cl, flat):
+            assert torch.equal(cl, g.detach()[0].permute(1, 2, 0).contiguous())
+
+    check()
+    # a raw-pointer parameter update (FusedAdam) bumps the version counters: the next use repacks, same plan object
+    from mobgs_b200.optim import FusedAdam
+    params = [p for p in net.parameters() if p.requires_grad]
+    for p in params:
+        p.grad = torch.randn_like(p)
+    FusedAdam([{"params": params, "lr": 1e-2, "name": "deformation"}], lr=0.0, eps=1e-15).step()
+    assert D._operand_pack(planes, w0, b0, heads) is pack
+    check()
+    # replacing a parameter's storage invalidates the plan
+    with torch.no_grad():
+        d.feature_out[0].weight.data = d.feature_out[0].weight.data.clone()
+    pack2 = D._operand_pack(planes, d.feature_out[0].weight, b0, heads)
+    assert pack2 is not pack
+    pack = pack2
+    w0 = d.feature_out[0].weight
+    check()
