@@ -46,6 +46,7 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "c4_1M_1080p_K7"
 REFERENCE_CONFIG = "c1_1k_128_K1"            # BASELINE configs[0]: the one config both arms can run in full
+TRAINING_SHAPE = "sb_150k_512x288_K9"        # what the reference actually trains at (host-bound without a CUDA graph)
 METRIC = "rendered_Mpix_per_s_train_step"   # K*H*W / (fwd+loss+bwd time); ms_per_step = train-step ms
 HBM_PEAK_FALLBACK = 6650.0                  # GB/s, B200_PROFILING.md fallback
 CPU_WINDOW = 64                             # side of the window the CPU arm rasterises (tile aligned)
@@ -566,6 +567,17 @@ def run_ours(args):
             extra["full_step"] = measure_full_step(args, job, flush, local)
         except Exception as e:  # noqa: BLE001  (the headline must survive a failure of the extra measurement)
             extra["full_step"] = {"error": f"{type(e).__name__}: {e}"}
+        try:    # host path: the same step as one CUDA graph, here and at the reference's real (host-bound) training shape
+            _lib.TIMING = None
+            extra["cuda_graph"] = measure_graphed(args, job, flush, local, ms, e2e_ms)
+            torch.cuda.empty_cache()
+            jsb = GpuJob(TRAINING_SHAPE, dev, 0, 1, False)
+            sb_ms, _ = timed(lambda: jsb.step(True), flush, 30, 5, local, 1)
+            sb_e2e, _ = timed(lambda: jsb.step(False), flush, 30, 5, local, 1)
+            extra["cuda_graph"][TRAINING_SHAPE] = measure_graphed(args, jsb, flush, local, sb_ms, sb_e2e, steps=30)
+            del jsb
+        except Exception as e:  # noqa: BLE001
+            extra.setdefault("cuda_graph", {})["error"] = f"{type(e).__name__}: {e}"
 
     if overlap:
         from mobgs_b200.dist import overlap_gradient_allreduce
@@ -616,6 +628,47 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_graphed(args, job, flush, local, eager_ms, eager_e2e_ms, steps=None):
+    """The headline step (K-sub-frame render + decode + blur mean + L1 + full backward) captured into ONE CUDA graph
+    (mobgs_b200.graphs.GraphedStep) and replayed: resident inputs, and end to end (pinned host inputs copied into the
+    graph's static buffers, loss copied back to the pinned ring, inside the timed step).  Every replay is validated
+    (tile-list capacity) before the next one is enqueued, so the host waits once per step."""
+    import torch
+    from mobgs_b200.graphs import GraphedStep
+    from mobgs_b200.losses import l1_loss
+    from mobgs_b200.subframes import render_subframes
+    steps = steps or args.steps
+    W, H = job.W, job.H
+
+    def fn(view, tpoly, tgt):
+        rays = build_rays(view.detach(), job.intr, W, H)
+        out = render_subframes(job.stat, job.dyn, view, job.Kmat, tpoly.clamp(0, 1), tpoly, rays, job.bg, W, H)
+        loss = l1_loss(out["render"], tgt)
+        loss.backward()
+        return loss.detach()
+
+    view = job.view_d.clone().requires_grad_(True)
+    step = GraphedStep(fn, [view, job.tpoly_d, job.tgt_d], job.all_params)
+    ins_res = step.static_inputs
+    res_ms, _ = timed(lambda: step(*ins_res), flush, steps, 3, local, 1)
+    ring = job.loss_ring
+
+    def e2e():
+        loss = step(job.view_host, job.tpoly_host, job.tgt_host)          # pinned host -> the graph's static inputs
+        ring[0:1].copy_(loss.reshape(1), non_blocking=True)
+    e2e_ms, _ = timed(e2e, flush, steps, 3, local, 1)
+    step.validate()
+    torch.cuda.synchronize()
+    n, cap = step.intersection_counts()[0]
+    out = {"workload": job.workload, "ms_per_step": res_ms, "e2e_ms_per_step": e2e_ms, "eager_ms_per_step": eager_ms,
+           "eager_e2e_ms_per_step": eager_e2e_ms, "replays": step.replays, "captures": step.captures,
+           "overflows": step.overflows, "intersections": n, "list_capacity": cap, "loss_on_host": float(ring[0]),
+           "note": "one cudaGraphLaunch per step; the host validates each replay (intersection count vs the capacity baked "
+                   "into the graph) before enqueueing the next"}
+    del step
+    return out
 
 
 def measure_strong_scaling(args, dev, rank, world, flush, local, workload="c4_1M_1080p_K9", views=2):

@@ -19,6 +19,7 @@ import weakref
 import torch
 
 from . import _lib as L
+from . import ops as _ops
 from .ops import _cams, _f32c, _p, _stream, build_tile_lists, EPS2D, NEAR, FAR, RADIUS_CLIP
 
 class GradSink:
@@ -60,6 +61,18 @@ RECYCLE_GRAD_RECORDS = os.environ.get("MOBGS_RECYCLE_GRAD_RECORDS", "1") != "0"
 def _take_grad_records(Kr, N, dev):
     """an all-zero [Kr,N,16] gradient-record buffer (recycled when possible)"""
     key = (int(Kr), int(N), dev.index)
+    cap = _ops.CAPTURE
+    if cap is not None and RECYCLE_GRAD_RECORDS:
+        # A CUDA graph owns its gradient-record buffers: an all-zero pool buffer (allocated before the capture) when
+        # there is one, else zeros from the graph's own memory (re-zeroed by a captured memset on every replay).  Either
+        # way the projection backward zeroes it behind its reads, so every replay starts from zeros; it is never
+        # returned to the shared pool (_recycle).
+        t = _GRAD_REC_POOL.pop(key, None)
+        if t is None:
+            t = torch.zeros(Kr, N, L.REC, device=dev)
+        _GRAD_REC_OUT[t.data_ptr()] = (key, weakref.ref(t))
+        cap.keep.append(t)
+        return t
     t = _GRAD_REC_POOL.pop(key, None) if RECYCLE_GRAD_RECORDS else None
     if t is not None:
         _GRAD_REC_USES[key] = _GRAD_REC_USES.get(key, 0) + 1
@@ -87,7 +100,8 @@ def _recyclable(g_rec) -> bool:
 
 def _recycle(g_rec):
     key, _ = _GRAD_REC_OUT.pop(g_rec.data_ptr())
-    _GRAD_REC_POOL[key] = g_rec
+    if _ops.CAPTURE is None:              # (a buffer baked into a CUDA graph stays the graph's)
+        _GRAD_REC_POOL[key] = g_rec
 
 
 # argument tails of L.BlendFwd / L.BlendBwd for launches without the fused decoder, up to (not including) list_masks

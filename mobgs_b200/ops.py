@@ -126,6 +126,13 @@ SPECULATIVE_LISTS = os.environ.get("MOBGS_SPECULATIVE_LISTS", "1") != "0"
 RECORD_ENTRIES = os.environ.get("MOBGS_RECORD_ENTRIES", "1") != "0"
 
 
+# Set by mobgs_b200.graphs.GraphedStep while it captures a CUDA graph (a graphs._Capture): the tile lists are then sized
+# from the capacity guess only, the intersection count travels to a pre-allocated pinned word by a captured copy, and the
+# "did the lists fit" check — the one host synchronisation of the eager path — moves behind the replay
+# (GraphedStep.validate), which redoes an overflowed step eagerly and re-captures.
+CAPTURE = None
+
+
 class BinPlan:
     """Counting pass fused into the projection (MobgsSynthFwd.bin_tile_counts): created by the caller that knows which
     lists the blend will walk BEFORE it projects, handed to `fused.synth_project(..., binning=plan)` — which lets the
@@ -210,6 +217,9 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
     key = (K, N, width, height, tuple(bin_specs), bool(tight), dev.index)
     guess = _CAP_CACHE.get(key)
     speculative = consume is not None and guess is not None and SPECULATIVE_LISTS
+    if CAPTURE is not None and not speculative:
+        raise RuntimeError("CUDA-graph capture needs the speculative list path: run the step eagerly once for this launch "
+                           "shape (capacity guess) and give build_tile_lists a `consume` callable")
     # Speculative calls also let the counting pass RECORD the intersections it finds (MobgsTileCount.entries), which turns
     # the emit pass into a streaming scatter; the exact-size (first / overflow) calls use the two-pass kernels.
     entries = cursor = None
@@ -245,6 +255,16 @@ def build_tile_lists(records, radii, depths, width, height, tight=True, specs=No
         tl.n_isect = n_isect
         _CAP_CACHE[key] = int(n_isect * 1.25) + 4096
         return tl if consume is None else (tl, consume(tl))
+    if CAPTURE is not None:
+        # being captured: no event, no host wait — the count lands in the capture's pinned word on every replay and
+        # GraphedStep.validate() compares it with the capacity baked into the graph
+        host_n = CAPTURE.pinned_word()
+        host_n.copy_(offsets[-1:], non_blocking=True)
+        tl = emit_sort(guess, use_entries=entries is not None)
+        out = consume(tl)
+        CAPTURE.checks.append((host_n, tl.capacity, key))
+        tl.n_isect = None
+        return tl, out
     host_n = torch.empty(1, dtype=torch.int32, pin_memory=True)
     host_n.copy_(offsets[-1:], non_blocking=True)
     ev = torch.cuda.Event()
