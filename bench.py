@@ -649,6 +649,9 @@ def measure_graphed(args, job, flush, local, eager_ms, eager_e2e_ms, steps=None)
         loss.backward()
         return loss.detach()
 
+    job.stats.pop("out", None)          # (the last eager step's autograd graph: its AccumulateGrad nodes would break the capture)
+    for p in job.all_params:
+        p.grad = None
     view = job.view_d.clone().requires_grad_(True)
     step = GraphedStep(fn, [view, job.tpoly_d, job.tgt_d], job.all_params)
     ins_res = step.static_inputs
@@ -656,7 +659,16 @@ def measure_graphed(args, job, flush, local, eager_ms, eager_e2e_ms, steps=None)
     ring = job.loss_ring
 
     def e2e():
-        loss = step(job.view_host, job.tpoly_host, job.tgt_host)          # pinned host -> the graph's static inputs
+        # as job.step(False): this step's pinned host inputs were copied on the side stream while the previous step ran
+        # (one H2D of the step's inputs per step); they reach the graph's static buffers by device copies
+        if "next" not in job.pending:
+            job.prefetch()
+        (v, tp, tg), ev = job.pending.pop("next")
+        torch.cuda.current_stream().wait_event(ev)
+        for t in (v, tp, tg):
+            t.record_stream(torch.cuda.current_stream())
+        loss = step(v, tp, tg)
+        job.prefetch()
         ring[0:1].copy_(loss.reshape(1), non_blocking=True)
     e2e_ms, _ = timed(e2e, flush, steps, 3, local, 1)
     step.validate()

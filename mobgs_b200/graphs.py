@@ -27,6 +27,7 @@ read tensors back to the host and must produce gradients only in `params`' .grad
 """
 from __future__ import annotations
 
+import gc
 from typing import Callable, Sequence
 
 import torch
@@ -67,6 +68,7 @@ class GraphedStep:
         self.replays = self.overflows = self.captures = 0
         self._pending = False
         self._graph = None
+        self._stream = None
         self._capture(first=True)
 
     # ------------------------------------------------------------------------------------------
@@ -84,20 +86,30 @@ class GraphedStep:
     def _capture(self, first: bool):
         if L.TIMING is not None:
             raise RuntimeError("per-call device timing (_lib.TIMING) records events and cannot run under capture")
+        # Warm-up and capture run on ONE side stream: autograd gives every leaf's AccumulateGrad node the stream it was
+        # created on, and a node created on another stream would make the engine synchronise the capturing stream with
+        # it, which invalidates the capture.  (The same happens when the caller still holds an autograd graph of an
+        # earlier eager step over these parameters — drop such references before constructing a GraphedStep.)
+        if self._stream is None:
+            self._stream = torch.cuda.Stream()
+        self._stream.wait_stream(torch.cuda.current_stream())
         if first:
             # eager runs settle the capacity guesses of every launch shape in the step (and the gradient-record pool)
-            for _ in range(self.warmup):
-                self._eager()
+            with torch.cuda.stream(self._stream):
+                for _ in range(self.warmup):
+                    self._eager()
         torch.cuda.synchronize()
         self._zero_grads()
+        gc.collect()
         cap = _Capture()
         graph = torch.cuda.CUDAGraph()
         ops.CAPTURE = cap
         try:
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph, stream=self._stream):
                 out = self.fn(*self.static_inputs)
         finally:
             ops.CAPTURE = None
+        torch.cuda.current_stream().wait_stream(self._stream)
         self._graph, self._cap = graph, cap
         self._single = torch.is_tensor(out)
         self.static_outputs = [out] if self._single else list(out)
@@ -149,11 +161,14 @@ class GraphedStep:
         self.overflows += 1
         for n, _c, key in over:
             ops._CAP_CACHE[key] = int(n * 1.25) + 4096
-        out = self._eager()                   # exact: the eager path redoes its own overflows
-        outs = [out] if torch.is_tensor(out) else list(out)
-        exact_out = [o.detach().clone() for o in outs]
-        exact_g = [None if p.grad is None else p.grad.detach().clone() for p in self.params]
-        exact_ig = [None if t.grad is None else t.grad.detach().clone() for t in self.static_inputs]
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream):      # (the stream of the capture: see _capture)
+            out = self._eager()               # exact: the eager path redoes its own overflows
+            outs = [out] if torch.is_tensor(out) else list(out)
+            exact_out = [o.detach().clone() for o in outs]
+            exact_g = [None if p.grad is None else p.grad.detach().clone() for p in self.params]
+            exact_ig = [None if t.grad is None else t.grad.detach().clone() for t in self.static_inputs]
+        del out, outs
         self._capture(first=False)
         with torch.no_grad():
             for dst, src in zip(self.static_outputs, exact_out):
@@ -161,4 +176,5 @@ class GraphedStep:
             for dst, src in zip(self.static_grads + self.static_input_grads, exact_g + exact_ig):
                 if dst is not None and src is not None:
                     dst.copy_(src)
+        torch.cuda.current_stream().synchronize()      # the side-stream temporaries are released only after their last use
         return False
