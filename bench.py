@@ -462,12 +462,17 @@ def run_ours(args):
         raise SystemExit("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    shard_sub = args.shard == "subframes" and world > 1
+    # gradient all-reduce overlapped with the second half of the projection backward: on by default at N > 1 (measured
+    # at N = 2: 5.879 -> 5.815 ms WITH high-priority collective streams, 5.926 ms without them — the collective's CTAs
+    # must win SM slots against the queued projection CTAs)
+    overlap = world > 1 and not shard_sub and (args.overlap or not args.no_overlap)
+    if overlap:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")      # read when the process group creates its streams
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    shard_sub = args.shard == "subframes" and world > 1
-    overlap = world > 1 and not shard_sub and args.overlap
     symmetric = None
     # measured (profiles/r2_allreduce_n*.json): 116 MB multimem all-reduce 0.285 ms vs NCCL 0.36 ms on 8 GPUs, but 1.03 ms vs
     # 0.245 ms on 2 — the in-switch reduction only pays with many peers, so it is used from 8 ranks up
@@ -899,8 +904,9 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra keys of the N=1 line (gpu_on_reference_config, full_step)")
     ap.add_argument("--overlap", action="store_true",
-                    help="N>1: chunked projection backward with the gradient all-reduce on a side stream (measured slower "
-                         "than one all-reduce at N = 8: NCCL's kernels compete with the backward for SMs; off by default)")
+                    help="N>1: projection backward in Gaussian ranges with each range's gradient all-reduce on a "
+                         "high-priority side stream (the default at N > 1)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one all-reduce after the whole backward")
     ap.add_argument("--no-symmetric", action="store_true", help="N>1: NCCL all-reduce instead of the NVLS multimem one")
     ap.add_argument("--overlap-chunks", type=int, default=2)
     ap.add_argument("--shard", default="views", choices=["views", "subframes"],

@@ -250,7 +250,8 @@ def overlap_gradient_allreduce(enable: bool = True, n_chunks: int = 2, group=Non
             return None
         return dist.all_reduce(t, group=group, async_op=True)
 
-    fused.GRAD_SINK = fused.GradSink(reduce, torch.cuda.Stream(), n_chunks)
+    # high priority: the collective's CTAs must get SM slots while the next range's projection kernel still has CTAs queued
+    fused.GRAD_SINK = fused.GradSink(reduce, torch.cuda.Stream(priority=-1), n_chunks)
     return fused.GRAD_SINK
 
 
