@@ -625,8 +625,11 @@ def run_ours(args):
         line.update(extra)
         if world > 1:
             line["allreduce_bytes_per_step"] = job.stats.get("allreduce_bytes")
-            line["gradient_allreduce"] = (f"overlapped: projection backward in {args.overlap_chunks} Gaussian ranges, NCCL "
-                                          "all-reduce of each range on a side stream" if overlap else
+            line["gradient_allreduce"] = (f"overlapped: projection backward in {args.overlap_chunks} Gaussian ranges, each "
+                                          "range's slice of the flat gradient buffer all-reduced on a high-priority side "
+                                          "stream while the next range's kernel runs ("
+                                          + ("multimem / NVLS symmetric memory" if symmetric is not None else "NCCL") + ")"
+                                          if overlap else
                                           ("one in-place multimem (NVLS symmetric-memory) all-reduce of the flat gradient "
                                            "buffer after the backward" if symmetric is not None else
                                            "one in-place NCCL all-reduce of the flat gradient buffer after the backward"))

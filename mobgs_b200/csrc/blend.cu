@@ -47,6 +47,11 @@ constexpr int kBlendThreads = kTilePix;   // 256
 #ifndef MOBGS_BWD_MIN_CTAS
 #define MOBGS_BWD_MIN_CTAS 4
 #endif
+// 1: decoder weight gradients of the backward prologue as 2 x 2 register blocks joined by shuffles (see
+// bwd_pixel_prologue); 0: one output per thread + shared-memory atomics (ablation)
+#ifndef MOBGS_BWD_WGRAD_BLOCKED
+#define MOBGS_BWD_WGRAD_BLOCKED 1
+#endif
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -405,7 +410,8 @@ constexpr int kProPad = kBlendThreads + 4;
 template <int D, bool DEC, bool POSE = false>
 __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k, int tid, bool inside, int ix, int iy,
                                                    float* sx, float* sg, float* sdec, float* swg,
-                                                   float& T_final, int& last, float (&v_c)[D], float& v_a) {
+                                                   float& T_final, int& last, float (&v_c)[D], float& v_a,
+                                                   float* spose = nullptr) {   // [8 warps][12] scratch (POSE)
   T_final = 1.f; v_a = 0.f; last = -1;
 #pragma unroll
   for (int c = 0; c < D; ++c) v_c[c] = 0.f;
@@ -523,13 +529,14 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
     if (POSE && want_pose) {
       // pose gradient (what mobgs_camera_rays_bwd reduces from a [.,6,H,W] image): 12 sums over the tile's pixels,
       // warp shuffles -> CTA accumulator swg[96..107] -> one atomicAdd per CTA and value (after the barrier below)
-      float v12[12];
+      // (transposing butterfly: 16 shuffles per warp instead of 60, the 12 sums land in 12 different lanes and are parked
+      // per warp without atomics; 12 threads join the 8 warps after the barrier below)
+      float v12[12], v16[16];
       pixel_ray_vjp<true>(sdec + (POSE ? 96 : 0), rin, ix, iy, gray, v12);
 #pragma unroll
-      for (int i = 0; i < 12; ++i) {
-        const float sum = warp_sum(v12[i]);
-        if ((tid & 31) == 0 && sum != 0.f) atomicAdd(&swg[(POSE ? 96 : 0) + i], sum);
-      }
+      for (int i = 0; i < 16; ++i) v16[i] = i < 12 ? v12[i % 12] : 0.f;
+      const int vidx = warp_transpose_sum16(v16, tid & 31);
+      if ((tid & 1) == 0 && vidx < 12) spose[(tid >> 5) * 12 + vidx] = v16[0];
     }
     if (inside) {
       const size_t p = (size_t)k * P + pp;
@@ -539,6 +546,62 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
       v_a = (a.g_alpha ? __ldg(a.g_alpha + p) : 0.f) + (al > kEdFloor ? -gd * depth_acc / (den * den) : 0.f);
     }
     __syncthreads();
+    if (POSE && want_pose && tid >= 96 && tid < 108) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kBlendThreads / 32; ++w) sum += spose[w * 12 + (tid - 96)];
+      swg[tid] = sum;
+    }
+#if MOBGS_BWD_WGRAD_BLOCKED
+    // The 90 weight-gradient sums over the tile's 256 pixels as 24 register blocks of 2 x 2 outputs (two factor rows a,
+    // two factor rows b: 4 LDS.128 feed 16 multiply-adds, where one output per thread needed 8), each block summed by
+    // the 8 lanes of a quarter-warp over interleaved pixel quads — the 8 lanes read 128 contiguous bytes of a row, one
+    // conflict-free wavefront — then joined by three shuffle stages and STORED by one lane: every output has exactly one
+    // owner, so the shared-memory atomics (CAS loops) of the one-output-per-thread form are gone too.
+    if (tid < 192) {
+      const int b = tid >> 3, s = tid & 7;
+      const float *fa0, *fa1, *fb0, *fb1;
+      int o0, o1;
+      if (b < 18) {                       // v_w1[j][i] = sum ghpre_j x_i: rows j = 2 jp, 2 jp + 1; columns i = 2 ip, 2 ip + 1
+        const int jp = b / 6, ip = b - 6 * jp;
+        fa0 = sg + (2 * jp) * kPad; fa1 = fa0 + kPad;
+        fb0 = sx + (2 * ip) * kPad; fb1 = fb0 + kPad;
+        o0 = (2 * jp) * 12 + 2 * ip; o1 = o0 + 12;
+      } else if (b < 21) {                // v_w2[c][h] = sum gpre_c relu(h)_h: c = 0, 1
+        const int hp = b - 18;
+        fa0 = sg + 6 * kPad; fa1 = fa0 + kPad;
+        fb0 = sg + (9 + 2 * hp) * kPad; fb1 = fb0 + kPad;
+        o0 = 72 + 2 * hp; o1 = o0 + 6;
+      } else {                            // c = 2 (second row of the block unused)
+        const int hp = b - 21;
+        fa0 = fa1 = sg + 8 * kPad;
+        fb0 = sg + (9 + 2 * hp) * kPad; fb1 = fb0 + kPad;
+        o0 = 84 + 2 * hp; o1 = -1;
+      }
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+#pragma unroll 2
+      for (int it = 0; it < kBlendThreads / 32; ++it) {
+        const int p = (it * 8 + s) * 4;
+        const float4 x0 = *reinterpret_cast<const float4*>(fa0 + p), x1 = *reinterpret_cast<const float4*>(fa1 + p);
+        const float4 y0 = *reinterpret_cast<const float4*>(fb0 + p), y1 = *reinterpret_cast<const float4*>(fb1 + p);
+        a00 += x0.x * y0.x + x0.y * y0.y + x0.z * y0.z + x0.w * y0.w;
+        a01 += x0.x * y1.x + x0.y * y1.y + x0.z * y1.z + x0.w * y1.w;
+        a10 += x1.x * y0.x + x1.y * y0.y + x1.z * y0.z + x1.w * y0.w;
+        a11 += x1.x * y1.x + x1.y * y1.y + x1.z * y1.z + x1.w * y1.w;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        a00 += __shfl_xor_sync(0xffffffffu, a00, o);
+        a01 += __shfl_xor_sync(0xffffffffu, a01, o);
+        a10 += __shfl_xor_sync(0xffffffffu, a10, o);
+        a11 += __shfl_xor_sync(0xffffffffu, a11, o);
+      }
+      if (s == 0) {
+        swg[o0] = a00; swg[o0 + 1] = a01;
+        if (o1 >= 0) { swg[o1] = a10; swg[o1 + 1] = a11; }
+      }
+    }
+#else
     if (tid < 180) {
       const int o = tid % 90, p0 = (tid / 90) * (kBlendThreads / 2);
       const float* fa = o < 72 ? sg + (o / 12) * kPad : sg + (6 + (o - 72) / 6) * kPad;
@@ -551,6 +614,7 @@ __device__ __forceinline__ void bwd_pixel_prologue(const MobgsBlendBwd& a, int k
       }
       if (acc != 0.f) atomicAdd(&swg[o], acc);
     }
+#endif
   }
 }
 
@@ -835,7 +899,7 @@ constexpr int kVWarp = 2 * kVUnit;             //   groups of a warp read four d
 constexpr int kAccRow = 17;                    // accumulator row stride: row t starts at bank 17 t
 constexpr int kAccFloats = MOBGS_BWD_DIRECT_RED ? 0 : kBwdBatch * kAccRow;
 constexpr int kTrScratch = (kBwdBatch + 1) * kRecRow + kAccFloats + 8 * 2 * kBlk * kFRow;   // floats
-static_assert(kTrScratch >= 27 * kProPad, "prologue scratch must fit the aliased buffers");
+static_assert(kTrScratch >= 27 * kProPad + 96, "prologue scratch (+ the pose partials) must fit the aliased buffers");
 constexpr size_t kTrSmemBytes = (size_t)(kTrScratch + 8 * kVWarp + 112 + 112) * 4 + kBwdBatch * 8 + 16 * kListRow + 8 * 4 + 16;
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
@@ -922,7 +986,7 @@ __global__ void __launch_bounds__(kBlendThreads, MOBGS_BWD_MIN_CTAS) blend_bwd_t
   float v_c[D];
   int last;
   bwd_pixel_prologue<D, DEC, POSE>(a, k, tid, inside, ix, iy, smem, smem + 12 * kProPad, sdec, swg,
-                             T_final, last, v_c, v_a);
+                             T_final, last, v_c, v_a, smem + 27 * kProPad);
   float v_fl0 = 0.f, v_fl1 = 0.f;
   if (FLOW && inside) {
     const float2 gf = __ldg(reinterpret_cast<const float2*>(a.g_flow + (((size_t)k * a.height + iy) * a.width + ix) * 2));

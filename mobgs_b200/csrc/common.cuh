@@ -50,6 +50,28 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum of 16 per-lane values over the warp with a transposing butterfly: every stage halves the values a lane holds while
+// doubling the lanes summed — 16 shuffles instead of 80.  Afterwards v[0] of every EVEN lane holds the complete warp sum
+// of value index `return` (lanes 2 i and 2 i + 1 hold the same one); each of the 16 values has exactly one even owner.
+__device__ __forceinline__ int warp_transpose_sum16(float (&v)[16], int lane) {
+  int vidx = 0;
+#pragma unroll
+  for (int o = 16, n = 8; o >= 2; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < n) {
+        const float send = up ? v[i] : v[i + n];
+        const float keep = up ? v[i + n] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    vidx += up ? n : 0;
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return vidx;
+}
+
 // 16-byte vector reduction to global memory (sm_90+): one L2 atomic op for four floats.
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
