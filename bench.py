@@ -521,7 +521,7 @@ def run_ours(args):
     ach = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
     traffic = traffic_src = None
     try:    # dram bytes of one launch from the committed `ncu --set full` capture of this workload
-        for name in ("r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):      # newest capture first
+        for name in ("r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):      # newest capture first
             pth = os.path.join(ROOT, "profiles", name)
             if os.path.exists(pth):
                 with open(pth) as f:
