@@ -93,3 +93,27 @@ def test_gradient_record_pool_recycles_only_its_own_live_buffers():
     b = fused._take_grad_records(2, 10, dev)                         # pool empty: a fresh zero buffer
     assert b is not a
     fused._GRAD_REC_POOL.clear(); fused._GRAD_REC_OUT.clear()
+
+
+def test_graph_capture_bookkeeping_and_no_cpu_path():
+    """Host side of the CUDA-graphed step: build_tile_lists refuses to be captured without a capacity guess (the capture
+    must never fall back to the synchronising exact-size path), and GraphedStep / the new single-launch helpers refuse to
+    run without a CUDA device instead of routing around the library."""
+    from mobgs_b200 import graphs, main_utils, ops
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(RuntimeError):
+        graphs.GraphedStep(lambda x: x, [torch.zeros(1)])
+    with pytest.raises(RuntimeError):
+        main_utils.depth_normals(torch.ones(1, 4, 4), 2.0, 2.0, 3.0, 3.0)
+    assert ops.CAPTURE is None
+
+    class FakeCapture:
+        checks, keep = [], []
+    ops.CAPTURE = FakeCapture()
+    try:
+        rec = torch.zeros(1, 4, 16)
+        with pytest.raises(RuntimeError, match="capture"):
+            ops.build_tile_lists(rec, torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 4), 37, 29, consume=lambda l: None)
+    finally:
+        ops.CAPTURE = None
