@@ -520,14 +520,18 @@ def run_ours(args):
     dom_bytes = bytes_bwd if dom == "mobgs_blend_bwd" else bytes_fwd
     ach = dom_bytes / (kernel_ms[dom] * 1e-3) / 1e9
     traffic = traffic_src = None
+    pipes = {}
     try:    # dram bytes of one launch from the committed `ncu --set full` capture of this workload
         for name in ("r2c_traffic.json", "r2b_traffic.json", "r2_traffic.json", "r1_traffic.json"):      # newest capture first
             pth = os.path.join(ROOT, "profiles", name)
             if os.path.exists(pth):
                 with open(pth) as f:
-                    traffic = json.load(f).get(args.workload, {}).get(dom)
+                    tj = json.load(f)
+                traffic = tj.get(args.workload, {}).get(dom)
                 if traffic is not None:
                     traffic_src = "profiles/" + name
+                    pipes = {"issue_slot_utilisation": tj.get("issue_slot_utilisation", {}).get(dom),
+                             "lsu_pipe_utilisation": tj.get("lsu_pipe_utilisation", {}).get(dom)}
                     break
     except Exception:  # noqa: BLE001
         pass
@@ -536,6 +540,9 @@ def run_ours(args):
                 "ms_per_launch": kernel_ms[dom], "algorithmic_bytes": dom_bytes,
                 "intersections_consumed": ieff, "intersections_listed": itot,
                 "intersections_per_gaussian_subframe": itot / max(1, len(my_k) * N), "pixels": P_loc,
+                # what actually bounds the kernel (same ncu capture as `traffic`): fraction of the issue slots / of the LSU
+                # (shared-memory wavefront) pipe in use
+                **{k: v for k, v in pipes.items() if v is not None},
                 "note": "the blend kernels are bound by instruction issue and the shared-memory pipe, not by HBM "
                         "(ncu summaries under profiles/); the HBM fraction is reported because BASELINE.json's "
                         "north_star asks for it. algorithmic_bytes = 132*I_eff + 52*P (bwd) / 68*I_eff + 48*P (fwd)"}
